@@ -1,0 +1,217 @@
+/*
+ * pv_b200.h - C ABI of libpvb200.so, the B200 (sm_100a) forward-path engine for the
+ * PyTorchVideo hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + an explicit cudaStream_t (passed as
+ * void* so that the header needs no CUDA include), allocates nothing, never throws, and returns
+ * 0 on success or a negative pv_status.  pv_last_error() returns a thread-local message.
+ *
+ * Activations are "NDHWC" (channels-last-3d): element (n,t,h,w,c) of a tensor lives at
+ *   base + (((n*T + t)*H + h)*W + w) * row_stride + c
+ * where row_stride >= C is the distance (in elements) between consecutive positions; a tensor
+ * may therefore be a channel slice of a wider buffer (this is how torch.cat(dim=1) is fused
+ * away).  Channel counts of internal activations are padded to a multiple of 8 and the pad
+ * lanes are kept at exactly zero.
+ *
+ * Each function cites the reference call site(s) (facebookresearch/pytorchvideo @ f3142bb,
+ * paths relative to the reference root) whose arithmetic it replaces.
+ */
+#ifndef PV_B200_H_
+#define PV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_ABI_VERSION 1
+
+typedef enum pv_status {
+  PV_OK = 0,
+  PV_ERR_INVALID = -1,     /* bad argument / unsupported shape                       */
+  PV_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                    */
+  PV_ERR_UNSUPPORTED = -3, /* no kernel for this configuration (never falls back)    */
+  PV_ERR_NO_DEVICE = -4    /* no sm_100 device visible                               */
+} pv_status;
+
+typedef enum pv_dtype { PV_F16 = 0, PV_F32 = 1, PV_U8 = 2 } pv_dtype;
+
+typedef enum pv_act {
+  PV_ACT_NONE = 0,
+  PV_ACT_RELU = 1,
+  PV_ACT_SWISH = 2,   /* x*sigmoid(x)        reference layers/swish.py:25-28     */
+  PV_ACT_GELU = 3,    /* exact erf GELU      reference layers/attention.py:74   */
+  PV_ACT_SIGMOID = 4
+} pv_act;
+
+typedef enum pv_conv_algo {
+  PV_ALGO_AUTO = 0,
+  PV_ALGO_DIRECT = 1,   /* CUDA-core tiled direct convolution (any shape, f16 or f32 storage) */
+  PV_ALGO_TCGEN05 = 2   /* TMA + tcgen05.mma implicit GEMM (f16 storage, fp32 TMEM accum)    */
+} pv_conv_algo;
+
+typedef enum pv_pool_mode { PV_POOL_MAX = 0, PV_POOL_AVG = 1 } pv_pool_mode;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------------------------- */
+int pv_abi_version(void);
+const char* pv_last_error(void);
+/* Fills sm_count / cc (major*10+minor); returns PV_ERR_NO_DEVICE when no GPU is visible. */
+int pv_device_info(int* sm_count, int* cc);
+/* Number of kernels launched by this library since load (bench.py "gpu_launches"). */
+long long pv_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Clip transform chain, fused (one kernel):
+ *   UniformTemporalSubsample -> Div255 -> Normalize -> ShortSideScale(bilinear) -> crop
+ * Replaces: transforms/functional.py:19-41 (uniform_temporal_subsample: idx_t is computed on the
+ * host with torch.linspace exactly as functional.py:39-40 and passed in), functional.py:604-615
+ * (div_255), transforms/transforms.py:177-195 (Normalize), functional.py:92-131
+ * (short_side_scale -> F.interpolate bilinear, align_corners=False), torchvision CenterCrop /
+ * RandomCrop / functional.py:302-347 (uniform_crop) window selection.
+ *
+ * src is a uint8 (or f32/f16) clip addressed as src[c*sc + t*st + h*sh + w*sw], so both the
+ * CTHW-contiguous layout and the decoder's THWC-interleaved layout (data/utils.py:26-31) work.
+ * The bilinear taps are host-computed tables (bit-exact w.r.t. ATen's index/lambda math):
+ *   for output row y:  rows y0[y], y1[y], weight ly[y] of row y1   (already offset by the crop)
+ *   for output col x:  cols x0[x], x1[x], weight lx[x] of col x1
+ * out[c][j][y][x] = ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11),
+ *   v = (float(src)/255 - mean[c]) / std[c], taken from frame idx_t[j];  dst is [C,n_t,oh,ow].
+ * With identity tables / mean 0 / std 1 / div255 0 the same kernel is each single transform
+ * (UniformTemporalSubsample, Div255, Normalize, ShortSideScale, crop) on its own.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pv_clip_transform_desc {
+  int C, n_t, out_h, out_w;
+  long long sc, st, sh, sw;   /* source strides in ELEMENTS of the source dtype    */
+  float mean[4], stdv[4];     /* per channel (C <= 4)                             */
+  int src_dtype;              /* PV_U8 (decoder frames), PV_F32 or PV_F16         */
+  int dst_dtype;              /* PV_F16 or PV_F32                                 */
+  int div255;                 /* 1: v = src/255 first (Div255); 0: v = src        */
+} pv_clip_transform_desc;
+
+int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void* src,
+                          const int32_t* idx_t,
+                          const int32_t* y0, const int32_t* y1, const float* ly,
+                          const int32_t* x0, const int32_t* x1, const float* lx,
+                          void* dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / dtype conversion at the API boundary.
+ * NCDHW (reference model input, models/net.py:41-44) -> NDHWC with C padded to c_pad (zeros).
+ * src dtype f32 or f16; dst dtype f16 or f32.
+ * ------------------------------------------------------------------------------------------- */
+int pv_ncdhw_to_ndhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                      int N, int C, int T, int H, int W, int c_pad, long long dst_row_stride,
+                      void* stream);
+/* Clears n floats (SE accumulators) with a stream-ordered memset. */
+int pv_zero_f32(float* dst, long long n, void* stream);
+/* NDHWC -> NCDHW f32 (for handing feature maps back to torch when a model has no head). */
+int pv_ndhwc_to_ncdhw(const void* src, int src_dtype, long long src_row_stride, float* dst,
+                      int N, int C, int T, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3-D convolution + folded BatchNorm(eval) scale/bias + optional residual + activation.
+ * Replaces nn.Conv3d -> nn.BatchNorm3d(eval) -> activation chains built at
+ * models/resnet.py:98-132 (conv_a/b/c), :422-438 (branch1), models/stem.py:80-87,
+ * models/slowfast.py:672-679 (FuseFastToSlow), models/x3d.py:66-88,160-217, models/csn.py:169,
+ * layers/convolutions.py:191-237 (Conv2plus1d), models/stem.py:330-337 (PatchEmbed) and the
+ * residual add + ReLU of models/resnet.py:1179-1189.
+ *   y = act( conv(x, w) * scale[co] + bias[co] (+ residual) )
+ * groups must be 1 (dense) or == Ci == Co (depthwise).
+ *
+ * Packed weights (host-side, see pytorchvideo_b200/engine/packing.py):
+ *   PV_ALGO_DIRECT, dense : w[tap][ci][co]        (storage dtype, Ci/Co padded)
+ *   depthwise (any algo)  : w[tap][c]             (storage dtype)
+ *   PV_ALGO_TCGEN05       : w[co][tap][ci_pad64]  (f16, K-major rows of length taps*ci_pad64)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pv_conv3d_desc {
+  int dtype;                 /* storage dtype of x, y, residual, w: PV_F16 | PV_F32          */
+  int N, Ti, Hi, Wi, Ci;     /* Ci, Co: padded channel counts                               */
+  int To, Ho, Wo, Co;
+  int kt, kh, kw;
+  int st, sh, sw;
+  int pt, ph, pw;
+  int dt, dh, dw;            /* dilation                                                    */
+  int groups;
+  int act;                   /* pv_act applied last                                         */
+  int has_residual;
+  long long x_row_stride, y_row_stride, res_row_stride;
+  int ci_pad64;              /* PV_ALGO_TCGEN05 only: per-tap K extent of the packed weights */
+} pv_conv3d_desc;
+
+int pv_conv3d_fwd(const pv_conv3d_desc* d, int algo, const void* x, const void* w,
+                  const float* scale, const float* bias, const void* residual, void* y,
+                  void* stream);
+/* 1 if PV_ALGO_TCGEN05 supports this descriptor (pure host-side check, no GPU needed). */
+int pv_conv3d_tcgen05_supported(const pv_conv3d_desc* d);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling. nn.MaxPool3d stem pool (models/stem.py:94-100), nn.AvgPool3d head pools
+ * (models/head.py:116-118, models/slowfast.py:333-341, models/x3d.py:490), MViT skip-path
+ * MaxPool3d (layers/attention.py:677-679).  AvgPool divides by the full kernel volume
+ * (count_include_pad=True, the torch default); MaxPool pads with -inf.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pv_pool3d_desc {
+  int dtype, mode;
+  int N, Ti, Hi, Wi, C;
+  int To, Ho, Wo;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  long long x_row_stride, y_row_stride;
+} pv_pool3d_desc;
+int pv_pool3d_fwd(const pv_pool3d_desc* d, const void* x, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Squeeze-Excitation (fvcore SqueezeExcitation as used at models/x3d.py:190-198):
+ *   pv_channel_sum : sums[n][c] += sum over positions of x        (sums must be zeroed)
+ *   pv_se_gate     : gate[n][c] = sigmoid(W2 relu(W1 (sums/npos) + b1) + b2)   (f32 weights)
+ *   pv_scale_act   : y = act(x * gate[n][c])   in place allowed
+ * ------------------------------------------------------------------------------------------- */
+int pv_channel_sum(const void* x, int dtype, long long row_stride, int N, long long npos, int C,
+                   float* sums, void* stream);
+int pv_se_gate(const float* sums, long long npos, int N, int C, int Cr,
+               const float* w1, const float* b1, const float* w2, const float* b2,
+               int c_stride_w, float* gate, void* stream);
+int pv_scale_act(const void* x, void* y, int dtype, long long x_row_stride,
+                 long long y_row_stride, int N, long long npos, int C, const float* gate,
+                 int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Head tail (models/head.py:371-391): optional softmax over channels per position
+ * (activation applied BEFORE the global average, head.py:383-390), then mean over positions,
+ * un-pad and cast to f32:  out[n][c] = mean_p act(x[n][p][c]),  c < C_valid.
+ * ------------------------------------------------------------------------------------------- */
+int pv_head_reduce(const void* x, int dtype, long long row_stride, int N, long long npos,
+                   int C_valid, int softmax, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MViT pieces (layers/attention.py).
+ * pv_layernorm : y = (x-mean)/sqrt(var+eps)*gamma+beta over the last dim (f32 statistics)
+ *                nn.LayerNorm(eps=1e-6) at attention.py:655,703 / vision_transformers.py:333.
+ * pv_linear    : y[m][n] = act(sum_k x[m][k] w[n][k] + bias[n]) (+ residual[m][n])
+ *                nn.Linear at attention.py:93-95,315-320,541,716  (routes to the conv kernels
+ *                as a 1x1x1 convolution; kept as its own entry point for the reference's
+ *                Linear call sites).
+ * pv_attention : o = softmax((q*scale) k^T) v (+ q)    attention.py:531-539, flash-style, the
+ *                N_q x N_k matrix is never materialised.  q/k/v/o are [B][N][H][D] with
+ *                explicit row strides (elements between consecutive tokens), D = head dim.
+ * ------------------------------------------------------------------------------------------- */
+int pv_layernorm(const void* x, void* y, int dtype, long long rows, int C,
+                 long long x_row_stride, long long y_row_stride, const float* gamma,
+                 const float* beta, float eps, void* stream);
+typedef struct pv_attention_desc {
+  int dtype;
+  int B, H, Nq, Nk, D;
+  long long q_row_stride, k_row_stride, v_row_stride, o_row_stride; /* per token           */
+  long long q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride;
+  float scale;
+  int add_q_residual;   /* residual_pool=True: o += q (cls row included, attention.py:535-536) */
+} pv_attention_desc;
+int pv_attention_fwd(const pv_attention_desc* d, const void* q, const void* k, const void* v,
+                     void* o, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PV_B200_H_ */

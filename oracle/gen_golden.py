@@ -1,0 +1,142 @@
+"""Golden-vector generator (runs ONLY in the authoring container, where /root/reference exists).
+
+Imports the unmodified reference (with the 3-symbol fvcore shim in oracle/shim), loads this
+repo's deterministic weights into the reference models with ``load_state_dict(strict=True)``
+(this also proves state_dict / module-tree compatibility), runs the reference CPU forward and
+stores the outputs as small fixtures under tests/golden/.  It also pins the oracle: the
+interpreter in oracle/interp.py, run over the REAL reference modules, must reproduce the
+reference output bit-for-bit, and the numpy transform restatement must match the reference's
+own transforms.
+
+    PYTHONPATH=oracle/shim:/root/reference python oracle/gen_golden.py [--only name]
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
+sys.path.insert(1, "/root/reference")
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def gen_models(only=None):
+    import pytorchvideo.models.hub as RH            # the reference
+    import pytorchvideo_b200.models.hub as PH       # this repo's parameter containers
+    from pytorchvideo_b200 import testing as TS
+    from oracle.interp import oracle_forward
+    for case, (hub, kw, B, T, H, W, is_sf) in TS.MODEL_CASES.items():
+        if only and case != only:
+            continue
+        t0 = time.time()
+        mine = getattr(PH, hub)(**kw)
+        TS.randomize_model(mine, seed=1234)
+        ref = getattr(RH, hub)(pretrained=False, **kw)
+        ref.load_state_dict(mine.state_dict(), strict=True)
+        ref.eval()
+        clip = TS.synthetic_clip(B, T, H, W, seed=42)
+        with torch.no_grad():
+            inp = TS.slowfast_inputs(clip) if is_sf else clip
+            out_ref = ref(list(inp) if is_sf else inp)          # list() - the reference mutates it
+            inp = TS.slowfast_inputs(clip) if is_sf else clip
+            out_orc_on_ref = oracle_forward(ref, inp)
+            out_orc_on_mine = oracle_forward(mine, inp)
+        assert torch.equal(out_ref, out_orc_on_ref), "oracle != reference on reference modules (%s)" % case
+        assert torch.equal(out_ref, out_orc_on_mine), "oracle != reference on product tree (%s)" % case
+        torch.save({"case": case, "hub": hub, "batch": B, "T": T, "H": H, "W": W, "weight_seed": 1234,
+                    "input_seed": 42, "output": out_ref.clone(),
+                    "input_checksum": TS.tensor_checksum(clip),
+                    "state_checksum": TS.state_checksum(mine)},
+                   os.path.join(GOLD, "model_%s.pt" % case))
+        print("%-14s ok  out %s  |out|max %.4f  (%.1fs)" % (case, tuple(out_ref.shape), float(out_ref.abs().max()),
+                                                            time.time() - t0), flush=True)
+
+
+def gen_transforms():
+    import pytorchvideo.transforms.functional as RF   # reference functional (imports fine without av)
+    from pytorchvideo.transforms import transforms as RT
+    import torchvision.transforms as TV
+    from oracle import transforms_ref as O
+    from pytorchvideo_b200 import testing as TS
+    out = {}
+    # (1) temporal indices: oracle restatement vs reference on a grid + the reference's known answer
+    grid = {}
+    for t in list(range(1, 80)) + [100, 128, 250, 300]:
+        for n in list(range(1, 40)) + [64, 100, 128]:
+            x = torch.arange(t).view(1, t, 1, 1)
+            ref_idx = RF.uniform_temporal_subsample(x, n).view(-1).numpy()
+            assert np.array_equal(ref_idx, O.linspace_indices(t, n)), (t, n)
+            if (t, n) in ((20, 10), (64, 16), (64, 32), (32, 8), (300, 128), (7, 13)):
+                grid["%d_%d" % (t, n)] = ref_idx.astype(np.int64)
+    out["indices"] = grid
+    # (2) small-clip chain goldens (reference order: subsample, /255, normalize, scale, center crop)
+    cases = []
+    for (T, H, W, n, side, crop, seed) in [(20, 40, 60, 10, 24, 16, 1), (9, 61, 37, 4, 30, 28, 2),
+                                           (16, 48, 48, 16, 48, 32, 3), (12, 90, 160, 5, 32, 32, 4)]:
+        clip = TS.synthetic_u8_clip(T, H, W, seed=seed)
+        mean, std = (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)
+        chain = TV.Compose([RT.UniformTemporalSubsample(n), RT.Div255(), RT.Normalize(mean, std),
+                            RT.ShortSideScale(side), TV.CenterCrop(crop)])
+        ref = chain(clip)
+        orc = O.val_chain(clip.numpy(), n, mean, std, side, crop)
+        err = float(np.abs(ref.numpy() - orc).max())
+        assert err <= 2e-6, ("oracle transform chain deviates from the reference", err)
+        cases.append({"T": T, "H": H, "W": W, "n": n, "side": side, "crop": crop, "seed": seed,
+                      "mean": mean, "std": std, "out": ref.clone(), "oracle_max_err": err})
+    out["chain_small"] = cases
+    # (3) BASELINE config 5 at full size: keep a strided sample + checksums
+    clip = TS.synthetic_u8_clip(64, 1080, 1920, seed=0)
+    mean, std = (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)
+    chain = TV.Compose([RT.UniformTemporalSubsample(16), RT.Div255(), RT.Normalize(mean, std),
+                        RT.ShortSideScale(256), TV.CenterCrop(224)])
+    t0 = time.time()
+    ref = chain(clip)
+    dt = time.time() - t0
+    orc = O.val_chain(clip.numpy(), 16, mean, std, 256, 224)
+    err = float(np.abs(ref.numpy() - orc).max())
+    assert err <= 2e-6, err
+    out["chain_full"] = {"T": 64, "H": 1080, "W": 1920, "n": 16, "side": 256, "crop": 224, "seed": 0,
+                         "mean": mean, "std": std, "sample": ref[:, ::5, ::7, ::9].clone(),
+                         "checksum": TS.tensor_checksum(ref), "ref_seconds": dt, "oracle_max_err": err}
+    # (4) bilinear tables: oracle vs ATen-extracted weights
+    import torch.nn.functional as F
+    for (i, o) in [(1080, 256), (1920, 455), (320, 224), (7, 13), (224, 224), (61, 30), (240, 320)]:
+        eye = torch.eye(i).view(1, i, 1, i)
+        w = F.interpolate(eye, size=(1, o), mode="bilinear", align_corners=False)[0, :, 0, :].numpy()
+        i0, i1, l1 = O.bilinear_table(i, o)
+        W = np.zeros((i, o), np.float32)
+        for j in range(o):
+            W[i0[j], j] += np.float32(1) - l1[j]
+            W[i1[j], j] += l1[j]
+        assert np.array_equal(W, w), ("bilinear table mismatch", i, o)
+    # (5) crops (reference known answers: tests/test_transforms.py:199-226, 334-346)
+    out["uniform_crop"] = {}
+    for (h, w, size) in [(20, 40, 16), (40, 20, 16), (30, 30, 10)]:
+        for idx in range(3):
+            x = torch.arange(h * w, dtype=torch.float32).view(1, 1, h, w)
+            ref = RF.uniform_crop(x, size, idx)
+            y, xo, hh, ww = O.uniform_crop_window(h, w, size, idx)
+            assert torch.equal(ref, x[:, :, y:y + hh, xo:xo + ww])
+            out["uniform_crop"]["%d_%d_%d_%d" % (h, w, size, idx)] = (y, xo)
+    torch.save(out, os.path.join(GOLD, "transforms.pt"))
+    print("transforms ok (full-size reference chain took %.2fs)" % dt, flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--skip-models", action="store_true")
+    ap.add_argument("--skip-transforms", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if not a.skip_transforms:
+        gen_transforms()
+    if not a.skip_models:
+        gen_models(a.only)

@@ -1,0 +1,61 @@
+"""In-tree build of libpvb200.so (sm_100a only) with plain nvcc.
+
+The built library is git-ignored but travels to the GPU box with the gpurun snapshot.  nvcc
+cross-compiles without a GPU, so this also runs in the CPU-only authoring container.
+"""
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libpvb200.so")
+SOURCES = ["pv_api.cu", "pv_transform.cu", "pv_simt.cu", "pv_igemm.cu", "pv_attention.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(_HERE, "..", "include", "pv_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into lib/libpvb200.so.  Returns the library path."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        if os.path.exists(LIB_PATH):   # GPU box without sources changed: keep the shipped binary
+            return LIB_PATH
+        raise RuntimeError("nvcc not found and no prebuilt libpvb200.so present")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,498 @@
+// Implicit-GEMM 3-D convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[m][co] = sum_{tap,ci} X[pos(m) + tap][ci] * Wt[co][tap][ci]        (fp32 accumulate in TMEM)
+//   y        = act(D * scale[co] + bias[co] (+ residual))               (fused epilogue)
+//
+// * Activations are NDHWC f16.  The GEMM-M tile (128 rows) is a BOX of output positions
+//   (b0 x b1 x b2 x b3 over the W/H/T/N-like dims, merged where the kernel is trivial), so for
+//   every filter tap the A operand is ONE TMA tiled load of box [64 ch, b0, b1, b2, b3] at
+//   shifted coordinates; TMA's out-of-bounds zero fill implements the convolution padding and
+//   the channel tail (Ci % 64 != 0).  Strided convolutions use one tensor map per stride-parity
+//   class (base pointer offset + multiplied global strides), so only documented tiled-mode
+//   features are relied on.
+// * B operand (packed weights, K-major rows of taps*ci_pad64) is a 2-D TMA load [64, BLOCK_N].
+// * Both land in 128B-swizzled shared memory and feed tcgen05.mma (M=128, N=BLOCK_N, K=16) via
+//   shared-memory descriptors; accumulators live in TMEM (double buffered) and are drained by
+//   four epilogue warps with tcgen05.ld.
+// * Warp-specialised persistent kernel: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+//   warps2-5 = epilogue; smem ring of `stages` {A,B} slots with full/empty mbarriers.
+#include "pv_common.cuh"
+#include "pv_sm100.cuh"
+
+#include <mutex>
+
+namespace pv {
+
+using namespace sm100;
+
+constexpr int IG_BM = 128;        // UMMA M
+constexpr int IG_BK = 64;         // K per pipeline stage (one 128B swizzle row of f16)
+constexpr int IG_MAX_TAPS = 32;
+constexpr int IG_MAX_MAPS = 8;
+constexpr int IG_THREADS = 192;
+constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;   // 16 KiB
+
+struct IgemmParams {
+  CUtensorMap a_maps[IG_MAX_MAPS];
+  CUtensorMap b_map;
+  // tiling over the 4 merged output dims (0 = innermost)
+  int O[4];        // output extents
+  int box[4];      // tile box
+  int nt[4];       // tiles per dim
+  int rows;        // box[0]*box[1]*box[2]*box[3] (<= 128)
+  int n_tiles, m_tiles;
+  int block_n;
+  int Co;
+  int taps, num_kc;
+  int stages;
+  int tmem_cols;
+  int act, has_residual;
+  long long y_row_stride, res_row_stride;
+  signed char tap_q[IG_MAX_TAPS][4];
+  unsigned char tap_map[IG_MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(IG_THREADS, 1)
+conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restrict__ scale,
+                    const float* __restrict__ bias, const __half* __restrict__ res,
+                    __half* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = P.stages;
+  const uint32_t b_bytes = (uint32_t)P.block_n * IG_BK * 2;
+  const uint32_t stage_bytes = IG_A_BYTES + b_bytes;
+  // barriers live after the tile ring
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&P.b_map);
+    prefetch_tmap(&P.a_maps[0]);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = P.n_tiles * P.m_tiles;
+  const int num_kb = P.taps * P.num_kc;
+
+  if (warp == 0) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)P.rows * (IG_BK * 2) + b_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % P.n_tiles;
+        int mt = tile / P.n_tiles;
+        int o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
+        const int n0 = n_tile * P.block_n;
+        for (int tap = 0; tap < P.taps; ++tap) {
+          const void* amap = &P.a_maps[P.tap_map[tap]];
+          const int c1 = o[0] + P.tap_q[tap][0], c2 = o[1] + P.tap_q[tap][1];
+          const int c3 = o[2] + P.tap_q[tap][2], c4 = o[3] + P.tap_q[tap][3];
+          for (int kc = 0; kc < P.num_kc; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + IG_A_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_5d(a_dst, amap, full_bar(stage), kc * IG_BK, c1, c2, c3, c4);
+            tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * IG_BK, n0);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(IG_BM, P.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t a_desc = make_kmajor_desc(a_addr, 128);
+          const uint64_t b_desc = make_kmajor_desc(a_addr + IG_A_BYTES, 128);
+#pragma unroll
+          for (int k = 0; k < IG_BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in (addr>>4)
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));            // frees the smem slot when the MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue warps ========================================
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;       // GEMM row inside the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % P.n_tiles;
+      int mt = tile / P.n_tiles;
+      int o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
+      // row -> position inside the box
+      int r = row;
+      bool valid = row < P.rows;
+      long long pos = 0, mul = 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = r % P.box[i];
+        r /= P.box[i];
+        const int oi = o[i] + ii;
+        valid = valid && (oi < P.O[i]);
+        pos += (long long)oi * mul;
+        mul *= P.O[i];
+      }
+      const int n0 = n_tile * P.block_n;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.block_n);
+      __half* yrow = y + pos * P.y_row_stride + n0;
+      const __half* rrow = res + pos * P.res_row_stride + n0;
+      for (int c0 = 0; c0 < P.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = n0 + c0 + h * 8;
+            if (col < P.Co) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                f[j] = __uint_as_float(v[h * 8 + j]) * __ldg(scale + col + j) + __ldg(bias + col + j);
+              if (P.has_residual) {
+                float rr[8];
+                ld8<__half>(rrow + c0 + h * 8, rr);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += rr[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], P.act);
+              st8<__half>(yrow + c0 + h * 8, f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// =============================================================================================
+// Host side: problem reduction, tile search, tensor maps, launch
+// =============================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct Dim4 {      // one merged spatial dim
+  long long I, O;  // input / output extent
+  int k, s, p, dil;
+  long long in_stride;   // in positions (rows) of the input tensor
+};
+
+struct IgemmPlan {
+  Dim4 dim[4];
+  int ndims;
+  int orig2m[4];   // original dim (0=W,1=H,2=T,3=N) -> merged dim index
+};
+
+// Reduce (W,H,T,N) to <=4 merged dims: runs of adjacent trivial dims (k=1,s=1,p=0) collapse.
+static void reduce_dims(const pv_conv3d_desc* d, IgemmPlan* pl) {
+  Dim4 raw[4] = {
+      {d->Wi, d->Wo, d->kw, d->sw, d->pw, d->dw, 1},
+      {d->Hi, d->Ho, d->kh, d->sh, d->ph, d->dh, (long long)d->Wi},
+      {d->Ti, d->To, d->kt, d->st, d->pt, d->dt, (long long)d->Wi * d->Hi},
+      {d->N, d->N, 1, 1, 0, 1, (long long)d->Wi * d->Hi * d->Ti},
+  };
+  int n = 0;
+  for (int i = 0; i < 4; ++i) {
+    const bool triv = raw[i].k == 1 && raw[i].s == 1 && raw[i].p == 0;
+    if (n > 0) {
+      Dim4& prev = pl->dim[n - 1];
+      const bool ptriv = prev.k == 1 && prev.s == 1 && prev.p == 0;
+      if (triv && ptriv && prev.in_stride * prev.I == raw[i].in_stride) {
+        prev.I *= raw[i].I;
+        prev.O *= raw[i].O;
+        pl->orig2m[i] = n - 1;
+        continue;
+      }
+    }
+    pl->orig2m[i] = n;
+    pl->dim[n++] = raw[i];
+  }
+  pl->ndims = n;
+  for (int i = n; i < 4; ++i) pl->dim[i] = {1, 1, 1, 1, 0, 1, pl->dim[n - 1].in_stride * pl->dim[n - 1].I};
+}
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+int conv3d_tcgen05_supported(const pv_conv3d_desc* d, char* why, size_t why_len) {
+#define NOPE(...)                          \
+  do {                                     \
+    if (why) snprintf(why, why_len, __VA_ARGS__); \
+    return 0;                              \
+  } while (0)
+  if (d->dtype != PV_F16) NOPE("tcgen05 path needs f16 storage");
+  if (d->groups != 1) NOPE("tcgen05 path is dense only (groups=%d)", d->groups);
+  if (d->Ci % 8 || d->Co % 8) NOPE("Ci/Co must be multiples of 8");
+  if (d->x_row_stride % 8 || d->y_row_stride % 8 || (d->has_residual && d->res_row_stride % 8))
+    NOPE("row strides must be multiples of 8 elements (16 B)");
+  if (d->kt * d->kh * d->kw > IG_MAX_TAPS) NOPE("too many taps");
+  if (d->st * d->sh * d->sw > IG_MAX_MAPS) NOPE("stride product > %d", IG_MAX_MAPS);
+  if (d->ci_pad64 < d->Ci || d->ci_pad64 % 64) NOPE("ci_pad64 must be a multiple of 64 >= Ci");
+  const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
+  if (M >= (1ll << 31)) NOPE("too many output positions");
+  for (int off : {d->pt, d->ph, d->pw, d->dt * (d->kt - 1), d->dh * (d->kh - 1), d->dw * (d->kw - 1)})
+    if (off > 100) NOPE("tap offset too large");
+  return 1;
+#undef NOPE
+}
+
+static double tile_cycles(int n) {   // crude per-k-block cost model
+  double mma = 2.0 * n, smem = 128.0 + n;
+  return mma > smem ? mma : smem;
+}
+
+int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                          const float* bias, const void* residual, void* y, cudaStream_t stream) {
+  char why[160];
+  if (!conv3d_tcgen05_supported(d, why, sizeof(why))) {
+    set_error("PV_ALGO_TCGEN05 unsupported: %s", why);
+    return PV_ERR_UNSUPPORTED;
+  }
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PV_ERR_CUDA; }
+
+  static int sm_count = 0;
+  static bool attr_set = false;
+  if (sm_count == 0) {
+    int dev = 0;
+    PV_CUDA_OK(cudaGetDevice(&dev));
+    PV_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+
+  IgemmPlan pl;
+  reduce_dims(d, &pl);
+  IgemmParams P;
+  memset(&P, 0, sizeof(P));
+
+  // ---- tile box search: maximise useful rows per 128-row tile
+  {
+    long long O[4];
+    for (int i = 0; i < 4; ++i) O[i] = pl.dim[i].O;
+    double best = -1;
+    int bb[4] = {1, 1, 1, 1};
+    for (int b0 = 1; b0 <= 128 && b0 <= O[0]; ++b0) {
+      for (int b1 = 1; b0 * b1 <= 128 && b1 <= O[1]; ++b1) {
+        for (int b2 = 1; b0 * b1 * b2 <= 128 && b2 <= O[2]; ++b2) {
+          int b3 = 128 / (b0 * b1 * b2);
+          if (b3 > O[3]) b3 = (int)O[3];
+          if (b3 < 1) b3 = 1;
+          const double tiles = (double)cdiv(O[0], b0) * cdiv(O[1], b1) * cdiv(O[2], b2) * cdiv(O[3], b3);
+          const double eff = (double)O[0] * O[1] * O[2] * O[3] / (tiles * 128.0);
+          // prefer efficiency, then longer inner runs
+          const double score = eff + 1e-6 * b0;
+          if (score > best) { best = score; bb[0] = b0; bb[1] = b1; bb[2] = b2; bb[3] = b3; }
+        }
+      }
+    }
+    long long mt = 1;
+    for (int i = 0; i < 4; ++i) {
+      P.O[i] = (int)O[i];
+      P.box[i] = bb[i];
+      P.nt[i] = (int)cdiv(O[i], bb[i]);
+      mt *= P.nt[i];
+    }
+    P.rows = bb[0] * bb[1] * bb[2] * bb[3];
+    P.m_tiles = (int)mt;
+  }
+
+  // ---- BLOCK_N: minimise waves * per-tile cost
+  {
+    const int co16 = (int)cdiv(d->Co, 16) * 16;
+    int cands[6] = {256, 128, 64, 32, 16, co16 <= 256 ? co16 : 256};
+    double best = 1e30;
+    int bn = 16;
+    for (int c : cands) {
+      if (c > 256 || c > co16) continue;
+      const long long tiles = (long long)P.m_tiles * cdiv(d->Co, c);
+      const double waves = (double)cdiv(tiles, sm_count);
+      const double cost = waves * tile_cycles(c) + 1e-3 * cdiv(d->Co, c);
+      if (cost < best) { best = cost; bn = c; }
+    }
+    P.block_n = bn;
+    P.n_tiles = (int)cdiv(d->Co, bn);
+  }
+  P.Co = d->Co;
+  P.taps = d->kt * d->kh * d->kw;
+  P.num_kc = d->ci_pad64 / 64;
+  P.act = d->act;
+  P.has_residual = d->has_residual;
+  P.y_row_stride = d->y_row_stride;
+  P.res_row_stride = d->has_residual ? d->res_row_stride : 0;
+  {
+    int cols = 2 * P.block_n, p2 = 32;
+    while (p2 < cols) p2 <<= 1;
+    P.tmem_cols = p2;
+  }
+  const int stage_bytes = IG_A_BYTES + P.block_n * IG_BK * 2;
+  {
+    int st = (200 * 1024) / stage_bytes;
+    if (st > 8) st = 8;
+    if (st < 2) st = 2;
+    P.stages = st;
+  }
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 8 * (2 * P.stages + 4) + 16;
+
+  // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)
+  // merged dims never merge a dim that has taps, so each non-trivial original dim maps to one
+  // merged dim.  Build per-merged-dim lists.
+  int ks[4], ss[4], ps[4], dls[4];
+  for (int i = 0; i < 4; ++i) { ks[i] = pl.dim[i].k; ss[i] = pl.dim[i].s; ps[i] = pl.dim[i].p; dls[i] = pl.dim[i].dil; }
+  const int* orig2m = pl.orig2m;
+  unsigned used_maps = 0;
+  for (int it = 0; it < d->kt; ++it)
+    for (int ih = 0; ih < d->kh; ++ih)
+      for (int iw = 0; iw < d->kw; ++iw) {
+        const int tap = (it * d->kh + ih) * d->kw + iw;
+        int q[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
+        const int offs[3] = {iw * d->dw - d->pw, ih * d->dh - d->ph, it * d->dt - d->pt};
+        const int strd[3] = {d->sw, d->sh, d->st};
+        for (int o = 0; o < 3; ++o) {
+          const int m = orig2m[o];
+          if (strd[o] == 1 && offs[o] == 0) continue;
+          const int qq = floordiv(offs[o], strd[o]);
+          q[m] = qq;
+          r[m] = offs[o] - qq * strd[o];
+        }
+        int cls = 0, mul = 1;
+        for (int m = 0; m < 4; ++m) { cls += r[m] * mul; mul *= ss[m]; }
+        if (cls >= IG_MAX_MAPS) { set_error("internal: parity class %d", cls); return PV_ERR_INVALID; }
+        P.tap_map[tap] = (unsigned char)cls;
+        for (int m = 0; m < 4; ++m) P.tap_q[tap][m] = (signed char)q[m];
+        used_maps |= 1u << cls;
+      }
+
+  // ---- tensor maps
+  for (int cls = 0; cls < IG_MAX_MAPS; ++cls) {
+    if (!(used_maps & (1u << cls))) continue;
+    int r[4], c = cls;
+    for (int m = 0; m < 4; ++m) { r[m] = c % ss[m]; c /= ss[m]; }
+    long long base_off = 0;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    gdim[0] = (cuuint64_t)d->Ci;
+    box[0] = 64;
+    bool empty = false;
+    for (int m = 0; m < 4; ++m) {
+      const long long cnt = (pl.dim[m].I - r[m] + ss[m] - 1) / ss[m];
+      if (cnt <= 0) empty = true;
+      gdim[m + 1] = (cuuint64_t)(cnt > 0 ? cnt : 1);
+      gstr[m] = (cuuint64_t)(pl.dim[m].in_stride * ss[m] * d->x_row_stride * 2);
+      box[m + 1] = (cuuint32_t)P.box[m];
+      base_off += (long long)r[m] * pl.dim[m].in_stride * d->x_row_stride;
+    }
+    (void)empty;
+    void* gptr = (void*)((const __half*)x + base_off);
+    CUresult cr = encode(&P.a_maps[cls], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, gptr, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(A, class %d) failed: %d (Ci=%d dims=%llu,%llu,%llu,%llu box=%u,%u,%u,%u)",
+                cls, (int)cr, d->Ci, (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+                (unsigned long long)gdim[3], (unsigned long long)gdim[4], box[1], box[2], box[3], box[4]);
+      return PV_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)P.taps * d->ci_pad64, (cuuint64_t)d->Co};
+    cuuint64_t gstr[1] = {(cuuint64_t)P.taps * d->ci_pad64 * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)P.block_n}, estr[2] = {1, 1};
+    CUresult cr = encode(&P.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)cr); return PV_ERR_CUDA; }
+  }
+
+  if (!attr_set) {
+    PV_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
+  if (total_tiles == 0) return PV_OK;
+  const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
+  conv3d_igemm_kernel<<<grid, IG_THREADS, smem_bytes, stream>>>(P, scale, bias, (const __half*)residual,
+                                                              (__half*)y);
+  PV_LAUNCH_OK("conv3d_igemm_kernel");
+  return PV_OK;
+}
+
+}  // namespace pv

@@ -1,0 +1,651 @@
+// CUDA-core kernels: layout conversion, tiled direct convolution (dense), depthwise stencils,
+// pooling, squeeze-excitation, head reduction, LayerNorm.  All are HBM-bound or serve shapes the
+// tcgen05 implicit-GEMM path does not take (3-channel stems, fp32 "parity" storage).
+#include "pv_common.cuh"
+
+namespace pv {
+
+// =============================================================================================
+// NCDHW <-> NDHWC
+// =============================================================================================
+template <typename SrcT, typename DstT>
+__global__ void ncdhw_to_ndhwc_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int C,
+                                      long long thw, int c_pad, long long dst_row_stride,
+                                      long long total_pos) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_pos) return;
+  long long n = p / thw, r = p - n * thw;
+  const SrcT* s = src + n * C * thw + r;
+  DstT* o = dst + p * dst_row_stride;
+  for (int c = 0; c < c_pad; ++c) {
+    float v = (c < C) ? Elem<SrcT>::ld(s + (long long)c * thw) : 0.f;
+    Elem<DstT>::st(o + c, v);
+  }
+}
+
+template <typename SrcT>
+__global__ void ndhwc_to_ncdhw_kernel(const SrcT* __restrict__ src, long long src_row_stride,
+                                      float* __restrict__ dst, int C, long long thw,
+                                      long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over N*C*thw (dst order)
+  if (i >= total) return;
+  long long r = i % thw;
+  long long nc = i / thw;
+  int c = (int)(nc % C);
+  long long n = nc / C;
+  dst[i] = Elem<SrcT>::ld(src + (n * thw + r) * src_row_stride + c);
+}
+
+// =============================================================================================
+// Dense direct convolution, tiled 64 positions x 64 output channels per CTA, K = (tap, ci)
+// flattened and consumed in chunks of 16.  fp32 accumulation regardless of storage type.
+// Requires Ci % 4 == 0, Co % 4 == 0.
+// =============================================================================================
+constexpr int DC_BM = 64, DC_BN = 64, DC_BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv3d_direct_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__ w,
+                     const float* __restrict__ scale, const float* __restrict__ bias,
+                     const T* __restrict__ res, T* __restrict__ y, long long M) {
+  __shared__ float As[DC_BK][DC_BM + 4];
+  __shared__ float Bs[DC_BK][DC_BN + 4];
+  __shared__ int pos_n[DC_BM], pos_t[DC_BM], pos_h[DC_BM], pos_w[DC_BM];
+
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * DC_BM;
+  const int n0 = blockIdx.y * DC_BN;
+
+  if (tid < DC_BM) {
+    long long m = m0 + tid;
+    if (m < M) {
+      int wo = (int)(m % d.Wo); long long r = m / d.Wo;
+      int ho = (int)(r % d.Ho); r /= d.Ho;
+      int to = (int)(r % d.To); int n = (int)(r / d.To);
+      pos_n[tid] = n; pos_t[tid] = to * d.st - d.pt; pos_h[tid] = ho * d.sh - d.ph;
+      pos_w[tid] = wo * d.sw - d.pw;
+    } else {
+      pos_n[tid] = -1; pos_t[tid] = 0; pos_h[tid] = 0; pos_w[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  const int K = d.kt * d.kh * d.kw * d.Ci;
+  // A loader: thread -> (position a_m, 4 consecutive k starting at a_k)
+  const int a_m = tid >> 2, a_k = (tid & 3) * 4;
+  // B loader: thread -> (k row b_k, 4 consecutive co starting at b_n)
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+  const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int an = pos_n[a_m], at = pos_t[a_m], ah = pos_h[a_m], aw = pos_w[a_m];
+
+  for (int k0 = 0; k0 < K; k0 += DC_BK) {
+    // ---- A tile
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      int k = k0 + a_k;
+      if (an >= 0 && k < K) {
+        int tap = k / d.Ci, ci = k - tap * d.Ci;
+        int kw_ = tap % d.kw; int r = tap / d.kw; int kh_ = r % d.kh; int kt_ = r / d.kh;
+        int ti = at + kt_ * d.dt, hi = ah + kh_ * d.dh, wi = aw + kw_ * d.dw;
+        if ((unsigned)ti < (unsigned)d.Ti && (unsigned)hi < (unsigned)d.Hi &&
+            (unsigned)wi < (unsigned)d.Wi) {
+          const T* p = x + ((((long long)an * d.Ti + ti) * d.Hi + hi) * d.Wi + wi) * d.x_row_stride + ci;
+          ld4<T>(p, v);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[a_k + i][a_m] = v[i];
+    }
+    // ---- B tile
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      int k = k0 + b_k, co = n0 + b_n;
+      if (k < K && co < d.Co) ld4<T>(w + (long long)k * d.Co + co, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[b_k][b_n + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DC_BK; ++kk) {
+      float a[4], b[4];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&As[kk][tm]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Bs[kk][tn]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int co = n0 + tn;
+  if (co >= d.Co) return;
+  float sc[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sc[j] = __ldg(scale + co + j); bi[j] = __ldg(bias + co + j); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + tm + i;
+    if (m >= M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] * sc[j] + bi[j];
+    if (d.has_residual) {
+      float r[4];
+      ld4<T>(res + m * d.res_row_stride + co, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += r[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], d.act);
+    st4<T>(y + m * d.y_row_stride + co, v);
+  }
+}
+
+// =============================================================================================
+// Depthwise convolution stencil (groups == C).  One thread = one output position x 8 channels;
+// consecutive lanes walk the channel groups of a position, then the next position, so every
+// warp-level load is a run of consecutive 16-byte vectors (coalesced in NDHWC).
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+dwconv3d_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__ w,
+                const float* __restrict__ scale, const float* __restrict__ bias,
+                const T* __restrict__ res, T* __restrict__ y, long long total) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = d.Co >> 3;
+  const int cg = (int)(e % G);
+  long long m = e / G;
+  const int c = cg * 8;
+  int wo = (int)(m % d.Wo); long long r = m / d.Wo;
+  int ho = (int)(r % d.Ho); r /= d.Ho;
+  int to = (int)(r % d.To); int n = (int)(r / d.To);
+  const int t0 = to * d.st - d.pt, h0 = ho * d.sh - d.ph, w0 = wo * d.sw - d.pw;
+
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int kt_ = 0; kt_ < d.kt; ++kt_) {
+    const int ti = t0 + kt_ * d.dt;
+    if ((unsigned)ti >= (unsigned)d.Ti) continue;
+    for (int kh_ = 0; kh_ < d.kh; ++kh_) {
+      const int hi = h0 + kh_ * d.dh;
+      if ((unsigned)hi >= (unsigned)d.Hi) continue;
+      const T* row = x + (((long long)n * d.Ti + ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
+      const T* wrow = w + (long long)((kt_ * d.kh + kh_) * d.kw) * d.Co + c;
+      for (int kw_ = 0; kw_ < d.kw; ++kw_) {
+        const int wi = w0 + kw_ * d.dw;
+        if ((unsigned)wi >= (unsigned)d.Wi) continue;
+        float xv[8], wv[8];
+        ld8<T>(row + (long long)wi * d.x_row_stride, xv);
+        ld8<T>(wrow + (long long)kw_ * d.Co, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[i], wv[i], acc[i]);
+      }
+    }
+  }
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = acc[i] * __ldg(scale + c + i) + __ldg(bias + c + i);
+  if (d.has_residual) {
+    float rr[8];
+    ld8<T>(res + m * d.res_row_stride + c, rr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += rr[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], d.act);
+  st8<T>(y + m * d.y_row_stride + c, v);
+}
+
+// =============================================================================================
+// Pooling (max / avg), NDHWC, one thread = one output position x 8 channels.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool3d_kernel(pv_pool3d_desc d, const T* __restrict__ x, T* __restrict__ y, long long total) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = d.C >> 3;
+  const int c = (int)(e % G) * 8;
+  long long m = e / G;
+  int wo = (int)(m % d.Wo); long long r = m / d.Wo;
+  int ho = (int)(r % d.Ho); r /= d.Ho;
+  int to = (int)(r % d.To); int n = (int)(r / d.To);
+  const int t0 = to * d.st - d.pt, h0 = ho * d.sh - d.ph, w0 = wo * d.sw - d.pw;
+  const bool is_max = d.mode == PV_POOL_MAX;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = is_max ? -INFINITY : 0.f;
+  for (int kt_ = 0; kt_ < d.kt; ++kt_) {
+    const int ti = t0 + kt_;
+    if ((unsigned)ti >= (unsigned)d.Ti) continue;
+    for (int kh_ = 0; kh_ < d.kh; ++kh_) {
+      const int hi = h0 + kh_;
+      if ((unsigned)hi >= (unsigned)d.Hi) continue;
+      const T* row = x + (((long long)n * d.Ti + ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
+      for (int kw_ = 0; kw_ < d.kw; ++kw_) {
+        const int wi = w0 + kw_;
+        if ((unsigned)wi >= (unsigned)d.Wi) continue;
+        float v[8];
+        ld8<T>(row + (long long)wi * d.x_row_stride, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = is_max ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+      }
+    }
+  }
+  if (!is_max) {
+    const float inv = 1.f / (float)(d.kt * d.kh * d.kw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  }
+  st8<T>(y + m * d.y_row_stride + c, acc);
+}
+
+// =============================================================================================
+// Squeeze-Excitation helpers
+// =============================================================================================
+// grid = (chunks, N); each CTA reduces `chunk` positions of one sample for all channels and
+// adds its partial sums with one atomic per channel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const T* __restrict__ x, long long row_stride, long long npos, int C,
+                   long long chunk, float* __restrict__ sums) {
+  extern __shared__ float sh[];   // [C]
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sh[c] = 0.f;
+  __syncthreads();
+  const int G = C >> 3;
+  const long long p0 = (long long)blockIdx.x * chunk;
+  const long long p1 = min(p0 + chunk, npos);
+  const int lanes_per_pos = G;
+  const int pos_per_iter = blockDim.x / lanes_per_pos;
+  if (pos_per_iter > 0) {
+    const int cg = threadIdx.x % lanes_per_pos, pl = threadIdx.x / lanes_per_pos;
+    if (pl < pos_per_iter) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (long long p = p0 + pl; p < p1; p += pos_per_iter) {
+        float v[8];
+        ld8<T>(x + ((long long)n * npos + p) * row_stride + cg * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sh[cg * 8 + i], acc[i]);
+    }
+  } else {   // more channel groups than threads
+    for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (long long p = p0; p < p1; ++p) {
+        float v[8];
+        ld8<T>(x + ((long long)n * npos + p) * row_stride + cg * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sh[cg * 8 + i] = acc[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(sums + (long long)n * C + c, sh[c]);
+}
+
+// one CTA per sample; Cr <= 256
+__global__ void se_gate_kernel(const float* __restrict__ sums, float inv_npos, int C, int Cr,
+                               const float* __restrict__ w1, const float* __restrict__ b1,
+                               const float* __restrict__ w2, const float* __restrict__ b2,
+                               int c_stride_w, float* __restrict__ gate) {
+  extern __shared__ float sh[];   // mean[C] + hidden[Cr]
+  float* mean = sh;
+  float* hid = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[(long long)n * C + c] * inv_npos;
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+    float a = b1[j];
+    for (int c = 0; c < C; ++c) a = fmaf(w1[(long long)j * c_stride_w + c], mean[c], a);
+    hid[j] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int j = 0; j < Cr; ++j) a = fmaf(w2[(long long)c * Cr + j], hid[j], a);
+    gate[(long long)n * C + c] = 1.f / (1.f + __expf(-a));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_act_kernel(const T* __restrict__ x, T* __restrict__ y, long long x_row_stride,
+                 long long y_row_stride, long long npos, int C, const float* __restrict__ gate,
+                 int act, long long total) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = C >> 3;
+  const int c = (int)(e % G) * 8;
+  long long m = e / G;
+  long long n = m / npos;
+  float v[8];
+  ld8<T>(x + m * x_row_stride + c, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float g = gate ? __ldg(gate + n * C + c + i) : 1.f;
+    v[i] = apply_act(v[i] * g, act);
+  }
+  st8<T>(y + m * y_row_stride + c, v);
+}
+
+// =============================================================================================
+// Head tail: optional per-position softmax over channels, then mean over positions -> f32.
+// one CTA per sample, blockDim = 256.
+// =============================================================================================
+template <typename T>
+__global__ void head_reduce_kernel(const T* __restrict__ x, long long row_stride, long long npos,
+                                   int C, int softmax, float* __restrict__ out) {
+  extern __shared__ float sh[];   // acc[C] + red[32]
+  float* acc = sh;
+  float* red = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
+  __syncthreads();
+  for (long long p = 0; p < npos; ++p) {
+    const T* row = x + ((long long)n * npos + p) * row_stride;
+    if (!softmax) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] += Elem<T>::ld(row + c);
+    } else {
+      float mx = -INFINITY;
+      for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, Elem<T>::ld(row + c));
+      for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+      __syncthreads();
+      mx = red[0];
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+      __syncthreads();
+      float sm = 0.f;
+      for (int c = threadIdx.x; c < C; c += blockDim.x) sm += expf(Elem<T>::ld(row + c) - mx);
+      for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sm;
+      __syncthreads();
+      sm = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sm += red[i];
+      __syncthreads();
+      const float inv = 1.f / sm;
+      for (int c = threadIdx.x; c < C; c += blockDim.x)
+        acc[c] += expf(Elem<T>::ld(row + c) - mx) * inv;
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)npos;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(long long)n * C + c] = acc[c] * inv;
+}
+
+// =============================================================================================
+// LayerNorm over the last dim, one warp per row, fp32 statistics (two-pass, like ATen).
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
+                 long long x_row_stride, long long y_row_stride, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* xr = x + row * x_row_stride;
+  float s = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float v[8];
+    ld8<T>(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float v[8];
+    ld8<T>(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float dlt = v[i] - mean; q = fmaf(dlt, dlt, q); }
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  T* yr = y + row * y_row_stride;
+  for (int c = lane * 8; c < C; c += 256) {
+    float v[8];
+    ld8<T>(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = (v[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
+    st8<T>(yr + c, v);
+  }
+}
+
+}  // namespace pv
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace pv;
+
+extern "C" int pv_ncdhw_to_ndhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int N,
+                                 int C, int T, int H, int W, int c_pad,
+                                 long long dst_row_stride, void* stream) {
+  PV_CHECK_ARG(src && dst, "null pointer");
+  PV_CHECK_ARG(c_pad >= C && dst_row_stride >= c_pad, "bad padding");
+  const long long thw = (long long)T * H * W, total = (long long)N * thw;
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+#define PV_CASE(ST, DT)                                                                          \
+  ncdhw_to_ndhwc_kernel<ST, DT><<<grid, block, 0, s>>>((const ST*)src, (DT*)dst, C, thw, c_pad, \
+                                                     dst_row_stride, total)
+  if (src_dtype == PV_F32 && dst_dtype == PV_F16) PV_CASE(float, __half);
+  else if (src_dtype == PV_F32 && dst_dtype == PV_F32) PV_CASE(float, float);
+  else if (src_dtype == PV_F16 && dst_dtype == PV_F16) PV_CASE(__half, __half);
+  else if (src_dtype == PV_F16 && dst_dtype == PV_F32) PV_CASE(__half, float);
+  else { set_error("unsupported dtype pair %d->%d", src_dtype, dst_dtype); return PV_ERR_INVALID; }
+#undef PV_CASE
+  PV_LAUNCH_OK("ncdhw_to_ndhwc_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_zero_f32(float* dst, long long n, void* stream) {
+  PV_CHECK_ARG(dst || n == 0, "null pointer");
+  if (n > 0) PV_CUDA_OK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(float), (cudaStream_t)stream));
+  return PV_OK;
+}
+
+extern "C" int pv_ndhwc_to_ncdhw(const void* src, int src_dtype, long long src_row_stride,
+                                 float* dst, int N, int C, int T, int H, int W, void* stream) {
+  PV_CHECK_ARG(src && dst, "null pointer");
+  const long long thw = (long long)T * H * W, total = (long long)N * C * thw;
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+  if (src_dtype == PV_F16)
+    ndhwc_to_ncdhw_kernel<__half><<<grid, block, 0, s>>>((const __half*)src, src_row_stride, dst, C, thw, total);
+  else if (src_dtype == PV_F32)
+    ndhwc_to_ncdhw_kernel<float><<<grid, block, 0, s>>>((const float*)src, src_row_stride, dst, C, thw, total);
+  else { set_error("unsupported dtype %d", src_dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("ndhwc_to_ncdhw_kernel");
+  return PV_OK;
+}
+
+namespace pv {
+int conv3d_check(const pv_conv3d_desc* d) {
+  PV_CHECK_ARG(d, "null descriptor");
+  PV_CHECK_ARG(d->dtype == PV_F16 || d->dtype == PV_F32, "conv dtype must be f16|f32");
+  PV_CHECK_ARG(d->N >= 0 && d->Ci > 0 && d->Co > 0, "bad sizes");
+  PV_CHECK_ARG(d->kt > 0 && d->kh > 0 && d->kw > 0 && d->st > 0 && d->sh > 0 && d->sw > 0 &&
+                   d->dt > 0 && d->dh > 0 && d->dw > 0, "bad kernel/stride/dilation");
+  const int to = (d->Ti + 2 * d->pt - d->dt * (d->kt - 1) - 1) / d->st + 1;
+  const int ho = (d->Hi + 2 * d->ph - d->dh * (d->kh - 1) - 1) / d->sh + 1;
+  const int wo = (d->Wi + 2 * d->pw - d->dw * (d->kw - 1) - 1) / d->sw + 1;
+  PV_CHECK_ARG(to == d->To && ho == d->Ho && wo == d->Wo,
+               "output dims (%d,%d,%d) inconsistent with conv arithmetic (%d,%d,%d)", d->To, d->Ho,
+               d->Wo, to, ho, wo);
+  PV_CHECK_ARG(d->groups == 1 || (d->groups == d->Ci && d->Ci == d->Co),
+               "groups must be 1 or Ci==Co (depthwise); got groups=%d Ci=%d Co=%d", d->groups,
+               d->Ci, d->Co);
+  PV_CHECK_ARG(d->x_row_stride >= d->Ci && d->y_row_stride >= d->Co, "row stride < channels");
+  PV_CHECK_ARG(!d->has_residual || d->res_row_stride >= d->Co, "residual row stride < Co");
+  return PV_OK;
+}
+
+int conv3d_direct_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                         const float* bias, const void* residual, void* y, cudaStream_t s) {
+  const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
+  if (M == 0) return PV_OK;
+  const int esz = d->dtype == PV_F16 ? 2 : 4;
+  if (d->groups == 1) {
+    PV_CHECK_ARG(d->Ci % 4 == 0 && d->Co % 4 == 0, "direct conv needs Ci%%4==0 && Co%%4==0");
+    PV_CHECK_ARG((d->x_row_stride * esz) % (4 * esz) == 0 && (d->y_row_stride % 4) == 0,
+                 "row strides must be multiples of 4 elements");
+    dim3 grid((unsigned)cdiv(M, DC_BM), (unsigned)cdiv(d->Co, DC_BN)), block(256);
+    if (d->dtype == PV_F16)
+      conv3d_direct_kernel<__half><<<grid, block, 0, s>>>(*d, (const __half*)x, (const __half*)w, scale, bias,
+                                                       (const __half*)residual, (__half*)y, M);
+    else
+      conv3d_direct_kernel<float><<<grid, block, 0, s>>>(*d, (const float*)x, (const float*)w, scale, bias,
+                                                      (const float*)residual, (float*)y, M);
+    PV_LAUNCH_OK("conv3d_direct_kernel");
+  } else {
+    PV_CHECK_ARG(d->Co % 8 == 0, "depthwise conv needs C%%8==0");
+    PV_CHECK_ARG(d->x_row_stride % 8 == 0 && d->y_row_stride % 8 == 0, "row strides must be multiples of 8");
+    const long long total = M * (d->Co / 8);
+    dim3 grid((unsigned)cdiv(total, 256)), block(256);
+    if (d->dtype == PV_F16)
+      dwconv3d_kernel<__half><<<grid, block, 0, s>>>(*d, (const __half*)x, (const __half*)w, scale, bias,
+                                                  (const __half*)residual, (__half*)y, total);
+    else
+      dwconv3d_kernel<float><<<grid, block, 0, s>>>(*d, (const float*)x, (const float*)w, scale, bias,
+                                                 (const float*)residual, (float*)y, total);
+    PV_LAUNCH_OK("dwconv3d_kernel");
+  }
+  return PV_OK;
+}
+}  // namespace pv
+
+extern "C" int pv_pool3d_fwd(const pv_pool3d_desc* d, const void* x, void* y, void* stream) {
+  PV_CHECK_ARG(d && x && y, "null argument");
+  PV_CHECK_ARG(d->dtype == PV_F16 || d->dtype == PV_F32, "pool dtype must be f16|f32");
+  PV_CHECK_ARG(d->C % 8 == 0 && d->x_row_stride % 8 == 0 && d->y_row_stride % 8 == 0,
+               "pool needs C and row strides %% 8 == 0");
+  PV_CHECK_ARG(d->mode == PV_POOL_MAX || d->mode == PV_POOL_AVG, "bad pool mode");
+  const int to = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  const int ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  const int wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  PV_CHECK_ARG(to == d->To && ho == d->Ho && wo == d->Wo, "pool output dims inconsistent");
+  const long long total = (long long)d->N * d->To * d->Ho * d->Wo * (d->C / 8);
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+  if (d->dtype == PV_F16)
+    pool3d_kernel<__half><<<grid, block, 0, s>>>(*d, (const __half*)x, (__half*)y, total);
+  else
+    pool3d_kernel<float><<<grid, block, 0, s>>>(*d, (const float*)x, (float*)y, total);
+  PV_LAUNCH_OK("pool3d_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_channel_sum(const void* x, int dtype, long long row_stride, int N,
+                              long long npos, int C, float* sums, void* stream) {
+  PV_CHECK_ARG(x && sums, "null pointer");
+  PV_CHECK_ARG(C % 8 == 0 && row_stride % 8 == 0, "C and row stride must be multiples of 8");
+  if (N == 0 || npos == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  long long chunks = cdiv(npos, 2048);
+  if (chunks > 1024) chunks = 1024;
+  const long long chunk = cdiv(npos, chunks);
+  chunks = cdiv(npos, chunk);
+  dim3 grid((unsigned)chunks, N), block(256);
+  size_t smem = (size_t)C * sizeof(float);
+  if (dtype == PV_F16)
+    channel_sum_kernel<__half><<<grid, block, smem, s>>>((const __half*)x, row_stride, npos, C, chunk, sums);
+  else if (dtype == PV_F32)
+    channel_sum_kernel<float><<<grid, block, smem, s>>>((const float*)x, row_stride, npos, C, chunk, sums);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("channel_sum_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_se_gate(const float* sums, long long npos, int N, int C, int Cr, const float* w1,
+                          const float* b1, const float* w2, const float* b2, int c_stride_w,
+                          float* gate, void* stream) {
+  PV_CHECK_ARG(sums && w1 && b1 && w2 && b2 && gate, "null pointer");
+  PV_CHECK_ARG(npos > 0 && C > 0 && Cr > 0, "bad sizes");
+  if (N == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t smem = (size_t)(C + Cr) * sizeof(float);
+  se_gate_kernel<<<N, 256, smem, s>>>(sums, 1.f / (float)npos, C, Cr, w1, b1, w2, b2, c_stride_w, gate);
+  PV_LAUNCH_OK("se_gate_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_scale_act(const void* x, void* y, int dtype, long long x_row_stride,
+                            long long y_row_stride, int N, long long npos, int C,
+                            const float* gate, int act, void* stream) {
+  PV_CHECK_ARG(x && y, "null pointer");
+  PV_CHECK_ARG(C % 8 == 0 && x_row_stride % 8 == 0 && y_row_stride % 8 == 0, "C/strides %% 8");
+  const long long total = (long long)N * npos * (C / 8);
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+  if (dtype == PV_F16)
+    scale_act_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, x_row_stride, y_row_stride,
+                                                 npos, C, gate, act, total);
+  else if (dtype == PV_F32)
+    scale_act_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, x_row_stride, y_row_stride,
+                                                npos, C, gate, act, total);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("scale_act_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_head_reduce(const void* x, int dtype, long long row_stride, int N,
+                              long long npos, int C_valid, int softmax, float* out, void* stream) {
+  PV_CHECK_ARG(x && out, "null pointer");
+  PV_CHECK_ARG(C_valid > 0 && npos > 0, "bad sizes");
+  if (N == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t smem = (size_t)(C_valid + 32) * sizeof(float);
+  if (dtype == PV_F16)
+    head_reduce_kernel<__half><<<N, 256, smem, s>>>((const __half*)x, row_stride, npos, C_valid, softmax, out);
+  else if (dtype == PV_F32)
+    head_reduce_kernel<float><<<N, 256, smem, s>>>((const float*)x, row_stride, npos, C_valid, softmax, out);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("head_reduce_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, int C,
+                            long long x_row_stride, long long y_row_stride, const float* gamma,
+                            const float* beta, float eps, void* stream) {
+  PV_CHECK_ARG(x && y && gamma && beta, "null pointer");
+  PV_CHECK_ARG(C % 8 == 0 && x_row_stride % 8 == 0 && y_row_stride % 8 == 0, "C/strides %% 8");
+  if (rows == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(rows, 8)), block(256);
+  if (dtype == PV_F16)
+    layernorm_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, rows, C, x_row_stride,
+                                                 y_row_stride, gamma, beta, eps);
+  else if (dtype == PV_F32)
+    layernorm_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, rows, C, x_row_stride,
+                                                y_row_stride, gamma, beta, eps);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("layernorm_kernel");
+  return PV_OK;
+}

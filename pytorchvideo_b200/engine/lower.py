@@ -1,0 +1,308 @@
+"""Lower a PyTorchVideo-style module tree into a Plan (structural walk, no tracing).
+
+Dispatch is by class *name* and attribute names, exactly the names the reference uses
+(models/net.py, resnet.py, stem.py, head.py, slowfast.py, x3d.py, layers/convolutions.py), so the
+same lowering accepts this package's own parameter-container modules and - where the reference
+is importable - the reference's modules themselves (state_dict-compatible drop-in).
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .plan import Plan, TRef
+
+
+def _t3(v):
+    if isinstance(v, (tuple, list)):
+        assert len(v) == 3
+        return tuple(int(i) for i in v)
+    return (int(v),) * 3
+
+
+def _act_code(m):
+    if m is None:
+        return L.ACT_NONE
+    n = type(m).__name__
+    if n == "ReLU":
+        return L.ACT_RELU
+    if n == "Swish":
+        return L.ACT_SWISH
+    if n == "GELU":
+        return L.ACT_GELU
+    if n == "Sigmoid":
+        return L.ACT_SIGMOID
+    if n == "Identity":
+        return L.ACT_NONE
+    raise NotImplementedError("activation %s has no B200 kernel" % n)
+
+
+def _is_bn(m):
+    return isinstance(m, nn.modules.batchnorm._BatchNorm) or type(m).__name__.startswith("NaiveSyncBatchNorm")
+
+
+class Lowering:
+    def __init__(self, plan: Plan):
+        self.p = plan
+
+    # ---- leaf helpers --------------------------------------------------------------------
+    def conv(self, x: TRef, conv: nn.Conv3d, bn=None, act=None, residual=None, name="conv"):
+        if type(conv).__name__ == "Conv2plus1d":
+            return self.conv2plus1d(x, conv, bn, act, residual, name)
+        if not isinstance(conv, nn.Conv3d):
+            raise NotImplementedError("%s: conv module %s unsupported" % (name, type(conv).__name__))
+        if isinstance(conv.padding, str):
+            raise NotImplementedError("string padding unsupported")
+        if conv.padding_mode != "zeros":
+            raise NotImplementedError("padding_mode %s unsupported" % conv.padding_mode)
+        if bn is not None and not _is_bn(bn):
+            raise NotImplementedError("%s: norm %s unsupported (BatchNorm only)" % (name, type(bn).__name__))
+        return self.p.emit_conv(x, conv.weight, conv.bias, bn, _t3(conv.stride), _t3(conv.padding),
+                                _t3(conv.dilation), conv.groups, _act_code(act), residual, name)
+
+    def conv2plus1d(self, x, m, bn, act, residual, name):
+        # layers/convolutions.py:232-237: conv_t -> norm -> activation -> conv_xy
+        h = self.conv(x, m.conv_t, getattr(m, "norm", None), getattr(m, "activation", None), None, name + ".conv_t")
+        return self.conv(h, m.conv_xy, bn, act, residual, name + ".conv_xy")
+
+    def pool(self, x, m, name="pool"):
+        n = type(m).__name__
+        if n == "MaxPool3d":
+            if _t3(m.dilation) != (1, 1, 1) or m.ceil_mode:
+                raise NotImplementedError("MaxPool3d dilation/ceil_mode unsupported")
+            k = _t3(m.kernel_size)
+            s = _t3(m.stride if m.stride is not None else m.kernel_size)
+            return self.p.emit_pool(x, L.POOL_MAX, k, s, _t3(m.padding), name)
+        if n == "AvgPool3d":
+            if m.ceil_mode or not m.count_include_pad or m.divisor_override is not None:
+                raise NotImplementedError("AvgPool3d options unsupported")
+            k = _t3(m.kernel_size)
+            s = _t3(m.stride if m.stride is not None else m.kernel_size)
+            return self.p.emit_pool(x, L.POOL_AVG, k, s, _t3(m.padding), name)
+        if n == "AdaptiveAvgPool3d":
+            osz = _t3(m.output_size)
+            if osz != (1, 1, 1):
+                raise NotImplementedError("AdaptiveAvgPool3d output_size %s unsupported" % (osz,))
+            k = (x.T, x.H, x.W)
+            return self.p.emit_pool(x, L.POOL_AVG, k, k, (0, 0, 0), name)
+        if n == "Identity":
+            return x
+        raise NotImplementedError("pool module %s unsupported" % n)
+
+    # ---- blocks --------------------------------------------------------------------------
+    def lower(self, m, x, name=""):
+        n = type(m).__name__
+        fn = getattr(self, "lower_" + n, None)
+        if fn is None:
+            raise NotImplementedError("no B200 lowering for module %s (%s)" % (n, name))
+        return fn(m, x, name)
+
+    def lower_Identity(self, m, x, name):
+        return x
+
+    def lower_Dropout(self, m, x, name):
+        return x   # eval mode
+
+    def lower_MaxPool3d(self, m, x, name):
+        return self.pool(x, m, name)
+
+    lower_AvgPool3d = lower_MaxPool3d
+    lower_AdaptiveAvgPool3d = lower_MaxPool3d
+
+    def lower_Net(self, m, x, name):
+        # models/net.py:41-44
+        for i, blk in enumerate(m.blocks):
+            x = self.lower(blk, x, "%sblocks.%d" % (name + "." if name else "", i))
+        return x
+
+    def lower_Sequential(self, m, x, name):
+        for i, blk in enumerate(m):
+            x = self.lower(blk, x, "%s.%d" % (name, i))
+        return x
+
+    def lower_ResNetBasicStem(self, m, x, name):
+        # models/stem.py:252-260: conv -> norm -> activation -> pool
+        x = self.conv(x, m.conv, m.norm, m.activation, None, name + ".conv")
+        if getattr(m, "pool", None) is not None:
+            x = self.pool(x, m.pool, name + ".pool")
+        return x
+
+    def lower_ResStage(self, m, x, name):
+        for i, blk in enumerate(m.res_blocks):
+            x = self.lower(blk, x, "%s.res_blocks.%d" % (name, i))
+        return x
+
+    def lower_ResBlock(self, m, x, name):
+        # models/resnet.py:1179-1189; branch_fusion is x + y for every builder in scope.
+        if m.branch1_conv is not None:
+            shortcut = self.conv(x, m.branch1_conv, getattr(m, "branch1_norm", None), None, None, name + ".branch1")
+        else:
+            shortcut = x
+        return self.bottleneck(m.branch2, x, shortcut, m.activation, name + ".branch2")
+
+    def lower_BottleneckBlock(self, m, x, name):
+        return self.bottleneck(m, x, None, None, name)
+
+    def bottleneck(self, m, x, shortcut, final_act, name):
+        # models/resnet.py:1345-1365 with the block's residual add + activation fused into conv_c
+        if type(m).__name__ != "BottleneckBlock":
+            raise NotImplementedError("branch2 module %s unsupported" % type(m).__name__)
+        h = self.conv(x, m.conv_a, m.norm_a, m.act_a, None, name + ".conv_a")
+        norm_b, se = m.norm_b, None
+        if isinstance(norm_b, nn.Sequential):      # X3D: Sequential(BN|Identity, SE|Identity), models/x3d.py:199-208
+            assert len(norm_b) == 2
+            se = norm_b[1] if type(norm_b[1]).__name__ == "SqueezeExcitation" else None
+            if se is None and type(norm_b[1]).__name__ != "Identity":
+                raise NotImplementedError("norm_b[1] %s unsupported" % type(norm_b[1]).__name__)
+            norm_b = norm_b[0] if _is_bn(norm_b[0]) else None
+        if se is None:
+            h = self.conv(h, m.conv_b, norm_b, m.act_b, None, name + ".conv_b")
+        else:
+            h = self.conv(h, m.conv_b, norm_b, None, None, name + ".conv_b")
+            blk = se.block
+            if type(blk[1]).__name__ != "ReLU" or type(blk[3]).__name__ != "Sigmoid":
+                raise NotImplementedError("SqueezeExcitation variant unsupported")
+            h = self.p.emit_se_scale_act(h, blk[0].weight, blk[0].bias, blk[2].weight, blk[2].bias,
+                                         _act_code(m.act_b), name + ".se")
+        return self.conv(h, m.conv_c, m.norm_c, final_act, shortcut, name + ".conv_c")
+
+    def lower_MultiPathWayWithFuse(self, m, x, name):
+        # models/net.py:107-122
+        assert isinstance(x, list), "input for MultiPathWayWithFuse needs to be a list of tensors"
+        out = list(x)
+        for i, blk in enumerate(m.multipathway_blocks):
+            if blk is not None:
+                out[i] = self.lower(blk, x[i], "%s.multipathway_blocks.%d" % (name, i))
+        if m.multipathway_fusion is not None:
+            out = self.lower(m.multipathway_fusion, out, name + ".multipathway_fusion")
+        return out
+
+    def lower_FuseFastToSlow(self, m, x, name):
+        # models/slowfast.py:720-729; the concat is fused away (both producers write into one buffer)
+        x_s, x_f = x[0], x[1]
+        fuse = self.conv(x_f, m.conv_fast_to_slow, m.norm, m.activation, None, name + ".conv_fast_to_slow")
+        return [self.p.concat_channels([x_s, fuse]), x_f]
+
+    def lower_PoolConcatPathway(self, m, x, name):
+        # models/slowfast.py:608-620
+        outs = []
+        for i, xi in enumerate(x):
+            if xi is None:
+                continue
+            if m.pool is not None and m.pool[i] is not None:
+                xi = self.pool(xi, m.pool[i], "%s.pool.%d" % (name, i))
+            outs.append(xi)
+        cat = self.p.concat_channels(outs) if len(outs) > 1 else outs[0]
+        return [cat] if getattr(m, "retain_list", False) else cat
+
+    def lower_ProjectedPool(self, m, x, name):
+        # models/x3d.py:791-806
+        x = self.conv(x, m.pre_conv, m.pre_norm, m.pre_act, None, name + ".pre_conv")
+        x = self.pool(x, m.pool, name + ".pool")
+        return self.conv(x, m.post_conv, m.post_norm, m.post_act, None, name + ".post_conv")
+
+    def lower_ResNetBasicHead(self, m, x, name):
+        # models/head.py:371-391
+        pool = getattr(m, "pool", None)
+        if pool is not None:
+            x = self.lower(pool, x, name + ".pool") if type(pool).__name__ == "ProjectedPool" else self.pool(x, pool, name + ".pool")
+        proj = m.proj
+        if not isinstance(proj, nn.Linear):
+            raise NotImplementedError("head proj %s unsupported" % type(proj).__name__)
+        w = proj.weight.reshape(proj.out_features, proj.in_features, 1, 1, 1)
+        x = self.p.emit_conv(x, w, proj.bias, None, (1, 1, 1), (0, 0, 0), (1, 1, 1), 1, L.ACT_NONE, None, name + ".proj")
+        act = getattr(m, "activation", None)
+        softmax = False
+        if act is not None:
+            an = type(act).__name__
+            if an == "Softmax":
+                if act.dim != 1:
+                    raise NotImplementedError("head softmax dim != 1")
+                softmax = True
+            elif an == "Sigmoid":
+                x = self.p.emit_act(x, L.ACT_SIGMOID, name + ".activation")
+            else:
+                raise NotImplementedError("head activation %s unsupported" % an)
+        if getattr(m, "output_pool", None) is not None:
+            return self.p.emit_head_reduce(x, softmax, name + ".output_pool")
+        if softmax:
+            raise NotImplementedError("head softmax without output_pool unsupported")
+        return self.p.emit_to_ncdhw(x, name + ".to_ncdhw")
+
+
+class CompiledModel:
+    """A frozen (model, input shapes) plan: static input/output buffers + one CUDA graph."""
+
+    def __init__(self, model, example_inputs, dtype="f16", use_tcgen05=True, use_graph=True):
+        L.require_device()
+        multi = isinstance(example_inputs, (list, tuple))
+        ins = list(example_inputs) if multi else [example_inputs]
+        for t in ins:
+            if t.dim() != 5:
+                raise RuntimeError("expected 5-D (B, C, T, H, W) input, got %s" % (tuple(t.shape),))
+        device = ins[0].device
+        if device.type != "cuda":
+            raise RuntimeError("pytorchvideo_b200 has no CPU path: inputs must be CUDA tensors")
+        dt = {"f16": L.PV_F16, "f32": L.PV_F32}[dtype]
+        self.multi = multi
+        self.plan = Plan(device, dt, use_tcgen05)
+        self.static_in = [torch.empty(t.shape, dtype=t.dtype if t.dtype in (torch.float16, torch.float32) else torch.float32,
+                                      device=device) for t in ins]
+        low = Lowering(self.plan)
+        xs = [self.plan.emit_input_ncdhw(s, s.shape[1], 4 if s.shape[1] <= 4 else (s.shape[1] + 7) // 8 * 8)
+              for s in self.static_in]
+        out = low.lower(model, xs if multi else xs[0], "")
+        if isinstance(out, TRef):
+            out = self.plan.emit_to_ncdhw(out, "output.to_ncdhw")
+        if isinstance(out, list):
+            raise NotImplementedError("models returning a list are unsupported")
+        self.out_buf, self.out_shape = out
+        self.plan.finalize()
+        self.graph = None
+        self.use_graph = use_graph
+        self.key = tuple((tuple(t.shape), t.dtype) for t in ins)
+
+    def _capture(self):
+        stream = torch.cuda.Stream(device=self.plan.device)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            self.plan.run(stream.cuda_stream)       # warm-up (also sets func attributes outside capture)
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            self.plan.run(torch.cuda.current_stream().cuda_stream)
+        self.graph = g
+
+    def output_view(self):
+        return self.out_buf.tensor[: int(torch.tensor(self.out_shape).prod())].view(*self.out_shape)
+
+    def __call__(self, inputs):
+        ins = list(inputs) if self.multi else [inputs]
+        for s, t in zip(self.static_in, ins):
+            s.copy_(t, non_blocking=True)     # H2D or D2D staging into the plan's static input
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self.plan.run(torch.cuda.current_stream().cuda_stream)
+        return self.output_view()
+
+
+def compile_model(model, example_inputs, dtype="f16", use_tcgen05=True, use_graph=True):
+    return CompiledModel(model, example_inputs, dtype, use_tcgen05, use_graph)
+
+
+def lower_only(model, example_inputs, dtype="f16", use_tcgen05=True):
+    """Host-side dry run (works without a GPU): build the plan on the CPU and return
+    (plan, output_shape).  Nothing can be executed; used by the CPU test-suite to check the
+    lowering, shape inference, channel padding, concat fusion and algorithm selection."""
+    multi = isinstance(example_inputs, (list, tuple))
+    ins = list(example_inputs) if multi else [example_inputs]
+    plan = Plan("cpu", {"f16": L.PV_F16, "f32": L.PV_F32}[dtype], use_tcgen05)
+    xs = [plan.emit_input_ncdhw(torch.empty(t.shape, dtype=torch.float32), t.shape[1],
+                                4 if t.shape[1] <= 4 else (t.shape[1] + 7) // 8 * 8) for t in ins]
+    out = Lowering(plan).lower(model, xs if multi else xs[0], "")
+    if isinstance(out, TRef):
+        out = plan.emit_to_ncdhw(out, "output.to_ncdhw")
+    return plan, out[1]

@@ -1,0 +1,67 @@
+"""Host-side, one-off parameter preparation: BatchNorm folding and weight re-layout.
+
+This is set-up work done once per compiled plan (the analogue of the reference's
+``EfficientBlockBase.convert`` step, accelerator/efficient_blocks/efficient_block_base.py:8-35 and
+layers/accelerator/mobile_cpu/convolutions.py:120-175 where BN is fused at convert time); it is
+not on the per-clip hot path.
+"""
+import torch
+
+
+def pad8(c):
+    return (int(c) + 7) // 8 * 8
+
+
+def pad_to(c, m):
+    return (int(c) + m - 1) // m * m
+
+
+def fold_bn(conv_bias, bn, c_out, c_out_pad):
+    """Return (scale, bias) fp32 CPU tensors of length c_out_pad for y = conv*scale + bias.
+
+    Eval-mode BatchNorm: y = (x - mean) / sqrt(var + eps) * gamma + beta, folded over an optional
+    convolution bias.  Pad lanes get scale = bias = 0 so padded channels stay exactly zero.
+    """
+    scale = torch.ones(c_out, dtype=torch.float64)
+    bias = torch.zeros(c_out, dtype=torch.float64)
+    if conv_bias is not None:
+        bias = conv_bias.detach().double().cpu().clone()
+    if bn is not None:
+        var = bn.running_var.detach().double().cpu()
+        mean = bn.running_mean.detach().double().cpu()
+        gamma = bn.weight.detach().double().cpu() if bn.weight is not None else torch.ones(c_out, dtype=torch.float64)
+        beta = bn.bias.detach().double().cpu() if bn.bias is not None else torch.zeros(c_out, dtype=torch.float64)
+        s = gamma / torch.sqrt(var + bn.eps)
+        bias = (bias - mean) * s + beta
+        scale = s
+    out_s = torch.zeros(c_out_pad, dtype=torch.float32)
+    out_b = torch.zeros(c_out_pad, dtype=torch.float32)
+    out_s[:c_out] = scale.float()
+    out_b[:c_out] = bias.float()
+    return out_s, out_b
+
+
+def pack_dense_direct(w, ci_pad, co_pad, dtype):
+    """[Co, Ci, kt, kh, kw] -> [taps, ci_pad, co_pad] (co contiguous)."""
+    co, ci, kt, kh, kw = w.shape
+    out = torch.zeros(kt * kh * kw, ci_pad, co_pad, dtype=dtype)
+    out[:, :ci, :co] = w.detach().cpu().permute(2, 3, 4, 1, 0).reshape(kt * kh * kw, ci, co).to(dtype)
+    return out.contiguous()
+
+
+def pack_depthwise(w, c_pad, dtype):
+    """[C, 1, kt, kh, kw] -> [taps, c_pad]."""
+    c, one, kt, kh, kw = w.shape
+    assert one == 1
+    out = torch.zeros(kt * kh * kw, c_pad, dtype=dtype)
+    out[:, :c] = w.detach().cpu().reshape(c, kt * kh * kw).t().to(dtype)
+    return out.contiguous()
+
+
+def pack_dense_tcgen05(w, ci_pad64, co_pad):
+    """[Co, Ci, kt, kh, kw] -> [co_pad, taps * ci_pad64] f16, K-major (k = tap * ci_pad64 + ci)."""
+    co, ci, kt, kh, kw = w.shape
+    taps = kt * kh * kw
+    out = torch.zeros(co_pad, taps, ci_pad64, dtype=torch.float16)
+    out[:co, :, :ci] = w.detach().cpu().permute(0, 2, 3, 4, 1).reshape(co, taps, ci).to(torch.float16)
+    return out.reshape(co_pad, taps * ci_pad64).contiguous()

@@ -1,0 +1,298 @@
+"""Static execution plan: symbolic NDHWC tensors + a list of libpvb200 launches.
+
+A ``TRef`` is a channels-last-3d activation living in a (possibly shared) buffer:
+element (n,t,h,w,c) is at ``buf + ((n*T+t)*H+h)*W+w) * row_stride + ch_off + c``.  Because ops
+resolve pointers only when they run, a tensor can be *retargeted* into a channel slice of a wider
+buffer after it was produced - that is how ``torch.cat([slow, fuse], dim=1)``
+(reference models/slowfast.py:728) disappears: both producers write straight into the concat
+buffer.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+from . import packing as PK
+
+_TORCH_DT = {L.PV_F16: torch.float16, L.PV_F32: torch.float32}
+_ESIZE = {L.PV_F16: 2, L.PV_F32: 4}
+
+
+class Buf:
+    def __init__(self, numel, dt):
+        self.numel = int(numel)
+        self.dt = dt
+        self.tensor = None
+
+
+class TRef:
+    def __init__(self, buf, N, T, H, W, C, Cp=None, ch_off=0, row_stride=None):
+        self.buf = buf
+        self.N, self.T, self.H, self.W = int(N), int(T), int(H), int(W)
+        self.C = int(C)
+        self.Cp = PK.pad8(C) if Cp is None else int(Cp)
+        self.ch_off = int(ch_off)
+        self.row_stride = self.Cp if row_stride is None else int(row_stride)
+
+    @property
+    def npos(self):
+        return self.T * self.H * self.W
+
+    @property
+    def dt(self):
+        return self.buf.dt
+
+    def ptr(self):
+        return self.buf.tensor.data_ptr() + self.ch_off * _ESIZE[self.buf.dt]
+
+    def retarget(self, buf, ch_off, row_stride):
+        self.buf, self.ch_off, self.row_stride = buf, int(ch_off), int(row_stride)
+
+    def shape5(self):
+        return (self.N, self.C, self.T, self.H, self.W)
+
+    def __repr__(self):
+        return "TRef(N=%d,C=%d(%d),T=%d,H=%d,W=%d,off=%d,rs=%d)" % (
+            self.N, self.C, self.Cp, self.T, self.H, self.W, self.ch_off, self.row_stride)
+
+
+def _conv_out(i, k, s, p, d):
+    return (i + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class Plan:
+    """Collects launches; ``finalize`` allocates, ``run`` replays (eagerly or as a CUDA graph)."""
+
+    def __init__(self, device, dt=L.PV_F16, use_tcgen05=True):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.dt = dt
+        self.use_tcgen05 = bool(use_tcgen05) and dt == L.PV_F16
+        self.ops = []          # (name, closure(stream_ptr))
+        self.bufs = []
+        self.consts = []       # keep device parameter tensors alive
+        self.zero_bufs = []    # f32 accumulators that must be cleared every run (SE sums)
+        self.finalized = False
+        self.graph = None
+        self.stats = {"tcgen05": 0, "direct": 0, "depthwise": 0, "other": 0}
+
+    # ---- memory --------------------------------------------------------------------------
+    def new_buf(self, numel, dt=None):
+        b = Buf(numel, self.dt if dt is None else dt)
+        self.bufs.append(b)
+        return b
+
+    def new_tensor(self, N, T, H, W, C, Cp=None, dt=None):
+        Cp = PK.pad8(C) if Cp is None else Cp
+        b = self.new_buf(N * T * H * W * Cp, dt)
+        return TRef(b, N, T, H, W, C, Cp)
+
+    def const(self, t, dtype=None):
+        t = t.detach().to(device=self.device, dtype=dtype if dtype is not None else t.dtype).contiguous()
+        self.consts.append(t)
+        return t
+
+    def finalize(self):
+        for b in self.bufs:
+            if b.tensor is None:
+                # zero-init so that pad lanes / never-written slices are finite
+                b.tensor = torch.zeros(max(b.numel, 8), dtype=_TORCH_DT[b.dt], device=self.device)
+        self.finalized = True
+
+    def bytes_allocated(self):
+        return sum(b.numel * _ESIZE[b.dt] for b in self.bufs)
+
+    # ---- execution -----------------------------------------------------------------------
+    def add(self, name, fn, kind="other"):
+        self.ops.append((name, fn))
+        self.stats[kind] = self.stats.get(kind, 0) + 1
+
+    def run(self, stream_ptr):
+        assert self.finalized
+        for _, fn in self.ops:
+            fn(stream_ptr)
+
+    def num_launches(self):
+        return len(self.ops)
+
+    # =====================================================================================
+    # op emitters
+    # =====================================================================================
+    def emit_input_ncdhw(self, static_in, C, c_pad):
+        """static_in: torch tensor [N,C,T,H,W] (f32|f16) whose storage is fixed for the plan."""
+        N, Cc, T, H, W = static_in.shape
+        assert Cc == C
+        out = self.new_tensor(N, T, H, W, C, Cp=c_pad)
+        src_dt = L.PV_F32 if static_in.dtype == torch.float32 else L.PV_F16
+        lib = self.lib
+
+        def fn(stream):
+            L.check(lib.pv_ncdhw_to_ndhwc(static_in.data_ptr(), src_dt, out.ptr(), out.dt, N, C, T, H, W,
+                                          out.Cp, out.row_stride, stream), "pv_ncdhw_to_ndhwc")
+        self.add("ncdhw_to_ndhwc", fn)
+        return out
+
+    def emit_conv(self, x, weight, conv_bias, bn, stride, padding, dilation, groups, act=L.ACT_NONE,
+                  residual=None, name="conv", force_algo=None):
+        """Conv3d (+folded BN/bias) (+residual) (+activation).  weight: [Co, Ci/g, kt, kh, kw]."""
+        co, cig, kt, kh, kw = weight.shape
+        ci = cig * groups
+        if ci != x.C:
+            # same error type the reference raises for a wrong channel count
+            raise RuntimeError("conv %s expects %d input channels, got %d" % (name, ci, x.C))
+        st, sh, sw = stride
+        pt, ph, pw = padding
+        dlt, dlh, dlw = dilation
+        To, Ho, Wo = _conv_out(x.T, kt, st, pt, dlt), _conv_out(x.H, kh, sh, ph, dlh), _conv_out(x.W, kw, sw, pw, dlw)
+        if min(To, Ho, Wo) <= 0:
+            raise RuntimeError("conv %s: kernel larger than (padded) input" % name)
+        co_pad = PK.pad8(co)
+        y = self.new_tensor(x.N, To, Ho, Wo, co, Cp=co_pad)
+        scale, bias = PK.fold_bn(conv_bias, bn, co, co_pad)
+        scale_d, bias_d = self.const(scale), self.const(bias)
+        depthwise = groups != 1
+        if depthwise and not (groups == ci == co):
+            raise RuntimeError("conv %s: only groups==1 or depthwise (groups==Cin==Cout) is supported" % name)
+        tdt = _TORCH_DT[self.dt]
+        ci_pad = x.Cp
+        ci_pad64 = PK.pad_to(ci_pad, 64)
+
+        d = L.Conv3dDesc()
+        d.dtype = self.dt
+        d.N, d.Ti, d.Hi, d.Wi, d.Ci = x.N, x.T, x.H, x.W, ci_pad
+        d.To, d.Ho, d.Wo, d.Co = To, Ho, Wo, co_pad
+        d.kt, d.kh, d.kw = kt, kh, kw
+        d.st, d.sh, d.sw = st, sh, sw
+        d.pt, d.ph, d.pw = pt, ph, pw
+        d.dt, d.dh, d.dw = dlt, dlh, dlw
+        d.groups = ci_pad if depthwise else 1
+        d.act = act
+        d.has_residual = 1 if residual is not None else 0
+        d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+        d.res_row_stride = residual.row_stride if residual is not None else 0
+        d.ci_pad64 = ci_pad64
+
+        if depthwise:
+            algo, kind = L.ALGO_DIRECT, "depthwise"
+            w_d = self.const(PK.pack_depthwise(weight, co_pad, tdt))
+        else:
+            want_tc = self.use_tcgen05 and bool(self.lib.pv_conv3d_tcgen05_supported(C.byref(d)))
+            if force_algo is not None:
+                want_tc = force_algo == L.ALGO_TCGEN05
+            if want_tc:
+                algo, kind = L.ALGO_TCGEN05, "tcgen05"
+                w_d = self.const(PK.pack_dense_tcgen05(weight, ci_pad64, co_pad))
+            else:
+                algo, kind = L.ALGO_DIRECT, "direct"
+                w_d = self.const(PK.pack_dense_direct(weight, ci_pad, co_pad, tdt))
+        lib = self.lib
+
+        def fn(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride   # may have been retargeted
+            d.res_row_stride = residual.row_stride if residual is not None else 0
+            L.check(lib.pv_conv3d_fwd(C.byref(d), algo, x.ptr(), w_d.data_ptr(), scale_d.data_ptr(),
+                                      bias_d.data_ptr(), residual.ptr() if residual is not None else None,
+                                      y.ptr(), stream), "pv_conv3d_fwd(%s)" % name)
+        self.add(name, fn, kind)
+        return y
+
+    def emit_pool(self, x, mode, kernel, stride, padding, name="pool"):
+        kt, kh, kw = kernel
+        st, sh, sw = stride
+        pt, ph, pw = padding
+        To, Ho, Wo = (x.T + 2 * pt - kt) // st + 1, (x.H + 2 * ph - kh) // sh + 1, (x.W + 2 * pw - kw) // sw + 1
+        if min(To, Ho, Wo) <= 0:
+            raise RuntimeError("pool %s: kernel %s larger than input (%d,%d,%d)" % (name, kernel, x.T, x.H, x.W))
+        y = self.new_tensor(x.N, To, Ho, Wo, x.C, Cp=x.Cp)
+        d = L.Pool3dDesc()
+        d.dtype, d.mode = self.dt, mode
+        d.N, d.Ti, d.Hi, d.Wi, d.C = x.N, x.T, x.H, x.W, x.Cp
+        d.To, d.Ho, d.Wo = To, Ho, Wo
+        d.kt, d.kh, d.kw, d.st, d.sh, d.sw, d.pt, d.ph, d.pw = kt, kh, kw, st, sh, sw, pt, ph, pw
+        lib = self.lib
+
+        def fn(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+            L.check(lib.pv_pool3d_fwd(C.byref(d), x.ptr(), y.ptr(), stream), "pv_pool3d_fwd(%s)" % name)
+        self.add(name, fn)
+        return y
+
+    def emit_se_scale_act(self, x, w1, b1, w2, b2, act, name="se"):
+        """In-place y = act(x * sigmoid(W2 relu(W1 mean(x) + b1) + b2)) (fvcore SqueezeExcitation)."""
+        Cr, Cc = w1.shape[0], w1.shape[1]
+        assert Cc == x.C
+        Cp = x.Cp
+        w1p = torch.zeros(Cr, Cp, dtype=torch.float32)
+        w1p[:, :Cc] = w1.detach().float().cpu().reshape(Cr, Cc)
+        w2p = torch.zeros(Cp, Cr, dtype=torch.float32)
+        w2p[:Cc] = w2.detach().float().cpu().reshape(Cc, Cr)
+        b2p = torch.zeros(Cp, dtype=torch.float32)
+        b2p[:Cc] = b2.detach().float().cpu()
+        w1d, b1d, w2d, b2d = self.const(w1p), self.const(b1.detach().float().cpu()), self.const(w2p), self.const(b2p)
+        sums = self.new_buf(x.N * Cp, L.PV_F32)
+        gate = self.new_buf(x.N * Cp, L.PV_F32)
+        self.zero_bufs.append(sums)
+        lib = self.lib
+        npos = x.npos
+
+        def fn_sum(stream):
+            L.check(lib.pv_zero_f32(sums.tensor.data_ptr(), x.N * Cp, stream), "pv_zero_f32")
+            L.check(lib.pv_channel_sum(x.ptr(), x.dt, x.row_stride, x.N, npos, Cp, sums.tensor.data_ptr(), stream),
+                    "pv_channel_sum(%s)" % name)
+
+        def fn_gate(stream):
+            L.check(lib.pv_se_gate(sums.tensor.data_ptr(), npos, x.N, Cp, Cr, w1d.data_ptr(), b1d.data_ptr(),
+                                   w2d.data_ptr(), b2d.data_ptr(), Cp, gate.tensor.data_ptr(), stream),
+                    "pv_se_gate(%s)" % name)
+
+        def fn_apply(stream):
+            L.check(lib.pv_scale_act(x.ptr(), x.ptr(), x.dt, x.row_stride, x.row_stride, x.N, npos, Cp,
+                                     gate.tensor.data_ptr(), act, stream), "pv_scale_act(%s)" % name)
+        self.add(name + ".sum", fn_sum)
+        self.add(name + ".gate", fn_gate)
+        self.add(name + ".apply", fn_apply)
+        return x
+
+    def emit_act(self, x, act, name="act"):
+        lib = self.lib
+
+        def fn(stream):
+            L.check(lib.pv_scale_act(x.ptr(), x.ptr(), x.dt, x.row_stride, x.row_stride, x.N, x.npos, x.Cp,
+                                     None, act, stream), "pv_scale_act(%s)" % name)
+        self.add(name, fn)
+        return x
+
+    def emit_head_reduce(self, x, softmax, name="head_reduce"):
+        out = self.new_buf(x.N * x.C, L.PV_F32)
+        lib = self.lib
+
+        def fn(stream):
+            L.check(lib.pv_head_reduce(x.ptr(), x.dt, x.row_stride, x.N, x.npos, x.C, 1 if softmax else 0,
+                                       out.tensor.data_ptr(), stream), "pv_head_reduce(%s)" % name)
+        self.add(name, fn)
+        return out, (x.N, x.C)
+
+    def emit_to_ncdhw(self, x, name="to_ncdhw"):
+        out = self.new_buf(x.N * x.C * x.npos, L.PV_F32)
+        lib = self.lib
+
+        def fn(stream):
+            L.check(lib.pv_ndhwc_to_ncdhw(x.ptr(), x.dt, x.row_stride, out.tensor.data_ptr(), x.N, x.C, x.T,
+                                          x.H, x.W, stream), "pv_ndhwc_to_ncdhw(%s)" % name)
+        self.add(name, fn)
+        return out, x.shape5()
+
+    def concat_channels(self, parts):
+        """Fuse torch.cat(parts, dim=1): retarget every part into one wide buffer (no copy)."""
+        p0 = parts[0]
+        for p in parts:
+            assert (p.N, p.T, p.H, p.W) == (p0.N, p0.T, p0.H, p0.W), "concat shape mismatch"
+            assert p.C == p.Cp or p is parts[-1], "only the last concat part may carry channel padding"
+        c_total = sum(p.C for p in parts)
+        cp_total = PK.pad8(sum(p.Cp for p in parts[:-1]) + parts[-1].Cp)
+        buf = self.new_buf(p0.N * p0.npos * cp_total)
+        off = 0
+        for p in parts:
+            p.retarget(buf, off, cp_total)
+            off += p.Cp
+        return TRef(buf, p0.N, p0.T, p0.H, p0.W, c_total, Cp=cp_total, ch_off=0, row_stride=cp_total)

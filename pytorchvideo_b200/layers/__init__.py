@@ -1,0 +1,5 @@
+from .swish import Swish  # noqa: F401
+from .convolutions import Conv2plus1d, ConvReduce3D, create_conv_2plus1d  # noqa: F401
+from .squeeze_excitation import SqueezeExcitation  # noqa: F401
+from .utils import round_repeats, round_width, set_attributes  # noqa: F401
+from .drop_path import DropPath  # noqa: F401

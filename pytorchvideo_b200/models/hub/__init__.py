@@ -1,0 +1,65 @@
+"""Named model configurations (reference models/hub/*.py).  ``pretrained=True`` needs network
+access for the checkpoint download and is therefore rejected in this offline build; load a local
+``checkpoint["model_state"]`` with ``model.load_state_dict`` instead (keys are identical)."""
+import torch.nn as nn
+
+from ..csn import create_csn
+from ..r2plus1d import create_r2plus1d
+from ..resnet import create_resnet
+from ..slowfast import create_slowfast
+from ..x3d import create_x3d
+
+
+def _build(builder, pretrained, **kwargs):
+    if pretrained:
+        raise RuntimeError("pretrained weights require a download; load a local state_dict instead")
+    return builder(**kwargs)
+
+
+def slow_r50(pretrained=False, progress=True, **kw):
+    return _build(create_resnet, pretrained, stem_conv_kernel_size=(1, 7, 7), head_pool_kernel_size=(8, 7, 7),
+                  model_depth=50, **kw)
+
+
+def c2d_r50(pretrained=False, progress=True, **kw):
+    return _build(create_resnet, pretrained, stem_conv_kernel_size=(1, 7, 7), stage1_pool=nn.MaxPool3d,
+                  stage_conv_a_kernel_size=((1, 1, 1),) * 4, **kw)
+
+
+def i3d_r50(pretrained=False, progress=True, **kw):
+    return _build(create_resnet, pretrained, stem_conv_kernel_size=(5, 7, 7), stage1_pool=nn.MaxPool3d,
+                  stage_conv_a_kernel_size=((3, 1, 1), [(3, 1, 1), (1, 1, 1)], [(3, 1, 1), (1, 1, 1)],
+                                            [(1, 1, 1), (3, 1, 1)]), **kw)
+
+
+def slowfast_r50(pretrained=False, progress=True, **kw):
+    return _build(create_slowfast, pretrained, model_depth=50, slowfast_fusion_conv_kernel_size=(7, 1, 1), **kw)
+
+
+def slowfast_r101(pretrained=False, progress=True, **kw):
+    return _build(create_slowfast, pretrained, model_depth=101, slowfast_fusion_conv_kernel_size=(5, 1, 1), **kw)
+
+
+def x3d_xs(pretrained=False, progress=True, **kw):
+    return _build(create_x3d, pretrained, input_clip_length=4, input_crop_size=160, **kw)
+
+
+def x3d_s(pretrained=False, progress=True, **kw):
+    return _build(create_x3d, pretrained, input_clip_length=13, input_crop_size=160, **kw)
+
+
+def x3d_m(pretrained=False, progress=True, **kw):
+    return _build(create_x3d, pretrained, input_clip_length=16, input_crop_size=224, **kw)
+
+
+def x3d_l(pretrained=False, progress=True, **kw):
+    return _build(create_x3d, pretrained, input_clip_length=16, input_crop_size=312, depth_factor=5.0, **kw)
+
+
+def csn_r101(pretrained=False, progress=True, **kw):
+    return _build(create_csn, pretrained, model_depth=101, stem_pool=nn.MaxPool3d, head_pool_kernel_size=(4, 7, 7),
+                  **kw)
+
+
+def r2plus1d_r50(pretrained=False, progress=True, **kw):
+    return _build(create_r2plus1d, pretrained, dropout_rate=0.5, **kw)

@@ -1,0 +1,118 @@
+"""GPU: per-kernel parity, CUDA path (through the C ABI) vs the CPU oracle arithmetic (torch fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _bn(c, seed):
+    g = torch.Generator().manual_seed(seed)
+    bn = nn.BatchNorm3d(c).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5); bn.bias.copy_(torch.rand(c, generator=g) - 0.5)
+        bn.running_mean.copy_(torch.rand(c, generator=g) - 0.5); bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    return bn
+
+
+def _ref_conv(x, w, b, bn, stride, padding, dilation, groups, act, res):
+    y = F.conv3d(x, w, b, stride, padding, dilation, groups)
+    if bn is not None:
+        y = bn(y)
+    if res is not None:
+        y = y + res
+    if act == "relu":
+        y = F.relu(y)
+    elif act == "swish":
+        y = y * torch.sigmoid(y)
+    return y
+
+
+CONV_CASES = [
+    # (N, Ci, T, H, W, Co, k, s, p, groups, act, residual)
+    (2, 3, 4, 20, 20, 24, (1, 3, 3), (1, 2, 2), (0, 1, 1), 1, "relu", False),       # X3D stem spatial
+    (1, 3, 6, 18, 18, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 1, "relu", False),        # SlowFast fast stem
+    (2, 24, 4, 10, 10, 54, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "relu", False),      # pointwise, odd widths
+    (2, 54, 4, 10, 10, 24, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, None, True),         # project + residual
+    (1, 64, 4, 12, 12, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "relu", False),      # conv_b
+    (1, 64, 4, 12, 12, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1), 1, "relu", False),      # strided conv_b
+    (1, 128, 6, 7, 7, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, "relu", False),       # temporal conv_a
+    (1, 8, 16, 6, 6, 16, (7, 1, 1), (4, 1, 1), (3, 0, 0), 1, "relu", False),        # lateral fusion conv
+    (2, 80, 2, 8, 8, 256, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, None, False),         # strided shortcut
+    (2, 56, 4, 9, 9, 56, (3, 3, 3), (1, 1, 1), (1, 1, 1), 56, "swish", False),      # depthwise
+    (2, 24, 6, 9, 9, 24, (5, 1, 1), (1, 1, 1), (2, 0, 0), 24, "relu", False),       # depthwise temporal
+    (1, 16, 4, 9, 9, 16, (3, 3, 3), (2, 2, 2), (1, 1, 1), 16, None, False),         # depthwise strided (CSN)
+]
+
+
+@pytest.mark.parametrize("dtype,algo", [("f32", "direct"), ("f16", "direct"), ("f16", "tcgen05")])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
+def test_conv3d_bn_act(case, dtype, algo):
+    from pytorchvideo_b200 import ops
+    N, Ci, T, H, W, Co, k, s, p, groups, act, use_res = case
+    if algo == "tcgen05" and (groups != 1 or Ci % 8 != 0):
+        pytest.skip("tensor-core path is dense, Ci%8==0")
+    g = torch.Generator().manual_seed(sum(v for v in case[:6]))
+    x = torch.randn(N, Ci, T, H, W, generator=g)
+    w = torch.randn(Co, Ci // groups, *k, generator=g) * (2.0 / (Ci // groups * np.prod(k))) ** 0.5
+    bn = _bn(Co, 5)
+    if dtype == "f16":   # compare against the oracle on the same f16-rounded operands
+        x, w = x.half().float(), w.half().float()
+    with torch.no_grad():
+        y0 = F.conv3d(x, w, None, s, p, (1, 1, 1), groups)
+        res = torch.randn(y0.shape, generator=g) if use_res else None
+        if res is not None and dtype == "f16":
+            res = res.half().float()
+        ref = _ref_conv(x, w, None, bn, s, p, (1, 1, 1), groups, act, res)
+    got, stats = ops.conv3d_bn_act(x.to(_dev()), w, None, bn, s, p, (1, 1, 1), groups, act,
+                                   None if res is None else res.to(_dev()), dtype, algo)
+    if algo == "tcgen05":
+        assert stats["tcgen05"] == 1
+    got = got.cpu()
+    assert got.shape == ref.shape
+    if dtype == "f32":
+        assert torch.allclose(got, ref, rtol=1e-3, atol=1e-4), float((got - ref).abs().max())
+    else:
+        # f16 storage: one rounding of the stored output (2^-11 relative) on top of fp32 accumulation
+        err = (got - ref).abs()
+        tol = 1e-3 * ref.abs() + 1e-3 * float(ref.abs().max()) * 0.5 + 1e-4
+        assert bool((err <= tol).all()), float(err.max())
+
+
+@pytest.mark.parametrize("mode,k,s,p", [("max", (1, 3, 3), (1, 2, 2), (0, 1, 1)), ("avg", (4, 5, 5), (1, 1, 1), (0, 0, 0)),
+                                        ("max", (3, 3, 3), (1, 2, 2), (1, 1, 1)), ("avg", (2, 1, 1), (2, 1, 1), (0, 0, 0))])
+def test_pool3d(mode, k, s, p):
+    from pytorchvideo_b200 import ops
+    x = torch.randn(2, 24, 4, 11, 11, generator=torch.Generator().manual_seed(3))
+    ref = F.max_pool3d(x, k, s, p) if mode == "max" else F.avg_pool3d(x, k, s, p)
+    got = ops.pool3d(x.to(_dev()), mode, k, s, p, "f32").cpu()
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_layernorm():
+    from pytorchvideo_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(77, 96, generator=g) * 3 + 1
+    gamma, beta = torch.rand(96, generator=g) + 0.5, torch.rand(96, generator=g) - 0.5
+    ref = F.layer_norm(x, (96,), gamma, beta, 1e-6)
+    got = ops.layernorm(x.to(_dev()), gamma, beta, 1e-6, "f32").cpu()
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("Nq,Nk,resid", [(50, 50, False), (393, 393, False), (130, 37, True)])
+def test_attention(Nq, Nk, resid):
+    from pytorchvideo_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, H, D = 2, 2, 96
+    q, k, v = (torch.randn(B, H, n, D, generator=g) for n in (Nq, Nk, Nk))
+    scale = D ** -0.5
+    attn = ((q * scale) @ k.transpose(-2, -1)).softmax(-1)
+    ref = attn @ v + (q if resid else 0)
+    got = ops.attention(q.to(_dev()), k.to(_dev()), v.to(_dev()), scale, resid, "f32").cpu()
+    assert torch.allclose(got, ref, rtol=1e-3, atol=1e-4), float((got - ref).abs().max())

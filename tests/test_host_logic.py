@@ -1,0 +1,113 @@
+"""CPU: host-side logic of the engine (packing, BN folding, lowering dry-run, sharding)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from pytorchvideo_b200 import _lib as L
+from pytorchvideo_b200 import parallel as PAR
+from pytorchvideo_b200 import testing as TS
+from pytorchvideo_b200.engine import packing as PK
+from pytorchvideo_b200.engine.lower import lower_only
+import pytorchvideo_b200.models.hub as PH
+from pytorchvideo_b200.transforms import functional as Fv
+from pytorchvideo_b200.transforms import FusedClipTransform
+
+
+def test_fold_bn_matches_torch():
+    torch.manual_seed(0)
+    conv = nn.Conv3d(6, 10, 1, bias=True)
+    bn = nn.BatchNorm3d(10).eval()
+    bn.running_mean.uniform_(-1, 1); bn.running_var.uniform_(0.5, 2); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.uniform_(-1, 1)
+    x = torch.randn(2, 6, 2, 3, 3)
+    ref = bn(conv(x))
+    s, b = PK.fold_bn(conv.bias, bn, 10, 16)
+    got = F.conv3d(x, conv.weight) * s[:10].view(1, -1, 1, 1, 1) + b[:10].view(1, -1, 1, 1, 1)
+    assert torch.allclose(ref, got, atol=1e-5)
+    assert float(s[10:].abs().sum()) == 0 and float(b[10:].abs().sum()) == 0
+
+
+def test_weight_packing_layouts():
+    w = torch.randn(10, 6, 3, 1, 3)
+    d = PK.pack_dense_direct(w, 8, 16, torch.float32)
+    assert d.shape == (9, 8, 16)
+    assert torch.equal(d[4, 2, 7], w[7, 2, 1, 0, 1]) and float(d[:, 6:, :].abs().sum()) == 0
+    t = PK.pack_dense_tcgen05(w, 64, 16)
+    assert t.shape == (16, 9 * 64) and t.dtype == torch.float16
+    assert t[7, 4 * 64 + 2] == w[7, 2, 1, 0, 1].half() and float(t[10:].abs().sum()) == 0
+    dw = PK.pack_depthwise(torch.randn(6, 1, 3, 3, 3), 8, torch.float16)
+    assert dw.shape == (27, 8)
+
+
+def test_tcgen05_support_predicate_is_host_only():
+    lib = L.load()
+    d = L.Conv3dDesc()
+    d.dtype, d.N, d.Ti, d.Hi, d.Wi, d.Ci = L.PV_F16, 2, 8, 14, 14, 256
+    d.To, d.Ho, d.Wo, d.Co = 8, 14, 14, 256
+    d.kt, d.kh, d.kw, d.st, d.sh, d.sw, d.pt, d.ph, d.pw, d.dt, d.dh, d.dw = 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1
+    d.groups, d.x_row_stride, d.y_row_stride, d.ci_pad64 = 1, 256, 256, 256
+    assert lib.pv_conv3d_tcgen05_supported(C.byref(d)) == 1
+    d.dtype = L.PV_F32
+    assert lib.pv_conv3d_tcgen05_supported(C.byref(d)) == 0
+    d.dtype, d.x_row_stride = L.PV_F16, 260
+    assert lib.pv_conv3d_tcgen05_supported(C.byref(d)) == 0
+
+
+def test_lowering_slowfast_dry_run():
+    m = PH.slowfast_r50().eval()
+    clip = torch.zeros(2, 3, 32, 224, 224)
+    plan, out_shape = lower_only(m, TS.slowfast_inputs(clip))
+    assert out_shape == (2, 400)
+    names = [n for n, _ in plan.ops]
+    # 2 stems (conv+pool each), 4 fusion convs, (3+4+6+3)*2 blocks * 3 convs + 8 shortcuts, head
+    n_conv = plan.stats["tcgen05"] + plan.stats["direct"]
+    assert n_conv == 2 + 4 + 2 * (16 * 3 + 4) + 1
+    assert plan.stats["tcgen05"] >= 100           # every C_in%8==0 dense conv goes to the tensor cores
+    assert any(n.endswith("multipathway_fusion.conv_fast_to_slow") for n in names)
+    assert "blocks.6.output_pool" in names
+
+
+def test_lowering_f32_mode_uses_no_tensor_core_path():
+    m = PH.x3d_xs().eval()
+    plan, out_shape = lower_only(m, torch.zeros(1, 3, 4, 160, 160), dtype="f32")
+    assert out_shape == (1, 400) and plan.stats["tcgen05"] == 0 and plan.stats["depthwise"] == 27
+
+
+def test_wrong_channel_count_raises_runtimeerror():
+    # reference behaviour asserted by tests/test_models_x3d.py:64-67 and test_models_slowfast.py:119-122
+    m = PH.x3d_xs().eval()
+    with pytest.raises(RuntimeError):
+        lower_only(m, torch.zeros(1, 4, 4, 160, 160))
+
+
+def test_concat_is_fused_into_channel_slices():
+    m = PH.slowfast_r50().eval()
+    plan, _ = lower_only(m, TS.slowfast_inputs(torch.zeros(1, 3, 32, 224, 224)))
+    # after stage 0 the slow tensor (64 ch) and the fused lateral (16 ch) share an 80-wide buffer
+    from pytorchvideo_b200.engine.plan import TRef
+    assert not any(n.startswith("cat") for n, _ in plan.ops)
+
+
+def test_transform_plan_matches_reference_formulas():
+    tr = FusedClipTransform(16, (0.45,) * 3, (0.225,) * 3, short_side=256, crop=("center", 224))
+    idx, hw, win = tr.plan((3, 64, 1080, 1920))
+    assert idx.tolist() == [0, 4, 8, 12, 16, 21, 25, 29, 33, 37, 42, 46, 50, 54, 58, 63]
+    assert hw == (256, 455) and win == (16, 116, 224, 224)
+    # host tables are the oracle's
+    from oracle import transforms_ref as O
+    for a, b in zip(Fv.bilinear_table(1920, 455), O.bilinear_table(1920, 455)):
+        assert np.array_equal(a, b)
+    assert Fv.uniform_crop_window(20, 40, 16, 2) == O.uniform_crop_window(20, 40, 16, 2)
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for n in (0, 1, 7, 8, 64, 257):
+        for w in (1, 2, 3, 8):
+            spans = [PAR.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,125 @@
+"""CPU: the oracle (oracle/) is pinned to the reference.
+
+* golden vectors under tests/golden/ were produced by the REAL reference (oracle/gen_golden.py,
+  run where /root/reference exists, asserting oracle == reference bit-for-bit);
+* here the oracle is re-run on the regenerated seeded weights/inputs and must reproduce them;
+* the reference's own known-answer tests for the transform path are restated verbatim.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import transforms_ref as O
+from oracle.interp import oracle_forward
+from pytorchvideo_b200 import testing as TS
+import pytorchvideo_b200.models.hub as PH
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gold(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+# ---- reference known answers (reference tests/test_transforms.py) -------------------------------
+def test_uniform_temporal_subsample_known_answer():
+    # tests/test_transforms.py:85-102: 20 frames -> 10 samples
+    assert O.linspace_indices(20, 10).tolist() == [0, 2, 4, 6, 8, 10, 12, 14, 16, 19]
+    assert O.linspace_indices(20, 20).tolist() == list(range(20))       # identity
+    assert O.linspace_indices(20, 1).tolist() == [0]                    # single sample = first frame
+    # SlowFast slow pathway of a 32-frame clip (datamodule/transforms.py:129-136)
+    assert O.linspace_indices(32, 8).tolist() == [0, 4, 8, 13, 17, 22, 26, 31]
+    assert O.linspace_indices(64, 16).tolist() == [0, 4, 8, 12, 16, 21, 25, 29, 33, 37, 42, 46, 50, 54, 58, 63]
+
+
+def test_indices_match_torch_linspace_everywhere():
+    for t in range(1, 301, 1):
+        for n in (1, 2, 3, 5, 8, 13, 16, 27, 29, 32, 64, 100, 128):
+            ref = torch.clamp(torch.linspace(0, t - 1, n), 0, t - 1).long().numpy()
+            assert np.array_equal(ref, O.linspace_indices(t, n)), (t, n)
+
+
+def test_index_goldens_from_reference():
+    g = _gold("transforms.pt")["indices"]
+    for key, idx in g.items():
+        t, n = (int(v) for v in key.split("_"))
+        assert np.array_equal(O.linspace_indices(t, n), idx), key
+
+
+def test_short_side_scale_shapes_known_answer():
+    # tests/test_transforms.py:104-144: 20x10 -> short side 5 -> 10x5 ; 10x20 -> 5x10
+    assert O.short_side_size(20, 10, 5) == (10, 5)
+    assert O.short_side_size(10, 20, 5) == (5, 10)
+    assert O.short_side_size(1080, 1920, 256) == (256, 455)
+
+
+def test_center_crop_known_answer():
+    # tests/test_transforms.py:334-346: 30x40 frame, crop 10 -> window [10:20, 15:25]
+    assert O.center_crop_window(30, 40, 10) == (10, 15, 10, 10)
+
+
+def test_uniform_crop_goldens():
+    g = _gold("transforms.pt")["uniform_crop"]
+    for key, (y, x) in g.items():
+        h, w, size, idx = (int(v) for v in key.split("_"))
+        assert O.uniform_crop_window(h, w, size, idx)[:2] == (y, x)
+
+
+def test_bilinear_table_matches_aten():
+    import torch.nn.functional as F
+    for (i, o) in [(1080, 256), (1920, 455), (320, 224), (7, 13), (224, 224), (61, 30)]:
+        eye = torch.eye(i).view(1, i, 1, i)
+        w = F.interpolate(eye, size=(1, o), mode="bilinear", align_corners=False)[0, :, 0, :].numpy()
+        i0, i1, l1 = O.bilinear_table(i, o)
+        W = np.zeros((i, o), np.float32)
+        for j in range(o):
+            W[i0[j], j] += np.float32(1) - l1[j]
+            W[i1[j], j] += l1[j]
+        assert np.array_equal(W, w), (i, o)
+
+
+def test_transform_chain_small_goldens():
+    for c in _gold("transforms.pt")["chain_small"]:
+        clip = TS.synthetic_u8_clip(c["T"], c["H"], c["W"], seed=c["seed"])
+        out = O.val_chain(clip.numpy(), c["n"], c["mean"], c["std"], c["side"], c["crop"])
+        np.testing.assert_allclose(out, c["out"].numpy(), rtol=0, atol=2e-6)
+
+
+def test_normalize_zero_mean_unit_std_property():
+    # tests/test_transforms.py:324-332 style property: normalising by the clip's own stats
+    x = np.random.RandomState(0).rand(3, 4, 8, 8).astype(np.float32)
+    m, s = x.mean(axis=(1, 2, 3)), x.std(axis=(1, 2, 3))
+    y = O.normalize(x, m, s)
+    np.testing.assert_allclose(y.mean(axis=(1, 2, 3)), 0, atol=1e-5)
+    np.testing.assert_allclose(y.std(axis=(1, 2, 3)), 1, atol=1e-5)
+
+
+# ---- models ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["x3d_xs", "slow_r50", "r2plus1d_r50"])
+def test_oracle_reproduces_reference_model_goldens(case):
+    g = _gold("model_%s.pt" % case)
+    hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
+    model = getattr(PH, hub)(**kw)
+    TS.randomize_model(model, seed=g["weight_seed"])
+    assert abs(TS.state_checksum(model) - g["state_checksum"]) <= 1e-6 * abs(g["state_checksum"])
+    clip = TS.synthetic_clip(B, T, H, W, seed=g["input_seed"])
+    np.testing.assert_allclose(TS.tensor_checksum(clip), g["input_checksum"], rtol=1e-12)
+    out = oracle_forward(model, TS.slowfast_inputs(clip) if is_sf else clip)
+    ref = g["output"]
+    # same ATen ops in the same order; allow for a different CPU's summation order
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_state_dict_keys_follow_the_reference_naming():
+    m = PH.slowfast_r50()
+    keys = set(m.state_dict())
+    for k in ["blocks.0.multipathway_blocks.0.conv.weight", "blocks.0.multipathway_fusion.conv_fast_to_slow.weight",
+              "blocks.1.multipathway_blocks.0.res_blocks.0.branch1_conv.weight",
+              "blocks.1.multipathway_blocks.1.res_blocks.2.branch2.norm_c.running_var", "blocks.6.proj.bias"]:
+        assert k in keys
+    x = PH.x3d_xs()
+    assert "blocks.1.res_blocks.0.branch2.norm_b.1.block.0.weight" in x.state_dict()
+    assert "blocks.0.conv.conv_t.weight" in x.state_dict() and "blocks.5.pool.pre_conv.weight" in x.state_dict()
