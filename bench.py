@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py - headline metric of BASELINE.json: clips/sec forward on synthetic clips.
+
+Workload at every N: SlowFast-8x8-R50 eval forward, batch 8 per GPU, 3x32x224x224 synthetic clips
+(slow 8 + fast 32 frames) - BASELINE.json configs[1].  One "step" = one forward pass over one
+batch; weak scaling (per-GPU batch fixed), clips sharded across ranks, one NCCL all-gather of the
+[8,400] logits per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement): value = whole-job
+clips/s with inputs resident in HBM; e2e = same through the public model call with pinned HOST
+inputs (H2D + D2H inside the timed region); roofline for the dominant kernel
+(conv3d_igemm_kernel, tensor-bound) from per-launch CUDA-event times; cpu_baseline = the oracle
+port of the reference forward timed on this box's host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (hub builder, per-GPU batch, T, H, W, slowfast?)
+    "slowfast_r50": ("slowfast_r50", 8, 32, 224, 224, True),
+    "x3d_m": ("x3d_m", 32, 16, 224, 224, False),
+    "x3d_xs": ("x3d_xs", 8, 4, 160, 160, False),
+    "slow_r50": ("slow_r50", 8, 8, 224, 224, False),
+    "csn_r101": ("csn_r101", 8, 32, 224, 224, False),
+    "r2plus1d_r50": ("r2plus1d_r50", 8, 16, 224, 224, False),
+}
+METRIC = "clips/sec forward (synthetic 3xTx224^2)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "tflops_burst": d.get("bf16_tflops", 1590.0),
+                "tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median of the upper half ~ clocks under load (idle samples before/after drag the median down)
+        med = sm[len(sm) * 3 // 4] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model_and_inputs(workload, batch_override=None):
+    import pytorchvideo_b200.models.hub as H
+    from pytorchvideo_b200 import testing as TS
+    hub, B, T, Hh, W, is_sf = WORKLOADS[workload]
+    if batch_override:
+        B = batch_override
+    model = TS.randomize_model(getattr(H, hub)(), seed=1234).eval()
+    return model, B, T, Hh, W, is_sf
+
+
+def make_inputs(B, T, H, W, is_sf, seed):
+    from pytorchvideo_b200 import testing as TS
+    clip = TS.synthetic_clip(B, T, H, W, seed=seed)
+    return TS.slowfast_inputs(clip) if is_sf else clip
+
+
+def cpu_baseline(model, T, H, W, is_sf, budget_s=20.0):
+    """Oracle port of the reference forward on the host cores, bounded sample (1 warm-up + timed)."""
+    from oracle.interp import oracle_forward
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = 1
+    inp = make_inputs(b, T, H, W, is_sf, seed=7)
+    t0 = time.perf_counter()
+    oracle_forward(model, inp)
+    one = time.perf_counter() - t0
+    b = max(1, min(8, int(budget_s / max(one, 1e-3) / 2)))
+    inp = make_inputs(b, T, H, W, is_sf, seed=7)
+    best = None
+    reps = 2 if one * b * 2 < budget_s else 1
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle_forward(model, inp)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": b / best, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": "%d clip(s) per forward, best of %d, torch fp32 CPU, %d threads" % (b, reps, cores)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
+    itself is a Python library that cannot travel to this box).  Rank 0 only."""
+    if rank != 0:
+        return
+    model, B, T, H, W, is_sf = build_model_and_inputs(args.workload)
+    from oracle.interp import oracle_forward
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = 1   # bounded sample: one clip per step
+    inp = make_inputs(b, T, H, W, is_sf, seed=7)
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle_forward(model, inp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_forward(model, inp)
+    dt = time.perf_counter() - t0
+    v = b * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "clip": [3, T, H, W], "batch_per_step": b,
+                       "note": "reference CPU forward restated in oracle/interp.py (bit-exact vs the reference in the authoring container)"},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": "%d clip per step x %d steps" % (b, args.steps)},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="slowfast_r50", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f16", choices=["f16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-kernels", default=None, help="write per-launch times (JSON) to this path")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from pytorchvideo_b200 import parallel as PAR
+    rank, local_rank, world = PAR.env_world()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from pytorchvideo_b200 import _lib
+    from pytorchvideo_b200.engine import compile_model
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    if world > 1:
+        PAR.init_process_group("nccl")
+
+    model, B, T, H, W, is_sf = build_model_and_inputs(args.workload)
+    host_in = make_inputs(B, T, H, W, is_sf, seed=42 + rank)          # this rank's shard of the global batch
+    host_list = host_in if is_sf else [host_in]
+    pinned = [t.pin_memory() for t in host_list]
+    dev_in = [t.to(dev) for t in host_list]
+    cm = compile_model(model, dev_in if is_sf else dev_in[0], dtype=args.precision, use_graph=True)
+    num_classes = cm.out_shape[1]
+    gathered = torch.empty((world * B, num_classes), dtype=torch.float32, device=dev)
+
+    def step_resident():
+        out = cm(dev_in if is_sf else dev_in[0])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+            return gathered
+        return out
+
+    host_out = torch.empty((B, num_classes), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        # the public call with HOST inputs: H2D of the clips, forward, D2H of the logits
+        out = cm(pinned if is_sf else pinned[0])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches_before = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in pinned)
+    d2h = host_out.numel() * host_out.element_size()
+
+    # ---- roofline of the dominant kernel (per-launch CUDA events, eager replay on torch's stream)
+    per_op = cm.plan.profile(iters=3)
+    kinds = {}
+    for m, t in zip(cm.plan.meta, per_op):
+        k = kinds.setdefault(m["kind"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        k["ms"] += t; k["flops"] += m["flops"]; k["bytes"] += m["bytes"]; k["n"] += 1
+    total_ms = sum(per_op)
+    peaks = load_peaks()
+    dom = max(kinds, key=lambda k: kinds[k]["ms"])
+    kd = kinds[dom]
+    if dom in ("tcgen05",):
+        achieved = kd["flops"] / (kd["ms"] * 1e-3) / 1e12
+        peak = peaks["tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv3d_igemm_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "launches": kd["n"], "avg_launch_us": kd["ms"] / kd["n"] * 1e3,
+                "share_of_step": kd["ms"] / total_ms, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
+    else:
+        achieved = kd["bytes"] / (kd["ms"] * 1e-3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "launches": kd["n"],
+                "avg_launch_us": kd["ms"] / kd["n"] * 1e3, "share_of_step": kd["ms"] / total_ms,
+                "peak_source": peaks["source"]}
+    model_flops = sum(m["flops"] for m in cm.plan.meta)
+    whole = {"model_gflop_per_clip": model_flops / B / 1e9,
+             "model_tflops_achieved": model_flops / (ms_per_step * 1e-3) / 1e12,
+             "frac_of_tensor_peak": model_flops / (ms_per_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
+             "kernel_ms_by_kind": {k: round(v["ms"], 4) for k, v in kinds.items()},
+             "sum_kernel_ms": round(total_ms, 4)}
+    if args.dump_kernels and rank == 0:
+        json.dump([{**m, "ms": t} for m, t in zip(cm.plan.meta, per_op)], open(args.dump_kernels, "w"), indent=0)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(model, T, H, W, is_sf)
+        line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "clip": [3, T, H, W], "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": "dp%d" % world, "l2": "inputs (%.0f MB/step) larger than L2; CUDA-graph replay" % (h2d / 1e6),
+                           "weights": "random (seeded), BN stats randomised"},
+                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": args.steps * cm.plan.num_launches(),
+                "launches_per_step": cm.plan.num_launches(),
+                "roofline": roof, "whole_model": whole, "clocks": clocks}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

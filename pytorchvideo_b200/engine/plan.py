@@ -69,6 +69,7 @@ class Plan:
         self.dt = dt
         self.use_tcgen05 = bool(use_tcgen05) and dt == L.PV_F16
         self.ops = []          # (name, closure(stream_ptr))
+        self.meta = []         # per-op {name, kind, flops, bytes} (algorithmic figures for the roofline)
         self.bufs = []
         self.consts = []       # keep device parameter tensors alive
         self.zero_bufs = []    # f32 accumulators that must be cleared every run (SE sums)
@@ -103,9 +104,31 @@ class Plan:
         return sum(b.numel * _ESIZE[b.dt] for b in self.bufs)
 
     # ---- execution -----------------------------------------------------------------------
-    def add(self, name, fn, kind="other"):
+    def add(self, name, fn, kind="other", flops=0.0, nbytes=0.0):
         self.ops.append((name, fn))
+        self.meta.append({"name": name, "kind": kind, "flops": float(flops), "bytes": float(nbytes)})
         self.stats[kind] = self.stats.get(kind, 0) + 1
+
+    def profile(self, iters=3):
+        """Per-launch device times (ms, mean over `iters`) measured with CUDA events on the
+        launching stream (torch's current stream); eager replay, one event pair per launch."""
+        assert self.finalized
+        stream = torch.cuda.current_stream(self.device)
+        sp = stream.cuda_stream
+        n = len(self.ops)
+        acc = [0.0] * n
+        for it in range(iters + 1):
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for (e0, e1), (_, fn) in zip(evs, self.ops):
+                e0.record(stream)
+                fn(sp)
+                e1.record(stream)
+            stream.synchronize()
+            if it == 0:
+                continue   # warm-up pass
+            for i, (e0, e1) in enumerate(evs):
+                acc[i] += e0.elapsed_time(e1)
+        return [a / iters for a in acc]
 
     def run(self, stream_ptr):
         assert self.finalized
@@ -193,7 +216,11 @@ class Plan:
             L.check(lib.pv_conv3d_fwd(C.byref(d), algo, x.ptr(), w_d.data_ptr(), scale_d.data_ptr(),
                                       bias_d.data_ptr(), residual.ptr() if residual is not None else None,
                                       y.ptr(), stream), "pv_conv3d_fwd(%s)" % name)
-        self.add(name, fn, kind)
+        esz = _ESIZE[self.dt]
+        m_out = x.N * To * Ho * Wo
+        flops = 2.0 * m_out * co * cig * kt * kh * kw
+        nbytes = (x.N * x.npos * ci + m_out * co * (2 if residual is not None else 1)) * esz + weight.numel() * esz
+        self.add(name, fn, kind, flops, nbytes)
         return y
 
     def emit_pool(self, x, mode, kernel, stride, padding, name="pool"):
