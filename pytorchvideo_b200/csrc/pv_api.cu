@@ -23,6 +23,12 @@ int conv3d_direct_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
 int conv3d_tcgen05_supported(const pv_conv3d_desc* d, char* why, size_t why_len);
 int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
                           const float* bias, const void* residual, void* y, cudaStream_t s);
+int conv3d_gather_supported(const pv_conv3d_desc* d);
+int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                         const float* bias, const void* residual, void* y, cudaStream_t s);
+// narrow inputs (C_in < 64, weights packed with the un-padded per-tap K extent) take the gather-fed
+// variant, everything else the TMA-fed one
+static bool wants_gather(const pv_conv3d_desc* d) { return d->Ci < 64 && d->ci_pad64 == d->Ci; }
 
 }  // namespace pv
 
@@ -53,6 +59,7 @@ extern "C" int pv_device_info(int* sm_count, int* cc) {
 
 extern "C" int pv_conv3d_tcgen05_supported(const pv_conv3d_desc* d) {
   if (!d) return 0;
+  if (pv::wants_gather(d)) return pv::conv3d_gather_supported(d);
   return pv::conv3d_tcgen05_supported(d, nullptr, 0);
 }
 
@@ -65,8 +72,11 @@ extern "C" int pv_conv3d_fwd(const pv_conv3d_desc* d, int algo, const void* x, c
   PV_CHECK_ARG(!d->has_residual || residual, "has_residual set but residual is null");
   cudaStream_t s = (cudaStream_t)stream;
   if (algo == PV_ALGO_AUTO)
-    algo = (d->groups == 1 && pv::conv3d_tcgen05_supported(d, nullptr, 0)) ? PV_ALGO_TCGEN05 : PV_ALGO_DIRECT;
-  if (algo == PV_ALGO_TCGEN05) return pv::conv3d_tcgen05_launch(d, x, w, scale, bias, residual, y, s);
+    algo = (d->groups == 1 && pv_conv3d_tcgen05_supported(d)) ? PV_ALGO_TCGEN05 : PV_ALGO_DIRECT;
+  if (algo == PV_ALGO_TCGEN05) {
+    if (pv::wants_gather(d)) return pv::conv3d_gather_launch(d, x, w, scale, bias, residual, y, s);
+    return pv::conv3d_tcgen05_launch(d, x, w, scale, bias, residual, y, s);
+  }
   if (algo == PV_ALGO_DIRECT) return pv::conv3d_direct_launch(d, x, w, scale, bias, residual, y, s);
   pv::set_error("unknown algo %d", algo);
   return PV_ERR_INVALID;

@@ -1,0 +1,363 @@
+// Implicit-GEMM convolution for NARROW inputs (C_in < 64: the 3-channel stems, the SlowFast Fast
+// pathway C=8..32, X3D's 24/48/56-wide tensors) on tcgen05 tensor cores.
+//
+// With few input channels one filter tap is only 8..64 bytes of K, so a 64-channel TMA box per tap
+// would be mostly zero fill.  Here the GEMM K axis is the flattened (tap, ci) index and the A tile
+// (128 output positions x 64 K-elements, 128B-swizzled K-major) is assembled by 8 producer warps
+// with coalesced 8/16-byte global loads (im2col gather, zero fill for padding) written straight to
+// the swizzled shared-memory layout the UMMA descriptor expects; weights still arrive by TMA.
+// MMA issue, TMEM double buffering and the fused epilogue are the same as in pv_igemm.cu.
+#include "pv_common.cuh"
+#include "pv_sm100.cuh"
+
+#include <mutex>
+
+namespace pv {
+
+using namespace sm100;
+
+constexpr int GG_BM = 128;
+constexpr int GG_BK = 64;
+constexpr int GG_A_BYTES = GG_BM * GG_BK * 2;
+constexpr int GG_MAX_UNITS = 256;
+constexpr int GG_EPI_WARPS = 4;
+constexpr int GG_PROD_WARPS = 8;
+constexpr int GG_PROD_THREADS = GG_PROD_WARPS * 32;
+constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 416
+
+struct GatherParams {
+  CUtensorMap b_map;
+  int N, Ti, Hi, Wi, To, Ho, Wo;
+  int st, sh, sw, pt, ph, pw;
+  int gbytes;        // gather unit: 8 or 16 bytes
+  int units_total;   // taps * (Ci*2/gbytes)
+  int upk;           // units per 64-element k-block: 128 / gbytes
+  int num_kb;
+  long long x_row_stride;
+  long long M;
+  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, act, has_residual;
+  long long y_row_stride, res_row_stride;
+  int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
+  unsigned int unit_d[GG_MAX_UNITS];  // packed (dt | dh<<8 | dw<<16) tap displacement (dilation applied)
+};
+
+__global__ void __launch_bounds__(GG_THREADS, 1)
+conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half* __restrict__ x,
+                           const float* __restrict__ scale, const float* __restrict__ bias,
+                           const __half* __restrict__ res, __half* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = P.stages;
+  const uint32_t b_bytes = (uint32_t)P.block_n * GG_BK * 2;
+  const uint32_t stage_bytes = GG_A_BYTES + b_bytes;
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int MMA_WARP = GG_EPI_WARPS;          // warp 4
+  constexpr int PROD_WARP0 = GG_EPI_WARPS + 1;    // warps 5..12
+
+  if (warp == MMA_WARP && lane == 0) {
+    prefetch_tmap(&P.b_map);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), GG_PROD_THREADS + 1);   // every producer thread + the expect_tx arrive
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), GG_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = P.n_tiles * P.m_tiles;
+
+  if (warp >= PROD_WARP0) {
+    // ================================ gather producers =======================================
+    const int ptid = threadIdx.x - PROD_WARP0 * 32;
+    const int row = ptid & 127;
+    const int half = ptid >> 7;
+    const int per_thread = P.upk >> 1;                 // units per k-block handled by this thread
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % P.n_tiles;
+      const int m_tile = tile / P.n_tiles;
+      const long long m = (long long)m_tile * GG_BM + row;
+      const bool row_ok = m < P.M;
+      int t0 = 0, h0 = 0, w0 = 0;
+      const __half* xrow = x;
+      if (row_ok) {
+        int wo = (int)(m % P.Wo); long long r = m / P.Wo;
+        int ho = (int)(r % P.Ho); r /= P.Ho;
+        int to = (int)(r % P.To); int n = (int)(r / P.To);
+        t0 = to * P.st - P.pt; h0 = ho * P.sh - P.ph; w0 = wo * P.sw - P.pw;
+        xrow = x + ((((long long)n * P.Ti + t0) * P.Hi + h0) * P.Wi + w0) * P.x_row_stride;
+      }
+      for (int kb = 0; kb < P.num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        uint8_t* a_tile = smem_gen + stage * stage_bytes;
+        if (ptid == 0) {
+          mbar_arrive_expect_tx(full_bar(stage), b_bytes);
+          tma_load_2d(smem_base + stage * stage_bytes + GG_A_BYTES, &P.b_map, full_bar(stage), kb * GG_BK,
+                      n_tile * P.block_n);
+        }
+        const int u0 = kb * P.upk + half * per_thread;
+        if (P.gbytes == 16) {
+#pragma unroll 4
+          for (int i = 0; i < per_thread; ++i) {
+            const int u = u0 + i;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok && u < P.units_total) {
+              const unsigned int dd = P.unit_d[u];
+              const int ti = t0 + (int)(dd & 0xffu), hi = h0 + (int)((dd >> 8) & 0xffu), wi = w0 + (int)(dd >> 16);
+              if ((unsigned)ti < (unsigned)P.Ti && (unsigned)hi < (unsigned)P.Hi && (unsigned)wi < (unsigned)P.Wi)
+                v = __ldg(reinterpret_cast<const uint4*>(xrow + P.unit_off[u]));
+            }
+            const uint32_t j = (uint32_t)(half * per_thread + i);       // 16B chunk index within the 128B row
+            *reinterpret_cast<uint4*>(a_tile + row_off + ((j ^ rsw) << 4)) = v;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < per_thread; ++i) {
+            const int u = u0 + i;
+            uint2 v = make_uint2(0u, 0u);
+            if (row_ok && u < P.units_total) {
+              const unsigned int dd = P.unit_d[u];
+              const int ti = t0 + (int)(dd & 0xffu), hi = h0 + (int)((dd >> 8) & 0xffu), wi = w0 + (int)(dd >> 16);
+              if ((unsigned)ti < (unsigned)P.Ti && (unsigned)hi < (unsigned)P.Hi && (unsigned)wi < (unsigned)P.Wi)
+                v = __ldg(reinterpret_cast<const uint2*>(xrow + P.unit_off[u]));
+            }
+            const uint32_t ui = (uint32_t)(half * per_thread + i);      // 8B unit index within the row
+            *reinterpret_cast<uint2*>(a_tile + row_off + (((ui >> 1) ^ rsw) << 4) + ((ui & 1u) << 3)) = v;
+          }
+        }
+        // make the generic-proxy smem writes visible to the tensor-core (async) proxy, then signal
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full_bar(stage));
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(GG_BM, P.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.block_n);
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t a_desc = make_kmajor_desc(a_addr, 128);
+          const uint64_t b_desc = make_kmajor_desc(a_addr + GG_A_BYTES, 128);
+          int units_left = P.units_total - kb * P.upk;
+          if (units_left > P.upk) units_left = P.upk;
+          const int k16 = (units_left * P.gbytes + 31) >> 5;   // 16-element (32 B) MMA steps that hold data
+          for (int k = 0; k < k16; ++k)
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == P.num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue warps ========================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % P.n_tiles;
+      const int m_tile = tile / P.n_tiles;
+      const long long pos = (long long)m_tile * GG_BM + row;
+      const bool valid = pos < P.M;
+      const int n0 = n_tile * P.block_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.block_n);
+      __half* yrow = y + pos * P.y_row_stride + n0;
+      const __half* rrow = res + pos * P.res_row_stride + n0;
+      for (int c0 = 0; c0 < P.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = n0 + c0 + h * 8;
+            if (col < P.Co) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                f[j] = __uint_as_float(v[h * 8 + j]) * __ldg(scale + col + j) + __ldg(bias + col + j);
+              if (P.has_residual) {
+                float rr[8];
+                ld8<__half>(rrow + c0 + h * 8, rr);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += rr[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], P.act);
+              st8<__half>(yrow + c0 + h * 8, f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();   // pv_igemm.cu
+
+int conv3d_gather_supported(const pv_conv3d_desc* d) {
+  if (d->dtype != PV_F16 || d->groups != 1) return 0;
+  if (!(d->Ci == 4 || (d->Ci % 8 == 0 && d->Ci < 64))) return 0;
+  if (d->Co % 8) return 0;
+  if (d->ci_pad64 != d->Ci) return 0;        // weights packed with the un-padded per-tap K extent
+  const int gbytes = d->Ci == 4 ? 8 : 16;
+  const int units = d->kt * d->kh * d->kw * (d->Ci * 2 / gbytes);
+  if (units > GG_MAX_UNITS) return 0;
+  if (d->x_row_stride % (gbytes / 2) || d->y_row_stride % 8 || (d->has_residual && d->res_row_stride % 8)) return 0;
+  if (d->dt * (d->kt - 1) > 255 || d->dh * (d->kh - 1) > 255 || d->dw * (d->kw - 1) > 65535) return 0;
+  const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
+  if (M >= (1ll << 31) * 64) return 0;
+  return 1;
+}
+
+int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                         const float* bias, const void* residual, void* y, cudaStream_t stream) {
+  if (!conv3d_gather_supported(d)) {
+    set_error("gather tcgen05 path does not support this convolution");
+    return PV_ERR_UNSUPPORTED;
+  }
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PV_ERR_CUDA; }
+  static int sm_count = 0;
+  static bool attr_set = false;
+  if (sm_count == 0) {
+    int dev = 0;
+    PV_CUDA_OK(cudaGetDevice(&dev));
+    PV_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GatherParams P;
+  memset(&P, 0, sizeof(P));
+  P.N = d->N; P.Ti = d->Ti; P.Hi = d->Hi; P.Wi = d->Wi; P.To = d->To; P.Ho = d->Ho; P.Wo = d->Wo;
+  P.st = d->st; P.sh = d->sh; P.sw = d->sw; P.pt = d->pt; P.ph = d->ph; P.pw = d->pw;
+  P.gbytes = d->Ci == 4 ? 8 : 16;
+  const int upt = d->Ci * 2 / P.gbytes;
+  const int taps = d->kt * d->kh * d->kw;
+  P.units_total = taps * upt;
+  P.upk = 128 / P.gbytes;
+  P.num_kb = (P.units_total + P.upk - 1) / P.upk;
+  P.x_row_stride = d->x_row_stride;
+  P.M = (long long)d->N * d->To * d->Ho * d->Wo;
+  P.m_tiles = (int)cdiv(P.M, GG_BM);
+  P.Co = d->Co;
+  P.act = d->act;
+  P.has_residual = d->has_residual;
+  P.y_row_stride = d->y_row_stride;
+  P.res_row_stride = d->has_residual ? d->res_row_stride : 0;
+  for (int it = 0; it < d->kt; ++it)
+    for (int ih = 0; ih < d->kh; ++ih)
+      for (int iw = 0; iw < d->kw; ++iw) {
+        const int tap = (it * d->kh + ih) * d->kw + iw;
+        const int dt = it * d->dt, dh = ih * d->dh, dw = iw * d->dw;
+        const long long off = (((long long)dt * d->Hi + dh) * d->Wi + dw) * d->x_row_stride;
+        for (int q = 0; q < upt; ++q) {
+          const int u = tap * upt + q;
+          const long long o = off + (long long)q * (P.gbytes / 2);
+          if (o > 0x7fffffffll) { set_error("gather offset overflow"); return PV_ERR_UNSUPPORTED; }
+          P.unit_off[u] = (int)o;
+          P.unit_d[u] = (unsigned)dt | ((unsigned)dh << 8) | ((unsigned)dw << 16);
+        }
+      }
+  {
+    const int co16 = (int)cdiv(d->Co, 16) * 16;
+    int bn = co16 <= 256 ? co16 : 256;
+    // keep a few hundred tiles in flight for small layers
+    while (bn > 64 && (long long)P.m_tiles * cdiv(d->Co, bn) < 2 * sm_count && (bn / 2) % 16 == 0) bn /= 2;
+    P.block_n = bn;
+    P.n_tiles = (int)cdiv(d->Co, bn);
+  }
+  {
+    int cols = 2 * P.block_n, p2 = 32;
+    while (p2 < cols) p2 <<= 1;
+    P.tmem_cols = p2;
+  }
+  const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
+  {
+    int st = (200 * 1024) / stage_bytes;
+    if (st > 8) st = 8;
+    if (st < 2) st = 2;
+    P.stages = st;
+  }
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 1024 + 8 * (2 * P.stages + 4) + 16;
+  {
+    const long long kpad = (long long)cdiv((long long)taps * d->Ci, 64) * 64;
+    cuuint64_t gdim[2] = {(cuuint64_t)kpad, (cuuint64_t)d->Co};
+    cuuint64_t gstr[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)P.block_n}, estr[2] = {1, 1};
+    CUresult cr = encode(&P.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B, gather) failed: %d", (int)cr); return PV_ERR_CUDA; }
+  }
+  if (!attr_set) {
+    PV_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    attr_set = true;
+  }
+  const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
+  if (total_tiles == 0) return PV_OK;
+  const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
+  conv3d_igemm_gather_kernel<<<grid, GG_THREADS, smem_bytes, stream>>>(P, (const __half*)x, scale, bias,
+                                                                      (const __half*)residual, (__half*)y);
+  PV_LAUNCH_OK("conv3d_igemm_gather_kernel");
+  return PV_OK;
+}
+
+}  // namespace pv

@@ -251,6 +251,39 @@ pool3d_kernel(pv_pool3d_desc d, const T* __restrict__ x, T* __restrict__ y, long
   st8<T>(y + m * d.y_row_stride + c, acc);
 }
 
+// Global pooling (kernel == whole T x H x W extent, the head pools): one CTA per (sample, 64-channel
+// slab); 8 channel-group lanes x 32 position lanes, 128-byte coalesced reads, smem tree reduce.
+template <typename T>
+__global__ void __launch_bounds__(256)
+global_pool_kernel(const T* __restrict__ x, T* __restrict__ y, long long x_row_stride,
+                   long long y_row_stride, long long npos, int C, int is_max) {
+  __shared__ float red[32][64 + 1];
+  const int n = blockIdx.y;
+  const int c0 = blockIdx.x * 64;
+  const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = c0 + cg * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = is_max ? -INFINITY : 0.f;
+  if (c < C) {
+    for (long long p = pl; p < npos; p += 32) {
+      float v[8];
+      ld8<T>(x + ((long long)n * npos + p) * x_row_stride + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = is_max ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[pl][cg * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float r = red[0][threadIdx.x];
+    for (int j = 1; j < 32; ++j) r = is_max ? fmaxf(r, red[j][threadIdx.x]) : r + red[j][threadIdx.x];
+    if (!is_max) r *= 1.f / (float)npos;
+    if (c0 + (int)threadIdx.x < C) Elem<T>::st(y + (long long)n * y_row_stride + c0 + threadIdx.x, r);
+  }
+}
+
 // =============================================================================================
 // Squeeze-Excitation helpers
 // =============================================================================================
@@ -552,6 +585,19 @@ extern "C" int pv_pool3d_fwd(const pv_pool3d_desc* d, const void* x, void* y, vo
   const long long total = (long long)d->N * d->To * d->Ho * d->Wo * (d->C / 8);
   if (total == 0) return PV_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (to == 1 && ho == 1 && wo == 1 && d->kt == d->Ti && d->kh == d->Hi && d->kw == d->Wi && d->pt == 0 &&
+      d->ph == 0 && d->pw == 0 && d->N <= 65535) {
+    const long long npos = (long long)d->Ti * d->Hi * d->Wi;
+    dim3 grid((unsigned)cdiv(d->C, 64), d->N), block(256);
+    if (d->dtype == PV_F16)
+      global_pool_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, d->x_row_stride,
+                                                      d->y_row_stride, npos, d->C, d->mode == PV_POOL_MAX);
+    else
+      global_pool_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, d->x_row_stride,
+                                                     d->y_row_stride, npos, d->C, d->mode == PV_POOL_MAX);
+    PV_LAUNCH_OK("global_pool_kernel");
+    return PV_OK;
+  }
   dim3 grid((unsigned)cdiv(total, 256)), block(256);
   if (d->dtype == PV_F16)
     pool3d_kernel<__half><<<grid, block, 0, s>>>(*d, (const __half*)x, (__half*)y, total);

@@ -59,9 +59,17 @@ def pack_depthwise(w, c_pad, dtype):
 
 
 def pack_dense_tcgen05(w, ci_pad64, co_pad):
-    """[Co, Ci, kt, kh, kw] -> [co_pad, taps * ci_pad64] f16, K-major (k = tap * ci_pad64 + ci)."""
+    """[Co, Ci, kt, kh, kw] -> [co_pad, pad64(taps * ci_pad64)] f16, K-major (k = tap * ci_pad64 + ci).
+
+    TMA-fed kernel: ci_pad64 is a multiple of 64.  Gather-fed kernel (C_in < 64): ci_pad64 is the
+    padded channel count itself and only the row end is padded to a multiple of 64."""
     co, ci, kt, kh, kw = w.shape
     taps = kt * kh * kw
     out = torch.zeros(co_pad, taps, ci_pad64, dtype=torch.float16)
     out[:co, :, :ci] = w.detach().cpu().permute(0, 2, 3, 4, 1).reshape(co, taps, ci).to(torch.float16)
-    return out.reshape(co_pad, taps * ci_pad64).contiguous()
+    out = out.reshape(co_pad, taps * ci_pad64)
+    k = out.shape[1]
+    kp = pad_to(k, 64)
+    if kp != k:
+        out = torch.cat([out, torch.zeros(co_pad, kp - k, dtype=torch.float16)], 1)
+    return out.contiguous()

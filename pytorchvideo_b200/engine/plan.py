@@ -178,7 +178,7 @@ class Plan:
             raise RuntimeError("conv %s: only groups==1 or depthwise (groups==Cin==Cout) is supported" % name)
         tdt = _TORCH_DT[self.dt]
         ci_pad = x.Cp
-        ci_pad64 = PK.pad_to(ci_pad, 64)
+        ci_pad64 = ci_pad if ci_pad < 64 else PK.pad_to(ci_pad, 64)   # < 64: gather-fed kernel, un-padded taps
 
         d = L.Conv3dDesc()
         d.dtype = self.dt

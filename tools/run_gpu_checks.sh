@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $
 run python __graft_entry__.py
 run python -m pytest tests/test_gpu_transforms.py -q -m gpu
 run python -m pytest tests/test_gpu_ops.py -q -m gpu -k "direct or pool or layernorm or attention"
-for i in 2 3 4 5 6 7 8; do
+for i in 0 1 2 3 4 5 6 7 8; do
   run python -m pytest tests/test_gpu_ops.py -q -m gpu -k "test_conv3d_bn_act and ${i}-f16-tcgen05"
 done
 run python -m pytest tests/test_gpu_models.py -q -m gpu -k "f32" -s
