@@ -105,6 +105,11 @@ int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void* src,
 int pv_ncdhw_to_ndhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
                       int N, int C, int T, int H, int W, int c_pad, long long dst_row_stride,
                       void* stream);
+/* Same, but every output row is x_w_phys pixels wide with w_pad zero pixels on the left and zeros
+ * on the right (dst holds N*T*H*w_phys*c_pad + c_pad*8 elements): the stem layout of window mode. */
+int pv_ncdhw_to_ndhwc_padw(const void* src, int src_dtype, void* dst, int dst_dtype,
+                           int N, int C, int T, int H, int W, int c_pad, int w_pad, int w_phys,
+                           void* stream);
 /* Clears n floats (SE accumulators) with a stream-ordered memset. */
 int pv_zero_f32(float* dst, long long n, void* stream);
 /* NDHWC -> NCDHW f32 (for handing feature maps back to torch when a model has no head). */
@@ -124,7 +129,9 @@ int pv_ndhwc_to_ncdhw(const void* src, int src_dtype, long long src_row_stride, 
  * Packed weights (host-side, see pytorchvideo_b200/engine/packing.py):
  *   PV_ALGO_DIRECT, dense : w[tap][ci][co]        (storage dtype, Ci/Co padded)
  *   depthwise (any algo)  : w[tap][c]             (storage dtype)
- *   PV_ALGO_TCGEN05       : w[co][tap][ci_pad64]  (f16, K-major rows of length taps*ci_pad64)
+ *   PV_ALGO_TCGEN05       : w[co][tap][ci_pad64]  (f16, K-major rows of length taps*ci_pad64;
+ *                           C_in < 64: ci_pad64 = Ci, row padded to a multiple of 64;
+ *                           window mode: w[co][kt*kh][win] with win = 16|32|64 >= kw*Ci)
  * ------------------------------------------------------------------------------------------- */
 typedef struct pv_conv3d_desc {
   int dtype;                 /* storage dtype of x, y, residual, w: PV_F16 | PV_F32          */
@@ -139,6 +146,10 @@ typedef struct pv_conv3d_desc {
   int has_residual;
   long long x_row_stride, y_row_stride, res_row_stride;
   int ci_pad64;              /* PV_ALGO_TCGEN05 only: per-tap K extent of the packed weights */
+  /* "window mode" for 3/4-channel stems on the tensor cores: the input rows physically carry
+   * x_w_pad zero pixels on the left (>= pw) and are x_w_phys pixels wide in memory (written that
+   * way by pv_ncdhw_to_ndhwc_padw); Wi stays the logical width.  0 = ordinary layout.           */
+  int x_w_pad, x_w_phys;
 } pv_conv3d_desc;
 
 int pv_conv3d_fwd(const pv_conv3d_desc* d, int algo, const void* x, const void* w,

@@ -34,7 +34,7 @@ class Conv3dDesc(C.Structure):
                 ("dt", C.c_int), ("dh", C.c_int), ("dw", C.c_int),
                 ("groups", C.c_int), ("act", C.c_int), ("has_residual", C.c_int),
                 ("x_row_stride", c_ll), ("y_row_stride", c_ll), ("res_row_stride", c_ll),
-                ("ci_pad64", C.c_int)]
+                ("ci_pad64", C.c_int), ("x_w_pad", C.c_int), ("x_w_phys", C.c_int)]
 
 
 class Pool3dDesc(C.Structure):
@@ -68,6 +68,8 @@ SIGNATURES = {
                                         c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pv_ncdhw_to_ndhwc": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_ll, c_vp]),
+    "pv_ncdhw_to_ndhwc_padw": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "pv_zero_f32": (C.c_int, [c_vp, c_ll, c_vp]),
     "pv_ndhwc_to_ncdhw": (C.c_int, [c_vp, C.c_int, c_ll, c_vp, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, c_vp]),

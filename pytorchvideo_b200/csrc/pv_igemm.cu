@@ -27,7 +27,7 @@ using namespace sm100;
 
 constexpr int IG_BM = 128;        // UMMA M
 constexpr int IG_BK = 64;         // K per pipeline stage (one 128B swizzle row of f16)
-constexpr int IG_MAX_TAPS = 32;
+constexpr int IG_MAX_TAPS = 64;
 constexpr int IG_MAX_MAPS = 8;
 constexpr int IG_THREADS = 192;
 constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;   // 16 KiB
@@ -44,6 +44,7 @@ struct IgemmParams {
   int block_n;
   int Co;
   int taps, num_kc;
+  int kbytes;      // bytes of K per smem row and pipeline stage: 128 (64 ch, SW128) | 64 | 32 (window mode)
   int stages;
   int tmem_cols;
   int act, has_residual;
@@ -59,8 +60,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stages = P.stages;
-  const uint32_t b_bytes = (uint32_t)P.block_n * IG_BK * 2;
-  const uint32_t stage_bytes = IG_A_BYTES + b_bytes;
+  const uint32_t a_bytes = (uint32_t)IG_BM * P.kbytes;
+  const uint32_t b_bytes = (uint32_t)P.block_n * P.kbytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int k_elems = P.kbytes >> 1;
   // barriers live after the tile ring
   const uint32_t bar_base = smem_base + stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -103,7 +106,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)P.rows * (IG_BK * 2) + b_bytes;
+      const uint32_t tx_bytes = (uint32_t)P.rows * P.kbytes + b_bytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % P.n_tiles;
         int mt = tile / P.n_tiles;
@@ -118,10 +121,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
           for (int kc = 0; kc < P.num_kc; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
-            const uint32_t b_dst = a_dst + IG_A_BYTES;
+            const uint32_t b_dst = a_dst + a_bytes;
             mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_5d(a_dst, amap, full_bar(stage), kc * IG_BK, c1, c2, c3, c4);
-            tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * IG_BK, n0);
+            tma_load_5d(a_dst, amap, full_bar(stage), kc * k_elems, c1, c2, c3, c4);
+            tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * k_elems, n0);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -143,10 +146,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t a_desc = make_kmajor_desc(a_addr, 128);
-          const uint64_t b_desc = make_kmajor_desc(a_addr + IG_A_BYTES, 128);
-#pragma unroll
-          for (int k = 0; k < IG_BK / 16; ++k) {
+          const uint64_t a_desc = make_kmajor_desc(a_addr, P.kbytes);
+          const uint64_t b_desc = make_kmajor_desc(a_addr + a_bytes, P.kbytes);
+          const int k16 = P.kbytes >> 5;
+          for (int k = 0; k < k16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in (addr>>4)
             umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                      (kb | k) != 0 ? 1u : 0u);
@@ -255,7 +258,8 @@ EncodeTiledFn get_encode_fn() {
 struct Dim4 {      // one merged spatial dim
   long long I, O;  // input / output extent
   int k, s, p, dil;
-  long long in_stride;   // in positions (rows) of the input tensor
+  long long stride_bytes;   // byte distance of +1 input index in this dim
+  bool nomerge;
 };
 
 struct IgemmPlan {
@@ -264,21 +268,41 @@ struct IgemmPlan {
   int orig2m[4];   // original dim (0=W,1=H,2=T,3=N) -> merged dim index
 };
 
+// Window mode (narrow C_in stems): the K axis of one pipeline stage is the contiguous run of
+// kw*Ci input elements that one output pixel reads in one (dt,dh) filter row.  The TMA tensor map
+// uses OVERLAPPING strides - dim0 = the run (padded to 16/32/64 elements), dim1 = output column
+// with byte stride sw*Ci*2 - so one tiled load delivers 128 sliding windows.  The input rows carry
+// x_w_pad physical zero pixels on the left (and enough on the right), written by the layout
+// conversion, which implements the W padding; H/T padding is TMA out-of-bounds fill as usual.
+static bool window_mode(const pv_conv3d_desc* d) { return d->x_w_pad > 0 && d->Ci <= 8; }
+static int window_elems(const pv_conv3d_desc* d) {
+  const int run = d->kw * d->Ci;
+  return run <= 16 ? 16 : (run <= 32 ? 32 : 64);
+}
+
 // Reduce (W,H,T,N) to <=4 merged dims: runs of adjacent trivial dims (k=1,s=1,p=0) collapse.
 static void reduce_dims(const pv_conv3d_desc* d, IgemmPlan* pl) {
-  Dim4 raw[4] = {
-      {d->Wi, d->Wo, d->kw, d->sw, d->pw, d->dw, 1},
-      {d->Hi, d->Ho, d->kh, d->sh, d->ph, d->dh, (long long)d->Wi},
-      {d->Ti, d->To, d->kt, d->st, d->pt, d->dt, (long long)d->Wi * d->Hi},
-      {d->N, d->N, 1, 1, 0, 1, (long long)d->Wi * d->Hi * d->Ti},
-  };
+  const long long rs = d->x_row_stride * 2;   // bytes per position
+  Dim4 raw[4];
+  if (window_mode(d)) {
+    const long long wp = d->x_w_phys;
+    raw[0] = {d->Wo, d->Wo, 1, 1, 0, 1, (long long)d->sw * rs, true};
+    raw[1] = {d->Hi, d->Ho, d->kh, d->sh, d->ph, d->dh, wp * rs, false};
+    raw[2] = {d->Ti, d->To, d->kt, d->st, d->pt, d->dt, wp * d->Hi * rs, false};
+    raw[3] = {d->N, d->N, 1, 1, 0, 1, wp * d->Hi * d->Ti * rs, false};
+  } else {
+    raw[0] = {d->Wi, d->Wo, d->kw, d->sw, d->pw, d->dw, rs, false};
+    raw[1] = {d->Hi, d->Ho, d->kh, d->sh, d->ph, d->dh, (long long)d->Wi * rs, false};
+    raw[2] = {d->Ti, d->To, d->kt, d->st, d->pt, d->dt, (long long)d->Wi * d->Hi * rs, false};
+    raw[3] = {d->N, d->N, 1, 1, 0, 1, (long long)d->Wi * d->Hi * d->Ti * rs, false};
+  }
   int n = 0;
   for (int i = 0; i < 4; ++i) {
-    const bool triv = raw[i].k == 1 && raw[i].s == 1 && raw[i].p == 0;
+    const bool triv = raw[i].k == 1 && raw[i].s == 1 && raw[i].p == 0 && !raw[i].nomerge;
     if (n > 0) {
       Dim4& prev = pl->dim[n - 1];
-      const bool ptriv = prev.k == 1 && prev.s == 1 && prev.p == 0;
-      if (triv && ptriv && prev.in_stride * prev.I == raw[i].in_stride) {
+      const bool ptriv = prev.k == 1 && prev.s == 1 && prev.p == 0 && !prev.nomerge;
+      if (triv && ptriv && prev.stride_bytes * prev.I == raw[i].stride_bytes) {
         prev.I *= raw[i].I;
         prev.O *= raw[i].O;
         pl->orig2m[i] = n - 1;
@@ -289,7 +313,8 @@ static void reduce_dims(const pv_conv3d_desc* d, IgemmPlan* pl) {
     pl->dim[n++] = raw[i];
   }
   pl->ndims = n;
-  for (int i = n; i < 4; ++i) pl->dim[i] = {1, 1, 1, 1, 0, 1, pl->dim[n - 1].in_stride * pl->dim[n - 1].I};
+  for (int i = n; i < 4; ++i)
+    pl->dim[i] = {1, 1, 1, 1, 0, 1, pl->dim[n - 1].stride_bytes * pl->dim[n - 1].I, false};
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -302,6 +327,22 @@ int conv3d_tcgen05_supported(const pv_conv3d_desc* d, char* why, size_t why_len)
   } while (0)
   if (d->dtype != PV_F16) NOPE("tcgen05 path needs f16 storage");
   if (d->groups != 1) NOPE("tcgen05 path is dense only (groups=%d)", d->groups);
+  if (window_mode(d)) {
+    if (d->Ci != 4 && d->Ci != 8) NOPE("window mode needs Ci in {4,8}");
+    if (d->Co % 8) NOPE("Co must be a multiple of 8");
+    if (d->dw != 1) NOPE("window mode needs dilation_w == 1");
+    if (d->x_row_stride != d->Ci) NOPE("window mode needs densely packed pixels");
+    if ((d->sw * d->Ci * 2) % 16) NOPE("window stride must be a multiple of 16 bytes");
+    if (d->kw * d->Ci > 64) NOPE("window run longer than 64 elements");
+    if (d->x_w_pad < d->pw) NOPE("physical W padding smaller than the conv padding");
+    if (d->x_w_phys < d->x_w_pad + d->Wi + (d->pw > 0 ? d->pw : 0) || (d->x_w_phys * d->Ci * 2) % 16)
+      NOPE("bad physical row width");
+    if (d->kt * d->kh > IG_MAX_TAPS) NOPE("too many (dt,dh) taps");
+    if (d->st * d->sh > IG_MAX_MAPS) NOPE("stride product too large");
+    if (d->ci_pad64 != window_elems(d)) NOPE("window mode: ci_pad64 must equal the window length %d", window_elems(d));
+    if (d->y_row_stride % 8 || (d->has_residual && d->res_row_stride % 8)) NOPE("row strides %% 8");
+    return 1;
+  }
   if (d->Ci % 8 || d->Co % 8) NOPE("Ci/Co must be multiples of 8");
   if (d->x_row_stride % 8 || d->y_row_stride % 8 || (d->has_residual && d->res_row_stride % 8))
     NOPE("row strides must be multiples of 8 elements (16 B)");
@@ -391,9 +432,12 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     P.block_n = bn;
     P.n_tiles = (int)cdiv(d->Co, bn);
   }
+  const bool wmode = window_mode(d);
+  const int win = wmode ? window_elems(d) : 64;
+  P.kbytes = 2 * win;
   P.Co = d->Co;
-  P.taps = d->kt * d->kh * d->kw;
-  P.num_kc = d->ci_pad64 / 64;
+  P.taps = wmode ? d->kt * d->kh : d->kt * d->kh * d->kw;
+  P.num_kc = wmode ? 1 : d->ci_pad64 / 64;
   P.act = d->act;
   P.has_residual = d->has_residual;
   P.y_row_stride = d->y_row_stride;
@@ -403,7 +447,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
-  const int stage_bytes = IG_A_BYTES + P.block_n * IG_BK * 2;
+  const int stage_bytes = (IG_BM + P.block_n) * P.kbytes;
   {
     int st = (200 * 1024) / stage_bytes;
     if (st > 8) st = 8;
@@ -419,13 +463,15 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   for (int i = 0; i < 4; ++i) { ks[i] = pl.dim[i].k; ss[i] = pl.dim[i].s; ps[i] = pl.dim[i].p; dls[i] = pl.dim[i].dil; }
   const int* orig2m = pl.orig2m;
   unsigned used_maps = 0;
+  const int kw_loop = wmode ? 1 : d->kw;
   for (int it = 0; it < d->kt; ++it)
     for (int ih = 0; ih < d->kh; ++ih)
-      for (int iw = 0; iw < d->kw; ++iw) {
-        const int tap = (it * d->kh + ih) * d->kw + iw;
+      for (int iw = 0; iw < kw_loop; ++iw) {
+        const int tap = (it * d->kh + ih) * kw_loop + iw;
         int q[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
-        const int offs[3] = {iw * d->dw - d->pw, ih * d->dh - d->ph, it * d->dt - d->pt};
-        const int strd[3] = {d->sw, d->sh, d->st};
+        // window mode: the W taps live inside the window and the W padding is physical
+        const int offs[3] = {wmode ? 0 : iw * d->dw - d->pw, ih * d->dh - d->ph, it * d->dt - d->pt};
+        const int strd[3] = {wmode ? 1 : d->sw, d->sh, d->st};
         for (int o = 0; o < 3; ++o) {
           const int m = orig2m[o];
           if (strd[o] == 1 && offs[o] == 0) continue;
@@ -446,24 +492,23 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (!(used_maps & (1u << cls))) continue;
     int r[4], c = cls;
     for (int m = 0; m < 4; ++m) { r[m] = c % ss[m]; c /= ss[m]; }
-    long long base_off = 0;
+    long long base_off = wmode ? (long long)(d->x_w_pad - d->pw) * d->Ci * 2 : 0;   // bytes
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
-    gdim[0] = (cuuint64_t)d->Ci;
-    box[0] = 64;
-    bool empty = false;
+    gdim[0] = (cuuint64_t)(wmode ? win : d->Ci);
+    box[0] = (cuuint32_t)win;
     for (int m = 0; m < 4; ++m) {
       const long long cnt = (pl.dim[m].I - r[m] + ss[m] - 1) / ss[m];
-      if (cnt <= 0) empty = true;
       gdim[m + 1] = (cuuint64_t)(cnt > 0 ? cnt : 1);
-      gstr[m] = (cuuint64_t)(pl.dim[m].in_stride * ss[m] * d->x_row_stride * 2);
+      gstr[m] = (cuuint64_t)(pl.dim[m].stride_bytes * ss[m]);
       box[m + 1] = (cuuint32_t)P.box[m];
-      base_off += (long long)r[m] * pl.dim[m].in_stride * d->x_row_stride;
+      base_off += (long long)r[m] * pl.dim[m].stride_bytes;
     }
-    (void)empty;
-    void* gptr = (void*)((const __half*)x + base_off);
+    void* gptr = (void*)((const char*)x + base_off);
+    const CUtensorMapSwizzle swz = P.kbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (P.kbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult cr = encode(&P.a_maps[cls], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, gptr, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(A, class %d) failed: %d (Ci=%d dims=%llu,%llu,%llu,%llu box=%u,%u,%u,%u)",
@@ -473,11 +518,14 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     }
   }
   {
-    cuuint64_t gdim[2] = {(cuuint64_t)P.taps * d->ci_pad64, (cuuint64_t)d->Co};
-    cuuint64_t gstr[1] = {(cuuint64_t)P.taps * d->ci_pad64 * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)P.block_n}, estr[2] = {1, 1};
+    const long long krow = (long long)P.taps * d->ci_pad64;     // window mode: ci_pad64 == window length
+    cuuint64_t gdim[2] = {(cuuint64_t)krow, (cuuint64_t)d->Co};
+    cuuint64_t gstr[1] = {(cuuint64_t)krow * 2};
+    cuuint32_t box[2] = {(cuuint32_t)win, (cuuint32_t)P.block_n}, estr[2] = {1, 1};
+    const CUtensorMapSwizzle swz = P.kbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (P.kbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult cr = encode(&P.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)cr); return PV_ERR_CUDA; }
   }

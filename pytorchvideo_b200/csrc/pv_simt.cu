@@ -23,6 +23,31 @@ __global__ void ncdhw_to_ndhwc_kernel(const SrcT* __restrict__ src, DstT* __rest
   }
 }
 
+// NCDHW -> NDHWC with physical zero padding along W (stem layout for the windowed-TMA conv)
+template <typename SrcT, typename DstT>
+__global__ void ncdhw_to_ndhwc_padw_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int C,
+                                           int T, int H, int W, int c_pad, int w_pad, int w_phys,
+                                           long long total_phys) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // physical pixel index
+  if (p >= total_phys) return;
+  const int wp = (int)(p % w_phys);
+  long long r = p / w_phys;            // (n*T + t)*H + h
+  const int w = wp - w_pad;
+  DstT* o = dst + p * c_pad;
+  if (w < 0 || w >= W) {
+    for (int c = 0; c < c_pad; ++c) Elem<DstT>::st(o + c, 0.f);
+    return;
+  }
+  const int h = (int)(r % H); r /= H;
+  const int t = (int)(r % T); const long long n = r / T;
+  const long long thw = (long long)T * H * W;
+  const SrcT* s = src + n * C * thw + ((long long)t * H + h) * W + w;
+  for (int c = 0; c < c_pad; ++c) {
+    float v = (c < C) ? Elem<SrcT>::ld(s + (long long)c * thw) : 0.f;
+    Elem<DstT>::st(o + c, v);
+  }
+}
+
 template <typename SrcT>
 __global__ void ndhwc_to_ncdhw_kernel(const SrcT* __restrict__ src, long long src_row_stride,
                                       float* __restrict__ dst, int C, long long thw,
@@ -492,6 +517,28 @@ extern "C" int pv_ncdhw_to_ndhwc(const void* src, int src_dtype, void* dst, int 
   else { set_error("unsupported dtype pair %d->%d", src_dtype, dst_dtype); return PV_ERR_INVALID; }
 #undef PV_CASE
   PV_LAUNCH_OK("ncdhw_to_ndhwc_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_ncdhw_to_ndhwc_padw(const void* src, int src_dtype, void* dst, int dst_dtype, int N,
+                                      int C, int T, int H, int W, int c_pad, int w_pad, int w_phys,
+                                      void* stream) {
+  PV_CHECK_ARG(src && dst, "null pointer");
+  PV_CHECK_ARG(c_pad >= C && w_pad >= 0 && w_phys >= w_pad + W, "bad padding");
+  const long long total = (long long)N * T * H * w_phys;
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+#define PV_CASE(ST, DT)                                                                         \
+  ncdhw_to_ndhwc_padw_kernel<ST, DT><<<grid, block, 0, s>>>((const ST*)src, (DT*)dst, C, T, H, W, c_pad, \
+                                                          w_pad, w_phys, total)
+  if (src_dtype == PV_F32 && dst_dtype == PV_F16) PV_CASE(float, __half);
+  else if (src_dtype == PV_F32 && dst_dtype == PV_F32) PV_CASE(float, float);
+  else if (src_dtype == PV_F16 && dst_dtype == PV_F16) PV_CASE(__half, __half);
+  else if (src_dtype == PV_F16 && dst_dtype == PV_F32) PV_CASE(__half, float);
+  else { set_error("unsupported dtype pair %d->%d", src_dtype, dst_dtype); return PV_ERR_INVALID; }
+#undef PV_CASE
+  PV_LAUNCH_OK("ncdhw_to_ndhwc_padw_kernel");
   return PV_OK;
 }
 

@@ -33,6 +33,8 @@ class TRef:
         self.Cp = PK.pad8(C) if Cp is None else int(Cp)
         self.ch_off = int(ch_off)
         self.row_stride = self.Cp if row_stride is None else int(row_stride)
+        self.lazy_src = None      # network input whose NCDHW->NDHWC conversion is emitted by its first consumer
+        self.padw = None          # (w_pad, w_phys): rows physically zero-padded along W (window-mode stems)
 
     @property
     def npos(self):
@@ -142,18 +144,39 @@ class Plan:
     # op emitters
     # =====================================================================================
     def emit_input_ncdhw(self, static_in, C, c_pad):
-        """static_in: torch tensor [N,C,T,H,W] (f32|f16) whose storage is fixed for the plan."""
+        """static_in: torch tensor [N,C,T,H,W] (f32|f16) whose storage is fixed for the plan.
+        The layout conversion is emitted lazily by the first consumer (a stem conv may ask for
+        physically W-padded rows, see pv_igemm.cu window mode)."""
         N, Cc, T, H, W = static_in.shape
         assert Cc == C
-        out = self.new_tensor(N, T, H, W, C, Cp=c_pad)
-        src_dt = L.PV_F32 if static_in.dtype == torch.float32 else L.PV_F16
-        lib = self.lib
-
-        def fn(stream):
-            L.check(lib.pv_ncdhw_to_ndhwc(static_in.data_ptr(), src_dt, out.ptr(), out.dt, N, C, T, H, W,
-                                          out.Cp, out.row_stride, stream), "pv_ncdhw_to_ndhwc")
-        self.add("ncdhw_to_ndhwc", fn)
+        out = TRef(None, N, T, H, W, C, Cp=c_pad)
+        out.lazy_src = static_in
         return out
+
+    def materialize_input(self, x, w_pad=0, w_phys=0):
+        if x.lazy_src is None:
+            return x
+        src = x.lazy_src
+        x.lazy_src = None
+        N, C, T, H, W = src.shape
+        src_dt = L.PV_F32 if src.dtype == torch.float32 else L.PV_F16
+        lib = self.lib
+        if w_pad > 0:
+            x.buf = self.new_buf(N * T * H * w_phys * x.Cp + 64 * x.Cp)
+            x.padw = (w_pad, w_phys)
+
+            def fn(stream):
+                L.check(lib.pv_ncdhw_to_ndhwc_padw(src.data_ptr(), src_dt, x.ptr(), x.dt, N, C, T, H, W, x.Cp,
+                                                  w_pad, w_phys, stream), "pv_ncdhw_to_ndhwc_padw")
+            self.add("ncdhw_to_ndhwc_padw", fn, "other", 0.0, src.numel() * src.element_size() + N * T * H * w_phys * x.Cp * 2)
+        else:
+            x.buf = self.new_buf(N * T * H * W * x.Cp)
+
+            def fn(stream):
+                L.check(lib.pv_ncdhw_to_ndhwc(src.data_ptr(), src_dt, x.ptr(), x.dt, N, C, T, H, W, x.Cp,
+                                              x.row_stride, stream), "pv_ncdhw_to_ndhwc")
+            self.add("ncdhw_to_ndhwc", fn, "other", 0.0, src.numel() * src.element_size() + N * T * H * W * x.Cp * 2)
+        return x
 
     def emit_conv(self, x, weight, conv_bias, bn, stride, padding, dilation, groups, act=L.ACT_NONE,
                   residual=None, name="conv", force_algo=None):
@@ -170,6 +193,22 @@ class Plan:
         if min(To, Ho, Wo) <= 0:
             raise RuntimeError("conv %s: kernel larger than (padded) input" % name)
         co_pad = PK.pad8(co)
+        if residual is not None:
+            self.materialize_input(residual)
+        # ---- network input: pick the layout its first consumer wants
+        window = False
+        if x.lazy_src is not None:
+            window = (self.use_tcgen05 and force_algo in (None, L.ALGO_TCGEN05) and groups == 1 and x.Cp == 4
+                      and dlw == 1 and (sw * x.Cp * 2) % 16 == 0 and kw * x.Cp <= 64 and kt * kh <= 64
+                      and st * sh <= 8 and pw > 0)
+            if window:
+                win = PK.window_elems(kw, x.Cp)
+                need = max(x.W + 2 * pw, (Wo - 1) * sw + (win + x.Cp - 1) // x.Cp)
+                self.materialize_input(x, w_pad=pw, w_phys=(need + 1) // 2 * 2)
+            else:
+                self.materialize_input(x)
+        elif x.padw is not None:
+            raise RuntimeError("W-padded stem input can only feed one window-mode convolution")
         y = self.new_tensor(x.N, To, Ho, Wo, co, Cp=co_pad)
         scale, bias = PK.fold_bn(conv_bias, bn, co, co_pad)
         scale_d, bias_d = self.const(scale), self.const(bias)
@@ -194,6 +233,9 @@ class Plan:
         d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
         d.res_row_stride = residual.row_stride if residual is not None else 0
         d.ci_pad64 = ci_pad64
+        if window:
+            d.x_w_pad, d.x_w_phys = x.padw
+            d.ci_pad64 = PK.window_elems(kw, x.Cp)
 
         if depthwise:
             algo, kind = L.ALGO_DIRECT, "depthwise"
@@ -202,9 +244,12 @@ class Plan:
             want_tc = self.use_tcgen05 and bool(self.lib.pv_conv3d_tcgen05_supported(C.byref(d)))
             if force_algo is not None:
                 want_tc = force_algo == L.ALGO_TCGEN05
+            if window and not want_tc:
+                raise RuntimeError("internal: window-mode stem rejected by the library: " + L.last_error())
             if want_tc:
                 algo, kind = L.ALGO_TCGEN05, "tcgen05"
-                w_d = self.const(PK.pack_dense_tcgen05(weight, ci_pad64, co_pad))
+                w_d = self.const(PK.pack_dense_window(weight, x.Cp, co_pad) if window
+                                 else PK.pack_dense_tcgen05(weight, ci_pad64, co_pad))
             else:
                 algo, kind = L.ALGO_DIRECT, "direct"
                 w_d = self.const(PK.pack_dense_direct(weight, ci_pad, co_pad, tdt))
@@ -224,6 +269,7 @@ class Plan:
         return y
 
     def emit_pool(self, x, mode, kernel, stride, padding, name="pool"):
+        self.materialize_input(x)
         kt, kh, kw = kernel
         st, sh, sw = stride
         pt, ph, pw = padding
@@ -300,6 +346,7 @@ class Plan:
         return out, (x.N, x.C)
 
     def emit_to_ncdhw(self, x, name="to_ncdhw"):
+        self.materialize_input(x)
         out = self.new_buf(x.N * x.C * x.npos, L.PV_F32)
         lib = self.lib
 
