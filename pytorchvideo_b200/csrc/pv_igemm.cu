@@ -18,6 +18,7 @@
 //   warps2-5 = epilogue; smem ring of `stages` {A,B} slots with full/empty mbarriers.
 #include "pv_common.cuh"
 #include "pv_sm100.cuh"
+#include "pv_epilogue.cuh"
 
 #include <mutex>
 
@@ -47,30 +48,32 @@ struct IgemmParams {
   int kbytes;      // bytes of K per smem row and pipeline stage: 128 (64 ch, SW128) | 64 | 32 (window mode)
   int stages;
   int tmem_cols;
-  int act, has_residual;
-  long long y_row_stride, res_row_stride;
+  EpiParams epi;
   signed char tap_q[IG_MAX_TAPS][4];
   unsigned char tap_map[IG_MAX_TAPS];
 };
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restrict__ scale,
-                    const float* __restrict__ bias, const __half* __restrict__ res,
-                    __half* __restrict__ y) {
+                    const float* __restrict__ bias) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = P.stages;
   const uint32_t a_bytes = (uint32_t)IG_BM * P.kbytes;
   const uint32_t b_bytes = (uint32_t)P.block_n * P.kbytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int k_elems = P.kbytes >> 1;
-  // barriers live after the tile ring
-  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  // epilogue staging (1024-aligned) and the barriers live after the tile ring
+  const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
+  const uint32_t staging = smem_base + staging_off;
+  const uint32_t bar_base = staging + EPI_STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const uint32_t res_bar = bar_base + 8u * (2 * stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,6 +89,8 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
     }
+    mbar_init(res_bar, 1);
+    prefetch_tmap(&P.epi.y_map);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -164,66 +169,22 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   } else {
     // ================================ epilogue warps ========================================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;       // GEMM row inside the tile
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % P.n_tiles;
       int mt = tile / P.n_tiles;
       int o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
-      // row -> position inside the box
-      int r = row;
-      bool valid = row < P.rows;
-      long long pos = 0, mul = 1;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ii = r % P.box[i];
-        r /= P.box[i];
-        const int oi = o[i] + ii;
-        valid = valid && (oi < P.O[i]);
-        pos += (long long)oi * mul;
-        mul *= P.O[i];
-      }
-      const int n0 = n_tile * P.block_n;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.block_n);
-      __half* yrow = y + pos * P.y_row_stride + n0;
-      const __half* rrow = res + pos * P.res_row_stride + n0;
-      for (int c0 = 0; c0 < P.block_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = n0 + c0 + h * 8;
-            if (col < P.Co) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                f[j] = __uint_as_float(v[h * 8 + j]) * __ldg(scale + col + j) + __ldg(bias + col + j);
-              if (P.has_residual) {
-                float rr[8];
-                ld8<__half>(rrow + c0 + h * 8, rr);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += rr[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], P.act);
-              st8<__half>(yrow + c0 + h * 8, f);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.block_n), staging, smem_gen + staging_off,
+                    res_bar, res_phase, quarter, lane, n_tile * P.block_n, o[0], o[1], o[2], o[3],
+                    tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (quarter == 0 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -424,6 +385,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     int bn = 16;
     for (int c : cands) {
       if (c > 256 || c > co16) continue;
+      if (c < co16 && (c % 64)) continue;   // several N tiles: TMA-store sub-tiles are 64 channels wide
       const long long tiles = (long long)P.m_tiles * cdiv(d->Co, c);
       const double waves = (double)cdiv(tiles, sm_count);
       const double cost = waves * tile_cycles(c) + 1e-3 * cdiv(d->Co, c);
@@ -438,10 +400,11 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   P.Co = d->Co;
   P.taps = wmode ? d->kt * d->kh : d->kt * d->kh * d->kw;
   P.num_kc = wmode ? 1 : d->ci_pad64 / 64;
-  P.act = d->act;
-  P.has_residual = d->has_residual;
-  P.y_row_stride = d->y_row_stride;
-  P.res_row_stride = d->has_residual ? d->res_row_stride : 0;
+  P.epi.block_n = P.block_n;
+  P.epi.Co = d->Co;
+  P.epi.rows = P.rows;
+  P.epi.act = d->act;
+  P.epi.has_residual = d->has_residual;
   {
     int cols = 2 * P.block_n, p2 = 32;
     while (p2 < cols) p2 <<= 1;
@@ -449,12 +412,13 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   }
   const int stage_bytes = (IG_BM + P.block_n) * P.kbytes;
   {
-    int st = (200 * 1024) / stage_bytes;
+    int st = (227 * 1024 - 2048 - EPI_STAGING_BYTES - 256) / stage_bytes;
     if (st > 8) st = 8;
     if (st < 2) st = 2;
     P.stages = st;
   }
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 8 * (2 * P.stages + 4) + 16;
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + EPI_STAGING_BYTES +
+                            8 * (2 * P.stages + 6) + 16;
 
   // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)
   // merged dims never merge a dim that has taps, so each non-trivial original dim maps to one
@@ -530,6 +494,41 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)cr); return PV_ERR_CUDA; }
   }
 
+  // ---- output / residual tensor maps (merged OUTPUT dims follow the input merge pattern)
+  {
+    const long long ostr_orig[4] = {1, d->Wo, (long long)d->Wo * d->Ho, (long long)d->Wo * d->Ho * d->To};
+    long long ostr[4] = {0, 0, 0, 0};
+    bool seen[4] = {false, false, false, false};
+    for (int o = 0; o < 4; ++o) {
+      const int m = pl.orig2m[o];
+      if (!seen[m]) { seen[m] = true; ostr[m] = ostr_orig[o]; }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1 && !d->has_residual) break;
+      const long long rs = pass == 0 ? d->y_row_stride : d->res_row_stride;
+      void* base = pass == 0 ? y : const_cast<void*>(residual);
+      cuuint64_t gdim[5], gstr[4];
+      cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+      gdim[0] = (cuuint64_t)d->Co;
+      box[0] = 64;
+      long long prev = rs * 2;      // byte extent covered so far (for filler dims)
+      for (int m = 0; m < 4; ++m) {
+        gdim[m + 1] = (cuuint64_t)P.O[m];
+        const long long sb = seen[m] ? ostr[m] * rs * 2 : prev;
+        gstr[m] = (cuuint64_t)sb;
+        prev = sb * (long long)P.O[m];
+        box[m + 1] = (cuuint32_t)P.box[m];
+      }
+      CUresult cr = encode(pass == 0 ? &P.epi.y_map : &P.epi.r_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, gdim,
+                           gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(%s) failed: %d", pass == 0 ? "Y" : "R", (int)cr);
+        return PV_ERR_CUDA;
+      }
+    }
+  }
+
   if (!attr_set) {
     PV_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -537,8 +536,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
-  conv3d_igemm_kernel<<<grid, IG_THREADS, smem_bytes, stream>>>(P, scale, bias, (const __half*)residual,
-                                                              (__half*)y);
+  conv3d_igemm_kernel<<<grid, IG_THREADS, smem_bytes, stream>>>(P, scale, bias);
   PV_LAUNCH_OK("conv3d_igemm_kernel");
   return PV_OK;
 }

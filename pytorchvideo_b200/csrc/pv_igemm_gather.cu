@@ -9,6 +9,7 @@
 // MMA issue, TMEM double buffering and the fused epilogue are the same as in pv_igemm.cu.
 #include "pv_common.cuh"
 #include "pv_sm100.cuh"
+#include "pv_epilogue.cuh"
 
 #include <mutex>
 
@@ -24,6 +25,7 @@ constexpr int GG_EPI_WARPS = 4;
 constexpr int GG_PROD_WARPS = 8;
 constexpr int GG_PROD_THREADS = GG_PROD_WARPS * 32;
 constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 416
+constexpr int GG_DEPTH = 3;        // k-blocks of cp.async in flight per producer thread (stages > GG_DEPTH)
 
 struct GatherParams {
   CUtensorMap b_map;
@@ -35,28 +37,30 @@ struct GatherParams {
   int num_kb;
   long long x_row_stride;
   long long M;
-  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, act, has_residual;
-  long long y_row_stride, res_row_stride;
+  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols;
+  EpiParams epi;
   int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
   unsigned int unit_d[GG_MAX_UNITS];  // packed (dt | dh<<8 | dw<<16) tap displacement (dilation applied)
 };
 
 __global__ void __launch_bounds__(GG_THREADS, 1)
 conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half* __restrict__ x,
-                           const float* __restrict__ scale, const float* __restrict__ bias,
-                           const __half* __restrict__ res, __half* __restrict__ y) {
+                           const float* __restrict__ scale, const float* __restrict__ bias) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = P.stages;
   const uint32_t b_bytes = (uint32_t)P.block_n * GG_BK * 2;
   const uint32_t stage_bytes = GG_A_BYTES + b_bytes;
-  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
+  const uint32_t staging = smem_base + staging_off;
+  const uint32_t bar_base = staging + EPI_STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const uint32_t res_bar = bar_base + 8u * (2 * stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,6 +77,8 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), GG_EPI_WARPS);
     }
+    mbar_init(res_bar, 1);
+    prefetch_tmap(&P.epi.y_map);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -89,14 +95,17 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
 
   if (warp >= PROD_WARP0) {
     // ================================ gather producers =======================================
+    // Fully asynchronous im2col gather: cp.async (zero-fill for padding / tails) straight into the
+    // swizzled A tile, GG_DEPTH k-blocks in flight per thread; a k-block is published to the MMA
+    // warp (proxy fence + mbarrier arrive) once its commit group has landed.
     const int ptid = threadIdx.x - PROD_WARP0 * 32;
     const int row = ptid & 127;
     const int half = ptid >> 7;
     const int per_thread = P.upk >> 1;                 // units per k-block handled by this thread
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t rsw = (uint32_t)(row & 7);
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage_i = 0, stage_c = 0, inflight = 0;
+    uint32_t phase_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % P.n_tiles;
       const int m_tile = tile / P.n_tiles;
@@ -112,48 +121,51 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
         xrow = x + ((((long long)n * P.Ti + t0) * P.Hi + h0) * P.Wi + w0) * P.x_row_stride;
       }
       for (int kb = 0; kb < P.num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        uint8_t* a_tile = smem_gen + stage * stage_bytes;
+        mbar_wait(empty_bar(stage_i), phase_i ^ 1u);
+        const uint32_t a_tile = smem_base + stage_i * stage_bytes;
         if (ptid == 0) {
-          mbar_arrive_expect_tx(full_bar(stage), b_bytes);
-          tma_load_2d(smem_base + stage * stage_bytes + GG_A_BYTES, &P.b_map, full_bar(stage), kb * GG_BK,
-                      n_tile * P.block_n);
+          mbar_arrive_expect_tx(full_bar(stage_i), b_bytes);
+          tma_load_2d(a_tile + GG_A_BYTES, &P.b_map, full_bar(stage_i), kb * GG_BK, n_tile * P.block_n);
         }
         const int u0 = kb * P.upk + half * per_thread;
-        if (P.gbytes == 16) {
-#pragma unroll 4
-          for (int i = 0; i < per_thread; ++i) {
-            const int u = u0 + i;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (row_ok && u < P.units_total) {
-              const unsigned int dd = P.unit_d[u];
-              const int ti = t0 + (int)(dd & 0xffu), hi = h0 + (int)((dd >> 8) & 0xffu), wi = w0 + (int)(dd >> 16);
-              if ((unsigned)ti < (unsigned)P.Ti && (unsigned)hi < (unsigned)P.Hi && (unsigned)wi < (unsigned)P.Wi)
-                v = __ldg(reinterpret_cast<const uint4*>(xrow + P.unit_off[u]));
+        for (int i = 0; i < per_thread; ++i) {
+          const int u = u0 + i;
+          const __half* src = x;
+          uint32_t nbytes = 0;
+          if (row_ok && u < P.units_total) {
+            const unsigned int dd = P.unit_d[u];
+            const int ti = t0 + (int)(dd & 0xffu), hi = h0 + (int)((dd >> 8) & 0xffu), wi = w0 + (int)(dd >> 16);
+            if ((unsigned)ti < (unsigned)P.Ti && (unsigned)hi < (unsigned)P.Hi && (unsigned)wi < (unsigned)P.Wi) {
+              src = xrow + P.unit_off[u];
+              nbytes = (uint32_t)P.gbytes;
             }
-            const uint32_t j = (uint32_t)(half * per_thread + i);       // 16B chunk index within the 128B row
-            *reinterpret_cast<uint4*>(a_tile + row_off + ((j ^ rsw) << 4)) = v;
           }
-        } else {
-#pragma unroll 4
-          for (int i = 0; i < per_thread; ++i) {
-            const int u = u0 + i;
-            uint2 v = make_uint2(0u, 0u);
-            if (row_ok && u < P.units_total) {
-              const unsigned int dd = P.unit_d[u];
-              const int ti = t0 + (int)(dd & 0xffu), hi = h0 + (int)((dd >> 8) & 0xffu), wi = w0 + (int)(dd >> 16);
-              if ((unsigned)ti < (unsigned)P.Ti && (unsigned)hi < (unsigned)P.Hi && (unsigned)wi < (unsigned)P.Wi)
-                v = __ldg(reinterpret_cast<const uint2*>(xrow + P.unit_off[u]));
-            }
-            const uint32_t ui = (uint32_t)(half * per_thread + i);      // 8B unit index within the row
-            *reinterpret_cast<uint2*>(a_tile + row_off + (((ui >> 1) ^ rsw) << 4) + ((ui & 1u) << 3)) = v;
+          const uint32_t ui = (uint32_t)(half * per_thread + i);
+          if (P.gbytes == 16) {
+            const uint32_t dst = a_tile + row_off + ((ui ^ rsw) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+          } else {
+            const uint32_t dst = a_tile + row_off + (((ui >> 1) ^ rsw) << 4) + ((ui & 1u) << 3);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
           }
         }
-        // make the generic-proxy smem writes visible to the tensor-core (async) proxy, then signal
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full_bar(stage));
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++stage_i == stages) { stage_i = 0; phase_i ^= 1u; }
+        if (++inflight > GG_DEPTH) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(GG_DEPTH) : "memory");
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar(stage_c));
+          if (++stage_c == stages) stage_c = 0;
+          --inflight;
+        }
       }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    fence_proxy_async_smem();
+    while (inflight > 0) {
+      mbar_arrive(full_bar(stage_c));
+      if (++stage_c == stages) stage_c = 0;
+      --inflight;
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ============================================
@@ -189,51 +201,19 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   } else {
     // ================================ epilogue warps ========================================
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % P.n_tiles;
       const int m_tile = tile / P.n_tiles;
-      const long long pos = (long long)m_tile * GG_BM + row;
-      const bool valid = pos < P.M;
-      const int n0 = n_tile * P.block_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.block_n);
-      __half* yrow = y + pos * P.y_row_stride + n0;
-      const __half* rrow = res + pos * P.res_row_stride + n0;
-      for (int c0 = 0; c0 < P.block_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = n0 + c0 + h * 8;
-            if (col < P.Co) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                f[j] = __uint_as_float(v[h * 8 + j]) * __ldg(scale + col + j) + __ldg(bias + col + j);
-              if (P.has_residual) {
-                float rr[8];
-                ld8<__half>(rrow + c0 + h * 8, rr);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += rr[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], P.act);
-              st8<__half>(yrow + c0 + h * 8, f);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.block_n), staging, smem_gen + staging_off,
+                    res_bar, res_phase, quarter, lane, n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0,
+                    tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (quarter == 0 && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -297,10 +277,6 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   P.M = (long long)d->N * d->To * d->Ho * d->Wo;
   P.m_tiles = (int)cdiv(P.M, GG_BM);
   P.Co = d->Co;
-  P.act = d->act;
-  P.has_residual = d->has_residual;
-  P.y_row_stride = d->y_row_stride;
-  P.res_row_stride = d->has_residual ? d->res_row_stride : 0;
   for (int it = 0; it < d->kt; ++it)
     for (int ih = 0; ih < d->kh; ++ih)
       for (int iw = 0; iw < d->kw; ++iw) {
@@ -318,8 +294,8 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   {
     const int co16 = (int)cdiv(d->Co, 16) * 16;
     int bn = co16 <= 256 ? co16 : 256;
-    // keep a few hundred tiles in flight for small layers
-    while (bn > 64 && (long long)P.m_tiles * cdiv(d->Co, bn) < 2 * sm_count && (bn / 2) % 16 == 0) bn /= 2;
+    // keep a few hundred tiles in flight for small layers (several N tiles must be multiples of 64)
+    while (bn > 64 && (long long)P.m_tiles * cdiv(d->Co, bn) < 2 * sm_count && (bn / 2) % 64 == 0) bn /= 2;
     P.block_n = bn;
     P.n_tiles = (int)cdiv(d->Co, bn);
   }
@@ -330,12 +306,30 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   }
   const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
   {
-    int st = (200 * 1024) / stage_bytes;
+    int st = (227 * 1024 - 2048 - EPI_STAGING_BYTES - 256) / stage_bytes;
     if (st > 8) st = 8;
-    if (st < 2) st = 2;
+    if (st < GG_DEPTH + 1) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
     P.stages = st;
   }
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 1024 + 8 * (2 * P.stages + 4) + 16;
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_STAGING_BYTES + 8 * (2 * P.stages + 6) + 16;
+  P.epi.block_n = P.block_n;
+  P.epi.Co = d->Co;
+  P.epi.rows = GG_BM;
+  P.epi.act = d->act;
+  P.epi.has_residual = d->has_residual;
+  for (int pass = 0; pass < 2; ++pass) {     // output / residual as [Co, M, 1, 1, 1]
+    if (pass == 1 && !d->has_residual) break;
+    const long long rs = pass == 0 ? d->y_row_stride : d->res_row_stride;
+    void* base = pass == 0 ? y : const_cast<void*>(residual);
+    cuuint64_t gdim[5] = {(cuuint64_t)d->Co, (cuuint64_t)P.M, 1, 1, 1};
+    cuuint64_t gstr[4] = {(cuuint64_t)rs * 2, (cuuint64_t)rs * 2 * (cuuint64_t)P.M, (cuuint64_t)rs * 2 * (cuuint64_t)P.M,
+                          (cuuint64_t)rs * 2 * (cuuint64_t)P.M};
+    cuuint32_t box[5] = {64, GG_BM, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = encode(pass == 0 ? &P.epi.y_map : &P.epi.r_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, gdim, gstr,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(gather %s) failed: %d", pass ? "R" : "Y", (int)cr); return PV_ERR_CUDA; }
+  }
   {
     const long long kpad = (long long)cdiv((long long)taps * d->Ci, 64) * 64;
     cuuint64_t gdim[2] = {(cuuint64_t)kpad, (cuuint64_t)d->Co};
@@ -354,8 +348,7 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
-  conv3d_igemm_gather_kernel<<<grid, GG_THREADS, smem_bytes, stream>>>(P, (const __half*)x, scale, bias,
-                                                                      (const __half*)residual, (__half*)y);
+  conv3d_igemm_gather_kernel<<<grid, GG_THREADS, smem_bytes, stream>>>(P, (const __half*)x, scale, bias);
   PV_LAUNCH_OK("conv3d_igemm_gather_kernel");
   return PV_OK;
 }
