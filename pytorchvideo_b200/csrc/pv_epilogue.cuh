@@ -5,7 +5,11 @@
 // brought in by a TMA tensor load into the SAME staging buffer and updated in place, so both the
 // residual read and the output write are full-line bulk transfers issued by one thread, with the
 // tile-edge and channel-tail clipping done by the TMA unit (no per-thread masks or address math).
-// Columns are processed in groups of <=128 (two 64-column sub-tiles, 32 KiB of staging).
+//
+// 8 epilogue warps: warp e owns TMEM lane quarter (e & 3) and the 64-column half (e >> 2) of every
+// 128-column group; folded-BN scale/bias for the tile are staged once in shared memory.  Staging is
+// 32 KiB = one 128-column group, or two alternating 64-column slots when BLOCK_N <= 64 so that the
+// previous tile's bulk store can still be draining while the next tile is staged.
 #pragma once
 #include "pv_common.cuh"
 #include "pv_sm100.cuh"
@@ -15,7 +19,10 @@ namespace sm100 {
 
 constexpr int EPI_GROUP_COLS = 128;
 constexpr int EPI_STAGING_BYTES = 2 * 128 * 128;   // two [128 rows x 64 f16] swizzled sub-tiles
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_SB_BYTES = 2 * 256 * 4;          // scale[256] + bias[256] (fp32) for the current tile
+constexpr int EPI_SMEM_BYTES = EPI_STAGING_BYTES + EPI_SB_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 
 struct EpiParams {
   CUtensorMap y_map;    // output  [Co, d1, d2, d3, d4], box [64, b1, b2, b3, b4], SWIZZLE_128B
@@ -33,81 +40,138 @@ __device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// Called by the 4 epilogue warps (128 threads) for one output tile.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if (ACT == PV_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == PV_ACT_NONE) return x;
+  return apply_act(x, ACT);
+}
+
+// One 64-column sub-tile of one row: two x32 TMEM loads, math, swizzled 16-byte cells.
+template <int ACT, bool RES>
+__device__ __forceinline__ void epi_subtile(uint32_t t_addr, uint8_t* srow, uint32_t rsw, const float* sc,
+                                            const float* bi, int ncols) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_addr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int cc = c0 + h * 8;
+      uint4* cell = reinterpret_cast<uint4*>(srow + ((((uint32_t)cc >> 3) ^ rsw) << 4));
+      const float4 s0 = *reinterpret_cast<const float4*>(sc + cc), s1 = *reinterpret_cast<const float4*>(sc + cc + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(bi + cc), b1 = *reinterpret_cast<const float4*>(bi + cc + 4);
+      float f[8];
+      f[0] = fmaf(__uint_as_float(v[h * 8 + 0]), s0.x, b0.x);
+      f[1] = fmaf(__uint_as_float(v[h * 8 + 1]), s0.y, b0.y);
+      f[2] = fmaf(__uint_as_float(v[h * 8 + 2]), s0.z, b0.z);
+      f[3] = fmaf(__uint_as_float(v[h * 8 + 3]), s0.w, b0.w);
+      f[4] = fmaf(__uint_as_float(v[h * 8 + 4]), s1.x, b1.x);
+      f[5] = fmaf(__uint_as_float(v[h * 8 + 5]), s1.y, b1.y);
+      f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), s1.z, b1.z);
+      f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), s1.w, b1.w);
+      if (RES) {
+        const uint4 rv = *cell;
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 r2 = __half22float2(rh[q]);
+          f[2 * q] += r2.x;
+          f[2 * q + 1] += r2.y;
+        }
+      }
+      uint4 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(act_t<ACT>(f[2 * q]), act_t<ACT>(f[2 * q + 1]));
+      *cell = ov;
+    }
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_subtile_res(bool res, uint32_t t_addr, uint8_t* srow, uint32_t rsw,
+                                                const float* sc, const float* bi, int ncols) {
+  if (res) epi_subtile<ACT, true>(t_addr, srow, rsw, sc, bi, ncols);
+  else epi_subtile<ACT, false>(t_addr, srow, rsw, sc, bi, ncols);
+}
+
+// Called by the 8 epilogue warps (256 threads) for one output tile.
+//   ewarp     : 0..7 index of this warp among the epilogue warps; `quarter` = hardware warp id & 3
 //   t_acc     : TMEM address of the accumulator (column base), lane field NOT yet applied
-//   staging   : shared address (1024-aligned) / generic pointer of the 32 KiB staging buffer
-//   res_bar   : mbarrier for the residual TMA loads, res_phase its running parity
-//   c1..c4    : tile origin in the output tensor map's spatial dims;  n0: first output channel
-//   tempty_bar: arrived (one lane per warp) as soon as the accumulator has been drained
+//   epi_smem  : shared address (1024-aligned) / generic pointer of the EPI_SMEM_BYTES region
+//   tile_seq  : running tile counter of this CTA (selects the staging slot when BLOCK_N <= 64)
 __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* __restrict__ scale,
                                               const float* __restrict__ bias, uint32_t t_acc,
-                                              uint32_t staging, uint8_t* staging_gen, uint32_t res_bar,
-                                              uint32_t& res_phase, int quarter, int lane, int n0, int c1,
-                                              int c2, int c3, int c4, uint32_t tempty_bar) {
+                                              uint32_t epi_smem, uint8_t* epi_gen, uint32_t res_bar,
+                                              uint32_t& res_phase, int ewarp, int quarter, int lane, int n0,
+                                              int c1, int c2, int c3, int c4, uint32_t tempty_bar,
+                                              int tile_seq) {
   const int row = quarter * 32 + lane;
-  const bool leader = (quarter == 0) && (lane == 0);
+  const int chalf = ewarp >> 2;
+  const int etid = ewarp * 32 + lane;
+  const bool leader = (etid == 0);
   const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
   const uint32_t rsw = (uint32_t)(row & 7);
+  float* sb = reinterpret_cast<float*>(epi_gen + EPI_STAGING_BYTES);
+  const bool narrow = E.block_n <= 64;           // one 64-col sub-tile per tile: alternate staging slots
+  // stage scale / bias of this N tile (zeros beyond Co keep pad lanes at exactly zero)
+  {
+    const int c = n0 + etid;
+    const bool ok = etid < E.block_n && c < E.Co;
+    sb[etid] = ok ? __ldg(scale + c) : 0.f;
+    sb[256 + etid] = ok ? __ldg(bias + c) : 0.f;
+  }
   for (int g0 = 0; g0 < E.block_n; g0 += EPI_GROUP_COLS) {
     const int gcols = min(EPI_GROUP_COLS, E.block_n - g0);
     const int nsub = (gcols + 63) >> 6;
-    // (a) staging is free once the previous group's stores have been read out of shared memory
+    const uint32_t slot = narrow ? (uint32_t)(tile_seq & 1) * 16384u : 0u;
+    // (a) the staging slot is free once the bulk store that last used it has read it out
     if (leader) {
-      tma_store_wait_read0();
+      if (narrow) tma_store_wait_read1(); else tma_store_wait_read0();
       if (E.has_residual) {
         mbar_arrive_expect_tx(res_bar, (uint32_t)(nsub * E.rows * 128));
         for (int s = 0; s < nsub; ++s)
-          tma_load_5d(staging + (uint32_t)s * 16384u, &E.r_map, res_bar, n0 + g0 + s * 64, c1, c2, c3, c4);
+          tma_load_5d(epi_smem + slot + (uint32_t)s * 16384u, &E.r_map, res_bar, n0 + g0 + s * 64, c1, c2, c3, c4);
       }
     }
+    epi_bar_sync();                 // slot free + scale/bias visible
     if (E.has_residual) {
       mbar_wait(res_bar, res_phase);
       res_phase ^= 1u;
-    } else {
-      epi_bar_sync();
     }
-    // (b) drain the accumulator, 16 columns at a time
-    for (int c0 = 0; c0 < gcols; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(t_row + (uint32_t)(g0 + c0), v);
-      tmem_ld_wait();
-      const int sub = c0 >> 6;
-      uint8_t* srow = staging_gen + sub * 16384 + row * 128;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = n0 + g0 + c0 + h * 8;          // global output channel of the first of 8 lanes
-        const uint32_t j = (uint32_t)(((c0 & 63) >> 3) + h);   // 16B chunk inside the 128B row
-        uint4* cell = reinterpret_cast<uint4*>(srow + ((j ^ rsw) << 4));
-        float f[8];
-        if (col < E.Co) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            f[q] = __uint_as_float(v[h * 8 + q]) * __ldg(scale + col + q) + __ldg(bias + col + q);
-          if (E.has_residual) {
-            const uint4 rv = *cell;
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 r2 = __half22float2(rh[q]);
-              f[2 * q] += r2.x;
-              f[2 * q + 1] += r2.y;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = apply_act(f[q], E.act);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = 0.f;
-        }
-        uint4 ov;
-        __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
-        *cell = ov;
+    // (b) drain this warp's 64-column half of the group
+    if (chalf < nsub) {
+      const int cbase = g0 + chalf * 64;
+      const int ncols = min(64, gcols - chalf * 64);
+      uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
+      const float* sc = sb + cbase;
+      const float* bi = sb + 256 + cbase;
+      switch (E.act) {
+        case PV_ACT_RELU: epi_subtile_res<PV_ACT_RELU>(E.has_residual, t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_NONE: epi_subtile_res<PV_ACT_NONE>(E.has_residual, t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_SWISH: epi_subtile_res<PV_ACT_SWISH>(E.has_residual, t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_GELU: epi_subtile_res<PV_ACT_GELU>(E.has_residual, t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        default: epi_subtile_res<PV_ACT_SIGMOID>(E.has_residual, t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
       }
     }
     if (g0 + EPI_GROUP_COLS >= E.block_n) {   // accumulator fully read: hand TMEM back to the MMA warp
@@ -120,7 +184,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* _
     epi_bar_sync();
     if (leader) {
       for (int s = 0; s < nsub; ++s)
-        tma_store_5d(&E.y_map, staging + (uint32_t)s * 16384u, n0 + g0 + s * 64, c1, c2, c3, c4);
+        tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, n0 + g0 + s * 64, c1, c2, c3, c4);
       tma_store_commit();
     }
   }

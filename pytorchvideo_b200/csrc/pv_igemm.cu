@@ -30,7 +30,7 @@ constexpr int IG_BM = 128;        // UMMA M
 constexpr int IG_BK = 64;         // K per pipeline stage (one 128B swizzle row of f16)
 constexpr int IG_MAX_TAPS = 64;
 constexpr int IG_MAX_MAPS = 8;
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = (2 + EPI_WARPS) * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;   // 16 KiB
 
 struct IgemmParams {
@@ -48,6 +48,7 @@ struct IgemmParams {
   int kbytes;      // bytes of K per smem row and pipeline stage: 128 (64 ch, SW128) | 64 | 32 (window mode)
   int stages;
   int tmem_cols;
+  int acc_stride;   // TMEM columns between the two accumulator stages (block_n rounded up to 32)
   EpiParams epi;
   signed char tap_q[IG_MAX_TAPS][4];
   unsigned char tap_map[IG_MAX_TAPS];
@@ -67,7 +68,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   // epilogue staging (1024-aligned) and the barriers live after the tile ring
   const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
   const uint32_t staging = smem_base + staging_off;
-  const uint32_t bar_base = staging + EPI_STAGING_BYTES;
+  const uint32_t bar_base = staging + EPI_SMEM_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
@@ -87,7 +88,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), EPI_WARPS);   // one arrive per epilogue warp
     }
     mbar_init(res_bar, 1);
     prefetch_tmap(&P.epi.y_map);
@@ -146,7 +147,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.block_n);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -169,9 +170,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   } else {
     // ================================ epilogue warps ========================================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    int acc = 0;
+    const int ewarp = warp - 2;
+    int acc = 0, tile_seq = 0;
     uint32_t acc_phase = 0, res_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
       const int n_tile = tile % P.n_tiles;
       int mt = tile / P.n_tiles;
       int o[4];
@@ -179,12 +181,12 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.block_n), staging, smem_gen + staging_off,
-                    res_bar, res_phase, quarter, lane, n_tile * P.block_n, o[0], o[1], o[2], o[3],
-                    tempty_bar(acc));
+      epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
+                    res_bar, res_phase, ewarp, quarter, lane, n_tile * P.block_n, o[0], o[1], o[2], o[3],
+                    tempty_bar(acc), tile_seq);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (quarter == 0 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
+    if (ewarp == 0 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -406,18 +408,19 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
   {
-    int cols = 2 * P.block_n, p2 = 32;
+    P.acc_stride = (P.block_n + 31) / 32 * 32;
+    int cols = 2 * P.acc_stride, p2 = 32;
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
   const int stage_bytes = (IG_BM + P.block_n) * P.kbytes;
   {
-    int st = (227 * 1024 - 2048 - EPI_STAGING_BYTES - 256) / stage_bytes;
+    int st = (227 * 1024 - 2048 - EPI_SMEM_BYTES - 256) / stage_bytes;
     if (st > 8) st = 8;
     if (st < 2) st = 2;
     P.stages = st;
   }
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + EPI_STAGING_BYTES +
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + EPI_SMEM_BYTES +
                             8 * (2 * P.stages + 6) + 16;
 
   // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)

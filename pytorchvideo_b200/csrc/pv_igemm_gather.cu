@@ -21,10 +21,10 @@ constexpr int GG_BM = 128;
 constexpr int GG_BK = 64;
 constexpr int GG_A_BYTES = GG_BM * GG_BK * 2;
 constexpr int GG_MAX_UNITS = 256;
-constexpr int GG_EPI_WARPS = 4;
+constexpr int GG_EPI_WARPS = EPI_WARPS;   // 8
 constexpr int GG_PROD_WARPS = 8;
 constexpr int GG_PROD_THREADS = GG_PROD_WARPS * 32;
-constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 416
+constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 544
 constexpr int GG_DEPTH = 3;        // k-blocks of cp.async in flight per producer thread (stages > GG_DEPTH)
 
 struct GatherParams {
@@ -37,7 +37,7 @@ struct GatherParams {
   int num_kb;
   long long x_row_stride;
   long long M;
-  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols;
+  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, acc_stride;
   EpiParams epi;
   int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
   unsigned int unit_d[GG_MAX_UNITS];  // packed (dt | dh<<8 | dw<<16) tap displacement (dilation applied)
@@ -54,7 +54,7 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   const uint32_t stage_bytes = GG_A_BYTES + b_bytes;
   const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
   const uint32_t staging = smem_base + staging_off;
-  const uint32_t bar_base = staging + EPI_STAGING_BYTES;
+  const uint32_t bar_base = staging + EPI_SMEM_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
@@ -64,8 +64,8 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int MMA_WARP = GG_EPI_WARPS;          // warp 4
-  constexpr int PROD_WARP0 = GG_EPI_WARPS + 1;    // warps 5..12
+  constexpr int MMA_WARP = GG_EPI_WARPS;          // warp 8
+  constexpr int PROD_WARP0 = GG_EPI_WARPS + 1;    // warps 9..16
 
   if (warp == MMA_WARP && lane == 0) {
     prefetch_tmap(&P.b_map);
@@ -178,7 +178,7 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.block_n);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -201,19 +201,19 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   } else {
     // ================================ epilogue warps ========================================
     const int quarter = warp & 3;
-    int acc = 0;
+    int acc = 0, tile_seq = 0;
     uint32_t acc_phase = 0, res_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
       const int n_tile = tile % P.n_tiles;
       const int m_tile = tile / P.n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.block_n), staging, smem_gen + staging_off,
-                    res_bar, res_phase, quarter, lane, n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0,
-                    tempty_bar(acc));
+      epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
+                    res_bar, res_phase, warp, quarter, lane, n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0,
+                    tempty_bar(acc), tile_seq);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (quarter == 0 && lane == 0) tma_store_wait_all();
+    if (warp == 0 && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -300,18 +300,19 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
     P.n_tiles = (int)cdiv(d->Co, bn);
   }
   {
-    int cols = 2 * P.block_n, p2 = 32;
+    P.acc_stride = (P.block_n + 31) / 32 * 32;
+    int cols = 2 * P.acc_stride, p2 = 32;
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
   const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
   {
-    int st = (227 * 1024 - 2048 - EPI_STAGING_BYTES - 256) / stage_bytes;
+    int st = (227 * 1024 - 2048 - EPI_SMEM_BYTES - 256) / stage_bytes;
     if (st > 8) st = 8;
     if (st < GG_DEPTH + 1) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
     P.stages = st;
   }
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_STAGING_BYTES + 8 * (2 * P.stages + 6) + 16;
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_SMEM_BYTES + 8 * (2 * P.stages + 6) + 16;
   P.epi.block_n = P.block_n;
   P.epi.Co = d->Co;
   P.epi.rows = GG_BM;
