@@ -416,7 +416,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   const int stage_bytes = (IG_BM + P.block_n) * P.kbytes;
   {
     int st = (227 * 1024 - 2048 - EPI_SMEM_BYTES - 256) / stage_bytes;
-    if (st > 8) st = 8;
+    if (st > 24) st = 24;
     if (st < 2) st = 2;
     P.stages = st;
   }

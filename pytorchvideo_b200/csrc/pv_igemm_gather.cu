@@ -70,7 +70,7 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   if (warp == MMA_WARP && lane == 0) {
     prefetch_tmap(&P.b_map);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), GG_PROD_THREADS + 1);   // every producer thread + the expect_tx arrive
+      mbar_init(full_bar(s), GG_PROD_WARPS + 1);   // one arrive per producer warp + the expect_tx arrive
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -154,7 +154,8 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
         if (++inflight > GG_DEPTH) {
           asm volatile("cp.async.wait_group %0;" ::"n"(GG_DEPTH) : "memory");
           fence_proxy_async_smem();
-          mbar_arrive(full_bar(stage_c));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(stage_c));
           if (++stage_c == stages) stage_c = 0;
           --inflight;
         }
@@ -162,8 +163,9 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     fence_proxy_async_smem();
+    __syncwarp();
     while (inflight > 0) {
-      mbar_arrive(full_bar(stage_c));
+      if (lane == 0) mbar_arrive(full_bar(stage_c));
       if (++stage_c == stages) stage_c = 0;
       --inflight;
     }
@@ -308,7 +310,7 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
   {
     int st = (227 * 1024 - 2048 - EPI_SMEM_BYTES - 256) / stage_bytes;
-    if (st > 8) st = 8;
+    if (st > 12) st = 12;
     if (st < GG_DEPTH + 1) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
     P.stages = st;
   }
