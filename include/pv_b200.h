@@ -150,6 +150,10 @@ typedef struct pv_conv3d_desc {
    * x_w_pad zero pixels on the left (>= pw) and are x_w_phys pixels wide in memory (written that
    * way by pv_ncdhw_to_ndhwc_padw); Wi stays the logical width.  0 = ordinary layout.           */
   int x_w_pad, x_w_phys;
+  /* Depthwise path only: element distance between consecutive samples of x / y when a sample is
+   * not T*H*W*row_stride apart (MViT token tensors carry a cls row in front of every sample's
+   * T*H*W patch tokens).  0 = densely packed.                                                   */
+  long long x_batch_stride, y_batch_stride;
 } pv_conv3d_desc;
 
 int pv_conv3d_fwd(const pv_conv3d_desc* d, int algo, const void* x, const void* w,
@@ -170,6 +174,7 @@ typedef struct pv_pool3d_desc {
   int To, Ho, Wo;
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
   long long x_row_stride, y_row_stride;
+  long long x_batch_stride, y_batch_stride;   /* 0 = densely packed (see pv_conv3d_desc) */
 } pv_pool3d_desc;
 int pv_pool3d_fwd(const pv_pool3d_desc* d, const void* x, void* y, void* stream);
 
@@ -198,7 +203,9 @@ int pv_head_reduce(const void* x, int dtype, long long row_stride, int N, long l
 
 /* ---------------------------------------------------------------------------------------------
  * MViT pieces (layers/attention.py).
- * pv_layernorm : y = (x-mean)/sqrt(var+eps)*gamma+beta over the last dim (f32 statistics)
+ * pv_layernorm : y = (x-mean)/sqrt(var+eps)*gamma+beta over C channels (f32 statistics); every row
+ *                holds `groups` consecutive groups of C channels normalised independently with the
+ *                same gamma/beta (groups = heads for the per-head norm_q/k/v, attention.py:200-205)
  *                nn.LayerNorm(eps=1e-6) at attention.py:655,703 / vision_transformers.py:333.
  * pv_linear    : y[m][n] = act(sum_k x[m][k] w[n][k] + bias[n]) (+ residual[m][n])
  *                nn.Linear at attention.py:93-95,315-320,541,716  (routes to the conv kernels
@@ -208,9 +215,18 @@ int pv_head_reduce(const void* x, int dtype, long long row_stride, int N, long l
  *                N_q x N_k matrix is never materialised.  q/k/v/o are [B][N][H][D] with
  *                explicit row strides (elements between consecutive tokens), D = head dim.
  * ------------------------------------------------------------------------------------------- */
-int pv_layernorm(const void* x, void* y, int dtype, long long rows, int C,
+int pv_layernorm(const void* x, void* y, int dtype, long long rows, int groups, int C,
                  long long x_row_stride, long long y_row_stride, const float* gamma,
                  const float* beta, float eps, void* stream);
+/* Strided row copy dst[r][0:C] = src[r][0:C] (cls-token rows around the pooling ops). */
+int pv_copy_rows(const void* src, void* dst, int dtype, long long rows, int C,
+                 long long src_row_stride, long long dst_row_stride, void* stream);
+/* MViT cls token + positional encoding (layers/positional_encoding.py:112-136):
+ *   y[b][0][:]   = pos[0][:]                      (pos[0] = cls_token + pos_embed_class, f32)
+ *   y[b][1+i][:] = x[b][i][:] + pos[1+i][:]       (pos[1+i] = spatial[i %% HW] + temporal[i / HW])
+ * x: [B][n_patch][C] (row stride x_row_stride), y: [B][1+n_patch][C] dense.                     */
+int pv_add_pos_cls(const void* x, void* y, int dtype, int B, long long n_patch, int C,
+                   long long x_row_stride, const float* pos, int has_cls, void* stream);
 typedef struct pv_attention_desc {
   int dtype;
   int B, H, Nq, Nk, D;

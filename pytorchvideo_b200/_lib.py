@@ -34,7 +34,8 @@ class Conv3dDesc(C.Structure):
                 ("dt", C.c_int), ("dh", C.c_int), ("dw", C.c_int),
                 ("groups", C.c_int), ("act", C.c_int), ("has_residual", C.c_int),
                 ("x_row_stride", c_ll), ("y_row_stride", c_ll), ("res_row_stride", c_ll),
-                ("ci_pad64", C.c_int), ("x_w_pad", C.c_int), ("x_w_phys", C.c_int)]
+                ("ci_pad64", C.c_int), ("x_w_pad", C.c_int), ("x_w_phys", C.c_int),
+                ("x_batch_stride", c_ll), ("y_batch_stride", c_ll)]
 
 
 class Pool3dDesc(C.Structure):
@@ -44,7 +45,8 @@ class Pool3dDesc(C.Structure):
                 ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int),
                 ("st", C.c_int), ("sh", C.c_int), ("sw", C.c_int),
                 ("pt", C.c_int), ("ph", C.c_int), ("pw", C.c_int),
-                ("x_row_stride", c_ll), ("y_row_stride", c_ll)]
+                ("x_row_stride", c_ll), ("y_row_stride", c_ll),
+                ("x_batch_stride", c_ll), ("y_batch_stride", c_ll)]
 
 
 class AttentionDesc(C.Structure):
@@ -84,8 +86,10 @@ SIGNATURES = {
                                C.c_int, c_vp]),
     "pv_head_reduce": (C.c_int, [c_vp, C.c_int, c_ll, C.c_int, c_ll, C.c_int, C.c_int, c_vp,
                                  c_vp]),
-    "pv_layernorm": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, c_ll, c_ll, c_vp, c_vp,
+    "pv_layernorm": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_ll, c_ll, c_vp, c_vp,
                                C.c_float, c_vp]),
+    "pv_copy_rows": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, c_ll, c_ll, c_vp]),
+    "pv_add_pos_cls": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_ll, C.c_int, c_ll, c_vp, C.c_int, c_vp]),
     "pv_attention_fwd": (C.c_int, [C.POINTER(AttentionDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 

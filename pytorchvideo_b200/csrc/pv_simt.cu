@@ -194,6 +194,9 @@ dwconv3d_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__
   int ho = (int)(r % d.Ho); r /= d.Ho;
   int to = (int)(r % d.To); int n = (int)(r / d.To);
   const int t0 = to * d.st - d.pt, h0 = ho * d.sh - d.ph, w0 = wo * d.sw - d.pw;
+  const long long xbs = d.x_batch_stride ? d.x_batch_stride : (long long)d.Ti * d.Hi * d.Wi * d.x_row_stride;
+  const long long ybs = d.y_batch_stride ? d.y_batch_stride : (long long)d.To * d.Ho * d.Wo * d.y_row_stride;
+  const long long mo = (((long long)to) * d.Ho + ho) * d.Wo + wo;   // position inside the sample
 
   float acc[8];
 #pragma unroll
@@ -205,7 +208,7 @@ dwconv3d_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__
     for (int kh_ = 0; kh_ < d.kh; ++kh_) {
       const int hi = h0 + kh_ * d.dh;
       if ((unsigned)hi >= (unsigned)d.Hi) continue;
-      const T* row = x + (((long long)n * d.Ti + ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
+      const T* row = x + (long long)n * xbs + (((long long)ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
       const T* wrow = w + (long long)((kt_ * d.kh + kh_) * d.kw) * d.Co + c;
       for (int kw_ = 0; kw_ < d.kw; ++kw_) {
         const int wi = w0 + kw_ * d.dw;
@@ -229,7 +232,7 @@ dwconv3d_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], d.act);
-  st8<T>(y + m * d.y_row_stride + c, v);
+  st8<T>(y + (long long)n * ybs + mo * d.y_row_stride + c, v);
 }
 
 // =============================================================================================
@@ -248,6 +251,8 @@ pool3d_kernel(pv_pool3d_desc d, const T* __restrict__ x, T* __restrict__ y, long
   int to = (int)(r % d.To); int n = (int)(r / d.To);
   const int t0 = to * d.st - d.pt, h0 = ho * d.sh - d.ph, w0 = wo * d.sw - d.pw;
   const bool is_max = d.mode == PV_POOL_MAX;
+  const long long xbs = d.x_batch_stride ? d.x_batch_stride : (long long)d.Ti * d.Hi * d.Wi * d.x_row_stride;
+  const long long ybs = d.y_batch_stride ? d.y_batch_stride : (long long)d.To * d.Ho * d.Wo * d.y_row_stride;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = is_max ? -INFINITY : 0.f;
@@ -257,7 +262,7 @@ pool3d_kernel(pv_pool3d_desc d, const T* __restrict__ x, T* __restrict__ y, long
     for (int kh_ = 0; kh_ < d.kh; ++kh_) {
       const int hi = h0 + kh_;
       if ((unsigned)hi >= (unsigned)d.Hi) continue;
-      const T* row = x + (((long long)n * d.Ti + ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
+      const T* row = x + (long long)n * xbs + (((long long)ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
       for (int kw_ = 0; kw_ < d.kw; ++kw_) {
         const int wi = w0 + kw_;
         if ((unsigned)wi >= (unsigned)d.Wi) continue;
@@ -273,7 +278,7 @@ pool3d_kernel(pv_pool3d_desc d, const T* __restrict__ x, T* __restrict__ y, long
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= inv;
   }
-  st8<T>(y + m * d.y_row_stride + c, acc);
+  st8<T>(y + (long long)n * ybs + ((((long long)to) * d.Ho + ho) * d.Wo + wo) * d.y_row_stride + c, acc);
 }
 
 // Global pooling (kernel == whole T x H x W extent, the head pools): one CTA per (sample, 64-channel
@@ -455,13 +460,15 @@ __global__ void head_reduce_kernel(const T* __restrict__ x, long long row_stride
 // =============================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
+layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int groups, int C,
                  long long x_row_stride, long long y_row_stride, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long rg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (row, group)
+  if (rg >= rows * groups) return;
+  const long long row = rg / groups;
+  const int grp = (int)(rg - row * groups);
   const int lane = threadIdx.x & 31;
-  const T* xr = x + row * x_row_stride;
+  const T* xr = x + row * x_row_stride + (long long)grp * C;
   float s = 0.f;
   for (int c = lane * 8; c < C; c += 256) {
     float v[8];
@@ -480,7 +487,7 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int
   }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)C + eps);
-  T* yr = y + row * y_row_stride;
+  T* yr = y + row * y_row_stride + (long long)grp * C;
   for (int c = lane * 8; c < C; c += 256) {
     float v[8];
     ld8<T>(xr + c, v);
@@ -489,6 +496,42 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int
       v[i] = (v[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
     st8<T>(yr + c, v);
   }
+}
+
+template <typename T>
+__global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, int C,
+                                 long long ss, long long ds) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = C >> 3;
+  if (e >= rows * G) return;
+  const long long r = e / G;
+  const int c = (int)(e - r * G) * 8;
+  float v[8];
+  ld8<T>(src + r * ss + c, v);
+  st8<T>(dst + r * ds + c, v);
+}
+
+template <typename T>
+__global__ void add_pos_cls_kernel(const T* __restrict__ x, T* __restrict__ y, long long n_patch, int C,
+                                   long long x_row_stride, const float* __restrict__ pos, int has_cls,
+                                   long long total) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = C >> 3;
+  const int c = (int)(e % G) * 8;
+  long long r = e / G;                         // output row over B * (has_cls + n_patch)
+  const long long nrow = n_patch + has_cls;
+  const long long b = r / nrow, i = r - b * nrow;
+  float v[8];
+  if (has_cls && i == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldg(pos + c + q);
+  } else {
+    ld8<T>(x + (b * n_patch + (i - has_cls)) * x_row_stride + c, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] += __ldg(pos + i * C + c + q);
+  }
+  st8<T>(y + r * C + c, v);
 }
 
 }  // namespace pv
@@ -539,6 +582,40 @@ extern "C" int pv_ncdhw_to_ndhwc_padw(const void* src, int src_dtype, void* dst,
   else { set_error("unsupported dtype pair %d->%d", src_dtype, dst_dtype); return PV_ERR_INVALID; }
 #undef PV_CASE
   PV_LAUNCH_OK("ncdhw_to_ndhwc_padw_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_copy_rows(const void* src, void* dst, int dtype, long long rows, int C,
+                            long long src_row_stride, long long dst_row_stride, void* stream) {
+  PV_CHECK_ARG(src && dst, "null pointer");
+  PV_CHECK_ARG(C % 8 == 0 && src_row_stride % 8 == 0 && dst_row_stride % 8 == 0, "C/strides %% 8");
+  const long long total = rows * (C / 8);
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+  if (dtype == PV_F16)
+    copy_rows_kernel<__half><<<grid, block, 0, s>>>((const __half*)src, (__half*)dst, rows, C, src_row_stride, dst_row_stride);
+  else if (dtype == PV_F32)
+    copy_rows_kernel<float><<<grid, block, 0, s>>>((const float*)src, (float*)dst, rows, C, src_row_stride, dst_row_stride);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("copy_rows_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_add_pos_cls(const void* x, void* y, int dtype, int B, long long n_patch, int C,
+                              long long x_row_stride, const float* pos, int has_cls, void* stream) {
+  PV_CHECK_ARG(x && y && pos, "null pointer");
+  PV_CHECK_ARG(C % 8 == 0 && x_row_stride % 8 == 0, "C/strides %% 8");
+  const long long total = (long long)B * (n_patch + (has_cls ? 1 : 0)) * (C / 8);
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+  if (dtype == PV_F16)
+    add_pos_cls_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, n_patch, C, x_row_stride, pos, has_cls ? 1 : 0, total);
+  else if (dtype == PV_F32)
+    add_pos_cls_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, n_patch, C, x_row_stride, pos, has_cls ? 1 : 0, total);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("add_pos_cls_kernel");
   return PV_OK;
 }
 
@@ -633,7 +710,7 @@ extern "C" int pv_pool3d_fwd(const pv_pool3d_desc* d, const void* x, void* y, vo
   if (total == 0) return PV_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (to == 1 && ho == 1 && wo == 1 && d->kt == d->Ti && d->kh == d->Hi && d->kw == d->Wi && d->pt == 0 &&
-      d->ph == 0 && d->pw == 0 && d->N <= 65535) {
+      d->ph == 0 && d->pw == 0 && d->N <= 65535 && d->x_batch_stride == 0 && d->y_batch_stride == 0) {
     const long long npos = (long long)d->Ti * d->Hi * d->Wi;
     dim3 grid((unsigned)cdiv(d->C, 64), d->N), block(256);
     if (d->dtype == PV_F16)
@@ -724,19 +801,20 @@ extern "C" int pv_head_reduce(const void* x, int dtype, long long row_stride, in
   return PV_OK;
 }
 
-extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, int C,
+extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, int groups, int C,
                             long long x_row_stride, long long y_row_stride, const float* gamma,
                             const float* beta, float eps, void* stream) {
   PV_CHECK_ARG(x && y && gamma && beta, "null pointer");
-  PV_CHECK_ARG(C % 8 == 0 && x_row_stride % 8 == 0 && y_row_stride % 8 == 0, "C/strides %% 8");
+  PV_CHECK_ARG(groups >= 1 && C % 8 == 0 && x_row_stride % 8 == 0 && y_row_stride % 8 == 0, "C/strides %% 8");
+  PV_CHECK_ARG(x_row_stride >= (long long)groups * C && y_row_stride >= (long long)groups * C, "row stride < groups*C");
   if (rows == 0) return PV_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((unsigned)cdiv(rows, 8)), block(256);
+  dim3 grid((unsigned)cdiv(rows * groups, 8)), block(256);
   if (dtype == PV_F16)
-    layernorm_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, rows, C, x_row_stride,
+    layernorm_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, rows, groups, C, x_row_stride,
                                                  y_row_stride, gamma, beta, eps);
   else if (dtype == PV_F32)
-    layernorm_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, rows, C, x_row_stride,
+    layernorm_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, rows, groups, C, x_row_stride,
                                                 y_row_stride, gamma, beta, eps);
   else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
   PV_LAUNCH_OK("layernorm_kernel");

@@ -306,3 +306,113 @@ def lower_only(model, example_inputs, dtype="f16", use_tcgen05=True):
     if isinstance(out, TRef):
         out = plan.emit_to_ncdhw(out, "output.to_ncdhw")
     return plan, out[1]
+
+
+# =============================================================================================
+# MViT lowering (models/vision_transformers.py:172-182, layers/attention.py)
+# =============================================================================================
+from . import plan as PL  # noqa: E402
+
+
+def _lower_mvit_block(low, blk, x, thw, name):
+    p = low.p
+    attn = blk.attn
+    if attn.pool_first:
+        raise NotImplementedError("pool_first=True is not used by any hub MViT and has no B200 lowering")
+    if getattr(blk, "norm1_is_batchnorm_1d", False) or getattr(blk, "norm2_is_batchnorm_1d", False):
+        raise NotImplementedError("batchnorm MViT variant unsupported")
+    has_cls = attn.has_cls_embed
+    heads, dim_att = attn.num_heads, attn.dim_out
+    xn = PL.emit_layernorm(p, x, blk.norm1, name + ".norm1")
+    # q/k/v projections as ONE GEMM over concatenated weights; q, k, v are channel slices of its output
+    if attn.separate_qkv:
+        w = torch.cat([attn.q.weight, attn.k.weight, attn.v.weight], 0)
+        b = None if attn.q.bias is None else torch.cat([attn.q.bias, attn.k.bias, attn.v.bias], 0)
+    else:
+        w, b = attn.qkv.weight, attn.qkv.bias
+    qkv = PL.emit_linear(p, xn, w, b, L.ACT_NONE, None, name + ".attn.qkv")
+    q, k, v = (PL.channel_slice(qkv, i * dim_att, dim_att) for i in range(3))
+    thw_q = thw
+    if getattr(attn, "pool_q", None) is not None:
+        q, thw_q = PL.emit_token_pool(p, q, thw, attn.pool_q, getattr(attn, "norm_q", None), heads, has_cls, name + ".attn.pool_q")
+    if getattr(attn, "pool_k", None) is not None:
+        k, _ = PL.emit_token_pool(p, k, thw, attn.pool_k, getattr(attn, "norm_k", None), heads, has_cls, name + ".attn.pool_k")
+    if getattr(attn, "pool_v", None) is not None:
+        v, _ = PL.emit_token_pool(p, v, thw, attn.pool_v, getattr(attn, "norm_v", None), heads, has_cls, name + ".attn.pool_v")
+    o = PL.emit_attention(p, q, k, v, heads, attn.scale, attn.residual_pool, name + ".attn.core")
+    widen = blk.dim != blk.dim_out
+    if blk.dim_mul_in_att and widen:
+        x = PL.emit_linear(p, xn, blk.proj.weight, blk.proj.bias, L.ACT_NONE, None, name + ".proj")
+    x_res = x
+    if getattr(blk, "pool_skip", None) is not None:
+        x_res, _ = PL.emit_token_pool(p, x, thw, blk.pool_skip, None, 1, has_cls, name + ".pool_skip")
+    x = PL.emit_linear(p, o, attn.proj.weight, attn.proj.bias, L.ACT_NONE, x_res, name + ".attn.proj")
+    xn2 = PL.emit_layernorm(p, x, blk.norm2, name + ".norm2")
+    if type(blk.mlp.act).__name__ != "GELU" or getattr(blk.mlp.act, "approximate", "none") != "none":
+        raise NotImplementedError("Mlp activation must be exact GELU")
+    h = PL.emit_linear(p, xn2, blk.mlp.fc1.weight, blk.mlp.fc1.bias, L.ACT_GELU, None, name + ".mlp.fc1")
+    if (not blk.dim_mul_in_att) and widen:
+        x = PL.emit_linear(p, xn2, blk.proj.weight, blk.proj.bias, L.ACT_NONE, None, name + ".proj")
+    x = PL.emit_linear(p, h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, L.ACT_NONE, x, name + ".mlp.fc2")
+    return x, thw_q
+
+
+def _lower_mvit(self, m, x, name):
+    p = self.p
+    pe = m.patch_embed
+    if type(pe).__name__ != "PatchEmbed":
+        raise NotImplementedError("MViT without a conv patch embedding is unsupported")
+    x = self.conv(x, pe.patch_model, None, None, None, "patch_embed.patch_model")
+    enc = m.cls_positional_encoding
+    T, H, W = enc.patch_embed_shape()
+    if (x.T, x.H, x.W) != (T, H, W):
+        raise RuntimeError("input clip gives a %s patch grid but the model was built for %s" % ((x.T, x.H, x.W), (T, H, W)))
+    has_cls = bool(enc.cls_embed_on)
+    with torch.no_grad():
+        if enc.sep_pos_embed:
+            pos = enc.pos_embed_spatial.detach().float().cpu().repeat(1, enc.num_temporal_patch, 1) + \
+                torch.repeat_interleave(enc.pos_embed_temporal.detach().float().cpu(), enc.num_spatial_patch, dim=1)
+            if has_cls:
+                pos = torch.cat([enc.pos_embed_class.detach().float().cpu(), pos], 1)
+        else:
+            pos = enc.pos_embed.detach().float().cpu().clone()
+        pos = pos[0].clone()
+        if has_cls:
+            pos[0] += enc.cls_token.detach().float().cpu()[0, 0]
+    x = PL.emit_pos_cls(p, x, pos, has_cls, "cls_positional_encoding")
+    thw = (T, H, W)
+    for i, blk in enumerate(m.blocks):
+        x, thw = _lower_mvit_block(self, blk, x, thw, "blocks.%d" % i)
+    head = m.head
+    if type(head).__name__ == "Identity":
+        raise NotImplementedError("headless MViT output is unsupported")
+    if type(head).__name__ != "VisionTransformerBasicHead":
+        raise NotImplementedError("MViT head %s unsupported" % type(head).__name__)
+    mode = head.sequence_pool.mode if head.sequence_pool is not None else None
+    ne = m.norm_embed
+    if mode == "cls":
+        # only the cls row reaches the head: normalise just those B rows
+        if type(ne).__name__ == "LayerNorm":
+            x = PL.emit_layernorm(p, x, ne, "norm_embed", rows_stride=x.npos * x.row_stride, rows=x.N)
+        else:
+            x = TRef(x.buf, x.N, 1, 1, 1, x.C, Cp=x.C, ch_off=x.ch_off, row_stride=x.npos * x.row_stride)
+    elif mode == "mean":
+        if type(ne).__name__ == "LayerNorm":
+            x = PL.emit_layernorm(p, x, ne, "norm_embed")
+        x = p.emit_pool(x, L.POOL_AVG, (1, 1, x.W), (1, 1, x.W), (0, 0, 0), "head.sequence_pool")
+    else:
+        raise NotImplementedError("sequence_pool=None MViT heads are unsupported")
+    x = PL.emit_linear(p, x, head.proj.weight, head.proj.bias, L.ACT_NONE, None, "head.proj")
+    act = head.activation
+    softmax = False
+    if act is not None:
+        if type(act).__name__ == "Softmax":
+            softmax = True
+        elif type(act).__name__ == "Sigmoid":
+            x = p.emit_act(x, L.ACT_SIGMOID, "head.activation")
+        else:
+            raise NotImplementedError("head activation unsupported")
+    return p.emit_head_reduce(x, softmax, "head.output")
+
+
+Lowering.lower_MultiscaleVisionTransformers = _lower_mvit

@@ -370,3 +370,164 @@ class Plan:
             p.retarget(buf, off, cp_total)
             off += p.Cp
         return TRef(buf, p0.N, p0.T, p0.H, p0.W, c_total, Cp=cp_total, ch_off=0, row_stride=cp_total)
+
+
+# =============================================================================================
+# Token-major (MViT) emitters.  A token tensor [B, Ntok, C] is a TRef with T=H=1, W=Ntok.
+# =============================================================================================
+def _tok(plan, B, ntok, C, dt=None):
+    return plan.new_tensor(B, 1, 1, ntok, C, Cp=C, dt=dt)
+
+
+def emit_linear(plan, x, weight, bias, act=L.ACT_NONE, residual=None, name="linear"):
+    """nn.Linear on tokens = 1x1x1 convolution (tcgen05 implicit GEMM in f16 mode)."""
+    w = weight.reshape(weight.shape[0], weight.shape[1], 1, 1, 1)
+    return plan.emit_conv(x, w, bias, None, (1, 1, 1), (0, 0, 0), (1, 1, 1), 1, act, residual, name)
+
+
+def emit_layernorm(plan, x, ln, name="ln", rows_stride=None, rows=None):
+    """LayerNorm over the channel dim of every token (or of `rows` rows spaced rows_stride apart)."""
+    C = x.C
+    assert tuple(ln.normalized_shape) == (C,), "LayerNorm width mismatch"
+    g = plan.const(ln.weight.detach().float().cpu())
+    b = plan.const(ln.bias.detach().float().cpu())
+    eps = float(ln.eps)
+    n_rows = x.N * x.npos if rows is None else rows
+    xs = x.row_stride if rows_stride is None else rows_stride
+    y = plan.new_tensor(x.N, 1, 1, x.npos if rows is None else 1, C, Cp=C)
+    lib = plan.lib
+
+    def fn(stream):
+        L.check(lib.pv_layernorm(x.ptr(), y.ptr(), x.dt, n_rows, 1, C, xs, y.row_stride, g.data_ptr(), b.data_ptr(),
+                                 eps, stream), "pv_layernorm(%s)" % name)
+    plan.add(name, fn, "other", 0.0, n_rows * C * 4)
+    return y
+
+
+def emit_pos_cls(plan, x, pos_table, has_cls, name="posenc"):
+    """x: patch tokens as produced by the patch-embed conv [B, T', H', W', C] -> [B, cls+THW, C]."""
+    n_patch = x.npos
+    C = x.C
+    pos = plan.const(pos_table.float().contiguous())
+    y = _tok(plan, x.N, n_patch + (1 if has_cls else 0), C)
+    lib = plan.lib
+
+    def fn(stream):
+        L.check(lib.pv_add_pos_cls(x.ptr(), y.ptr(), x.dt, x.N, n_patch, C, x.row_stride, pos.data_ptr(),
+                                   1 if has_cls else 0, stream), "pv_add_pos_cls")
+    plan.add(name, fn, "other", 0.0, 2 * x.N * n_patch * C * 2)
+    return y
+
+
+def emit_token_pool(plan, x, thw, pool, norm, heads, has_cls, name="pool"):
+    """_AttentionPool (layers/attention.py:162-212) on a token tensor/slice x [B, cls+THW, dim]:
+    depthwise Conv3d / MaxPool3d over the (T,H,W) grid of the patch tokens (cls row passes through),
+    then the per-head LayerNorm over head_dim (cls row included).  Returns (tokens, thw')."""
+    import ctypes as C_
+    T, H, W = thw
+    dim = x.C
+    cls = 1 if has_cls else 0
+    assert x.npos == cls + T * H * W, "token count does not match thw"
+    kind = type(pool).__name__
+    if kind == "Conv3d":
+        k, s, p, dl = [tuple(int(v) for v in t) for t in (pool.kernel_size, pool.stride, pool.padding, pool.dilation)]
+        if pool.groups != pool.in_channels or pool.in_channels != pool.out_channels or pool.bias is not None:
+            raise NotImplementedError("%s: only depthwise, bias-free pooling convs are supported" % name)
+        if dim % pool.in_channels:
+            raise RuntimeError("%s: pool channels do not divide the token width" % name)
+    elif kind == "MaxPool3d":
+        k, s, p = [tuple(int(v) for v in (t if isinstance(t, (tuple, list)) else (t,) * 3))
+                   for t in (pool.kernel_size, pool.stride, pool.padding)]
+        dl = (1, 1, 1)
+    else:
+        raise NotImplementedError("%s: pool module %s unsupported" % (name, kind))
+    To = (T + 2 * p[0] - dl[0] * (k[0] - 1) - 1) // s[0] + 1
+    Ho = (H + 2 * p[1] - dl[1] * (k[1] - 1) - 1) // s[1] + 1
+    Wo = (W + 2 * p[2] - dl[2] * (k[2] - 1) - 1) // s[2] + 1
+    y = _tok(plan, x.N, cls + To * Ho * Wo, dim)
+    lib = plan.lib
+    esz = _ESIZE[plan.dt]
+    if kind == "Conv3d":
+        reps = dim // pool.in_channels
+        w_full = pool.weight.detach().cpu().repeat(reps, 1, 1, 1, 1)      # same filter for every head
+        w_d = plan.const(PK.pack_depthwise(w_full, dim, _TORCH_DT[plan.dt]))
+        ones = plan.const(torch.ones(dim, dtype=torch.float32))
+        zeros = plan.const(torch.zeros(dim, dtype=torch.float32))
+        d = L.Conv3dDesc()
+        d.dtype = plan.dt
+        d.N, d.Ti, d.Hi, d.Wi, d.Ci = x.N, T, H, W, dim
+        d.To, d.Ho, d.Wo, d.Co = To, Ho, Wo, dim
+        d.kt, d.kh, d.kw = k
+        d.st, d.sh, d.sw = s
+        d.pt, d.ph, d.pw = p
+        d.dt, d.dh, d.dw = dl
+        d.groups, d.act, d.has_residual = dim, L.ACT_NONE, 0
+
+        def fn(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+            d.x_batch_stride, d.y_batch_stride = x.npos * x.row_stride, y.npos * y.row_stride
+            L.check(lib.pv_conv3d_fwd(C_.byref(d), L.ALGO_DIRECT, x.ptr() + cls * x.row_stride * esz, w_d.data_ptr(),
+                                      ones.data_ptr(), zeros.data_ptr(), None, y.ptr() + cls * y.row_stride * esz,
+                                      stream), "pv_conv3d_fwd(%s)" % name)
+        plan.add(name + ".dwconv", fn, "depthwise", 2.0 * x.N * To * Ho * Wo * dim * k[0] * k[1] * k[2],
+                 (x.N * T * H * W + x.N * To * Ho * Wo) * dim * esz)
+    else:
+        d = L.Pool3dDesc()
+        d.dtype, d.mode = plan.dt, L.POOL_MAX
+        d.N, d.Ti, d.Hi, d.Wi, d.C = x.N, T, H, W, dim
+        d.To, d.Ho, d.Wo = To, Ho, Wo
+        d.kt, d.kh, d.kw = k
+        d.st, d.sh, d.sw = s
+        d.pt, d.ph, d.pw = p
+
+        def fn(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+            d.x_batch_stride, d.y_batch_stride = x.npos * x.row_stride, y.npos * y.row_stride
+            L.check(lib.pv_pool3d_fwd(C_.byref(d), x.ptr() + cls * x.row_stride * esz,
+                                      y.ptr() + cls * y.row_stride * esz, stream), "pv_pool3d_fwd(%s)" % name)
+        plan.add(name + ".maxpool", fn, "other", 0.0, (x.N * T * H * W + x.N * To * Ho * Wo) * dim * esz)
+    if cls:
+        def fn_cls(stream):
+            L.check(lib.pv_copy_rows(x.ptr(), y.ptr(), x.dt, x.N, dim, x.npos * x.row_stride, y.npos * y.row_stride,
+                                     stream), "pv_copy_rows(%s)" % name)
+        plan.add(name + ".cls", fn_cls)
+    if norm is not None and type(norm).__name__ != "Identity":
+        if type(norm).__name__ != "LayerNorm":
+            raise NotImplementedError("%s: pool norm %s unsupported" % (name, type(norm).__name__))
+        hd = int(norm.normalized_shape[0])
+        assert dim % hd == 0
+        g = plan.const(norm.weight.detach().float().cpu())
+        b = plan.const(norm.bias.detach().float().cpu())
+        eps = float(norm.eps)
+
+        def fn_ln(stream):
+            L.check(lib.pv_layernorm(y.ptr(), y.ptr(), y.dt, y.N * y.npos, dim // hd, hd, y.row_stride, y.row_stride,
+                                     g.data_ptr(), b.data_ptr(), eps, stream), "pv_layernorm(%s)" % name)
+        plan.add(name + ".norm", fn_ln)
+    return y, (To, Ho, Wo)
+
+
+def emit_attention(plan, q, k, v, heads, scale, residual_pool, name="attn"):
+    import ctypes as C_
+    B, Nq, Nk, dim = q.N, q.npos, k.npos, q.C
+    assert k.C == dim and v.C == dim and v.npos == Nk and dim % heads == 0
+    o = _tok(plan, B, Nq, dim)
+    d = L.AttentionDesc()
+    d.dtype, d.B, d.H, d.Nq, d.Nk, d.D = plan.dt, B, heads, Nq, Nk, dim // heads
+    d.scale, d.add_q_residual = float(scale), 1 if residual_pool else 0
+    lib = plan.lib
+
+    def fn(stream):
+        d.q_row_stride, d.k_row_stride, d.v_row_stride, d.o_row_stride = q.row_stride, k.row_stride, v.row_stride, o.row_stride
+        d.q_batch_stride, d.k_batch_stride = Nq * q.row_stride, Nk * k.row_stride
+        d.v_batch_stride, d.o_batch_stride = Nk * v.row_stride, Nq * o.row_stride
+        L.check(lib.pv_attention_fwd(C_.byref(d), q.ptr(), k.ptr(), v.ptr(), o.ptr(), stream), "pv_attention_fwd(%s)" % name)
+    plan.add(name, fn, "attention", 4.0 * B * heads * Nq * Nk * (dim // heads),
+             (B * Nq * dim * 2 + 2 * B * Nk * dim) * _ESIZE[plan.dt])
+    return o
+
+
+def channel_slice(x, off, C):
+    """View of C channels starting at `off` (no copy)."""
+    t = TRef(x.buf, x.N, x.T, x.H, x.W, C, Cp=C, ch_off=x.ch_off + off, row_stride=x.row_stride)
+    return t

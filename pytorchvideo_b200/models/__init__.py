@@ -9,3 +9,6 @@ from .stem import ResNetBasicStem, create_res_basic_stem  # noqa: F401
 from .weight_init import init_net_weights  # noqa: F401
 from .x3d import (ProjectedPool, create_x3d, create_x3d_bottleneck_block, create_x3d_head,  # noqa: F401
                   create_x3d_res_block, create_x3d_res_stage, create_x3d_stem)
+from .head import SequencePool, VisionTransformerBasicHead, create_vit_basic_head  # noqa: F401,E402
+from .stem import PatchEmbed, create_conv_patch_embed  # noqa: F401,E402
+from .vision_transformers import MultiscaleVisionTransformers, create_multiscale_vision_transformers  # noqa: F401,E402

@@ -39,3 +39,31 @@ def create_res_basic_head(*, in_features, out_features, pool=nn.AvgPool3d, outpu
         dropout=nn.Dropout(dropout_rate) if dropout_rate > 0 else None,
         output_pool=nn.AdaptiveAvgPool3d(1) if output_with_global_average else None,
     )
+
+
+class SequencePool(nn.Module):
+    """'cls': first token, 'mean': token average (head.py:11-36)."""
+
+    def __init__(self, mode):
+        super().__init__()
+        assert mode in ["cls", "mean"], "Unsupported mode for SequencePool."
+        self.mode = mode
+
+
+class VisionTransformerBasicHead(B200Module):
+    """sequence_pool -> dropout -> Linear -> activation (head.py:485-535)."""
+
+    def __init__(self, sequence_pool=None, dropout=None, proj=None, activation=None):
+        super().__init__()
+        set_attributes(self, locals())
+        assert self.proj is not None
+
+
+def create_vit_basic_head(*, in_features, out_features, seq_pool_type="cls", dropout_rate=0.5, activation=None):
+    assert seq_pool_type in ["cls", "mean", "none"]
+    if seq_pool_type in ("cls", "mean"):
+        pool = SequencePool(seq_pool_type)
+    else:
+        pool = None
+    return VisionTransformerBasicHead(sequence_pool=pool, dropout=nn.Dropout(dropout_rate) if dropout_rate > 0.0 else None,
+                                      proj=nn.Linear(in_features, out_features), activation=_head_activation(activation))

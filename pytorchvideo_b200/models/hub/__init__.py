@@ -63,3 +63,25 @@ def csn_r101(pretrained=False, progress=True, **kw):
 
 def r2plus1d_r50(pretrained=False, progress=True, **kw):
     return _build(create_r2plus1d, pretrained, dropout_rate=0.5, **kw)
+
+
+_MVIT_VIDEO_BASE = {
+    "spatial_size": 224, "temporal_size": 16,
+    "embed_dim_mul": [[1, 2.0], [3, 2.0], [14, 2.0]], "atten_head_mul": [[1, 2.0], [3, 2.0], [14, 2.0]],
+    "pool_q_stride_size": [[1, 1, 2, 2], [3, 1, 2, 2], [14, 1, 2, 2]], "pool_kv_stride_adaptive": [1, 8, 8],
+    "pool_kvq_kernel": [3, 3, 3],
+}
+
+
+def mvit_base_16x4(pretrained=False, progress=True, **kw):
+    from ..vision_transformers import create_multiscale_vision_transformers
+    cfg = dict(_MVIT_VIDEO_BASE)
+    cfg.update(kw)
+    return _build(create_multiscale_vision_transformers, pretrained, **cfg)
+
+
+def mvit_base_32x3(pretrained=False, progress=True, **kw):
+    from ..vision_transformers import create_multiscale_vision_transformers
+    cfg = dict(_MVIT_VIDEO_BASE, temporal_size=32)
+    cfg.update(kw)
+    return _build(create_multiscale_vision_transformers, pretrained, **cfg)

@@ -26,3 +26,20 @@ def create_res_basic_stem(*, in_channels, out_channels, conv_kernel_size=(3, 7, 
         pool=None if pool is None else pool(kernel_size=pool_kernel_size, stride=pool_stride,
                                             padding=pool_padding),
     )
+
+
+class PatchEmbed(B200Module):
+    """Patchifying conv; on device its NDHWC output already IS the (B, THW, C) token layout, so the
+    reference's flatten(2).transpose(1, 2) (stem.py:289-292) costs nothing."""
+
+    def __init__(self, *, patch_model=None):
+        super().__init__()
+        set_attributes(self, locals())
+        assert self.patch_model is not None
+
+
+def create_conv_patch_embed(*, in_channels, out_channels, conv_kernel_size=(1, 16, 16), conv_stride=(1, 4, 4),
+                            conv_padding=(1, 7, 7), conv_bias=True, conv=nn.Conv3d):
+    return PatchEmbed(patch_model=conv(in_channels=in_channels, out_channels=out_channels,
+                                       kernel_size=conv_kernel_size, stride=conv_stride, padding=conv_padding,
+                                       bias=conv_bias))

@@ -65,7 +65,7 @@ def layernorm(x, gamma, beta, eps=1e-6, dtype="f16"):
     y = torch.empty_like(xs)
     g, b = gamma.float().contiguous().to(x.device), beta.float().contiguous().to(x.device)
     rows, Cc = xs.shape
-    L.check(lib.pv_layernorm(xs.data_ptr(), y.data_ptr(), _DT[dtype], rows, Cc, Cc, Cc, g.data_ptr(), b.data_ptr(),
+    L.check(lib.pv_layernorm(xs.data_ptr(), y.data_ptr(), _DT[dtype], rows, 1, Cc, Cc, Cc, g.data_ptr(), b.data_ptr(),
                              float(eps), _stream(x.device)), "pv_layernorm")
     torch.cuda.synchronize(x.device)
     return y.float()

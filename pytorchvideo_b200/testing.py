@@ -89,4 +89,7 @@ MODEL_CASES = {
     "csn_r101": ("csn_r101", {}, 1, 32, 224, 224, False),
     "r2plus1d_r50": ("r2plus1d_r50", {}, 1, 16, 224, 224, False),
     "i3d_r50": ("i3d_r50", {}, 1, 8, 224, 224, False),
+    "mvit_base_16x4": ("mvit_base_16x4", {}, 1, 16, 224, 224, False),
+    # same architecture on a 8x112x112 clip (785 tokens): cheap enough for the f32 CUDA-core parity mode
+    "mvit_base_8x112": ("mvit_base_16x4", {"spatial_size": 112, "temporal_size": 8}, 2, 8, 112, 112, False),
 }

@@ -35,7 +35,8 @@ def _to_dev(inp):
     return [t.cuda() for t in inp] if isinstance(inp, list) else inp.cuda()
 
 
-@pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50"])
+@pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50",
+                                  "mvit_base_8x112"])
 def test_model_f32_parity_mode(case):
     from pytorchvideo_b200 import config
     g, model, inp, _ = _setup(case)
@@ -54,7 +55,8 @@ def test_model_f32_parity_mode(case):
     assert bool((err <= tol).all()), "max err %.3e (scale %.3g)" % (float(err.max()), scale)
 
 
-@pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50"])
+@pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50",
+                                  "mvit_base_8x112", "mvit_base_16x4"])
 def test_model_f16_tensor_core_path(case):
     g, model, inp, _ = _setup(case)
     ref = g["output"]

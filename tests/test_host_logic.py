@@ -111,3 +111,12 @@ def test_shard_bounds_cover_batch_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_lowering_mvit_dry_run_counts_match_the_reference_macs():
+    m = PH.mvit_base_16x4().eval()
+    plan, out_shape = lower_only(m, torch.zeros(1, 3, 16, 224, 224))
+    assert out_shape == (1, 400)
+    gmac = sum(x["flops"] for x in plan.meta) / 2e9
+    assert abs(gmac - 70.60) < 0.05            # 70.60 GMAC/clip hook-counted on the reference
+    assert plan.stats["attention"] == 16 and plan.stats["tcgen05"] == 1 + 16 * 4 + 3 + 1

@@ -97,7 +97,7 @@ def test_normalize_zero_mean_unit_std_property():
 
 
 # ---- models ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["x3d_xs", "slow_r50", "r2plus1d_r50"])
+@pytest.mark.parametrize("case", ["x3d_xs", "slow_r50", "r2plus1d_r50", "mvit_base_8x112"])
 def test_oracle_reproduces_reference_model_goldens(case):
     g = _gold("model_%s.pt" % case)
     hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
@@ -120,6 +120,11 @@ def test_state_dict_keys_follow_the_reference_naming():
               "blocks.1.multipathway_blocks.0.res_blocks.0.branch1_conv.weight",
               "blocks.1.multipathway_blocks.1.res_blocks.2.branch2.norm_c.running_var", "blocks.6.proj.bias"]:
         assert k in keys
+    v = PH.mvit_base_16x4()
+    for k in ["cls_positional_encoding.pos_embed_spatial", "blocks.1.attn.pool_q.weight",
+              "blocks.1.attn._attention_pool_q.pool.weight", "blocks.0.proj.weight", "head.proj.bias"]:
+        assert k in v.state_dict()
+    assert len(v.state_dict()) == 482
     x = PH.x3d_xs()
     assert "blocks.1.res_blocks.0.branch2.norm_b.1.block.0.weight" in x.state_dict()
     assert "blocks.0.conv.conv_t.weight" in x.state_dict() and "blocks.5.pool.pre_conv.weight" in x.state_dict()
