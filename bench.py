@@ -36,6 +36,7 @@ WORKLOADS = {
     "slow_r50": ("slow_r50", 8, 8, 224, 224, False),
     "csn_r101": ("csn_r101", 8, 32, 224, 224, False),
     "r2plus1d_r50": ("r2plus1d_r50", 8, 16, 224, 224, False),
+    "mvit_base_16x4": ("mvit_base_16x4", 8, 16, 224, 224, False),
 }
 METRIC = "clips/sec forward (synthetic 3xTx224^2)"
 
@@ -116,16 +117,35 @@ def make_inputs(B, T, H, W, is_sf, seed):
     return TS.slowfast_inputs(clip) if is_sf else clip
 
 
+def pick_cpu_threads(model, T, H, W, is_sf):
+    """The reference (ATen/oneDNN conv3d) does not scale to every core of a 128-thread host at these
+    sizes - pick the thread count that is actually fastest (candidates <= visible cores)."""
+    from oracle.interp import oracle_forward
+    cores = os.cpu_count() or 1
+    cands = sorted(set(c for c in (8, 16, 32, 64, cores) if c <= cores))
+    inp = make_inputs(1, T, H, W, is_sf, seed=7)
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        if best_t is None:
+            oracle_forward(model, inp)          # warm-up (allocator, oneDNN primitives)
+        t0 = time.perf_counter()
+        oracle_forward(model, inp)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        if dt > 4 * best_t:
+            break                               # more threads only get slower from here
+    torch.set_num_threads(best)
+    return best, best_t
+
+
 def cpu_baseline(model, T, H, W, is_sf, budget_s=20.0):
     """Oracle port of the reference forward on the host cores, bounded sample (1 warm-up + timed)."""
     from oracle.interp import oracle_forward
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores, one = pick_cpu_threads(model, T, H, W, is_sf)
     b = 1
     inp = make_inputs(b, T, H, W, is_sf, seed=7)
-    t0 = time.perf_counter()
-    oracle_forward(model, inp)
-    one = time.perf_counter() - t0
     b = max(1, min(8, int(budget_s / max(one, 1e-3) / 2)))
     inp = make_inputs(b, T, H, W, is_sf, seed=7)
     best = None
@@ -146,8 +166,7 @@ def run_reference(args, rank, world):
         return
     model, B, T, H, W, is_sf = build_model_and_inputs(args.workload)
     from oracle.interp import oracle_forward
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores, _ = pick_cpu_threads(model, T, H, W, is_sf)
     b = 1   # bounded sample: one clip per step
     inp = make_inputs(b, T, H, W, is_sf, seed=7)
     for _ in range(max(1, min(args.warmup, 1))):
@@ -272,10 +291,10 @@ def main():
     peaks = load_peaks()
     dom = max(kinds, key=lambda k: kinds[k]["ms"])
     kd = kinds[dom]
-    if dom in ("tcgen05",):
+    if dom in ("tcgen05", "attention"):
         achieved = kd["flops"] / (kd["ms"] * 1e-3) / 1e12
         peak = peaks["tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv3d_igemm_kernel", "achieved": achieved, "peak": peak,
+        roof = {"bound": "tensor", "kernel": "conv3d_igemm_kernel" if dom == "tcgen05" else "attention_kernel", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "launches": kd["n"], "avg_launch_us": kd["ms"] / kd["n"] * 1e3,
                 "share_of_step": kd["ms"] / total_ms, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}

@@ -156,6 +156,16 @@ typedef struct pv_conv3d_desc {
   long long x_batch_stride, y_batch_stride;
 } pv_conv3d_desc;
 
+/* Temporal tap reduction used to factor a (kt,kh,kw) stem convolution with few output channels into
+ * a (1,kh,kw) convolution producing kt*Co channels (one group of Co per temporal tap, all taps in ONE
+ * tensor-core pass over the input) followed by this sum:
+ *   y[n][t][p][co] = act(scale[co] * sum_dt Yk[n][t*st + dt*dil - pt][p][dt*Co + co] + bias[co])
+ * (frames outside [0,Ti) contribute zero = the temporal zero padding).  Same arithmetic as the
+ * direct convolution up to one f16 rounding of the per-tap partial sums.                          */
+int pv_temporal_tap_sum(const void* yk, void* y, int dtype, int N, int Ti, int To, long long hw, int Co,
+                        int kt, int st, int pt, int dil, const float* scale, const float* bias, int act,
+                        long long in_row_stride, long long out_row_stride, void* stream);
+
 int pv_conv3d_fwd(const pv_conv3d_desc* d, int algo, const void* x, const void* w,
                   const float* scale, const float* bias, const void* residual, void* y,
                   void* stream);

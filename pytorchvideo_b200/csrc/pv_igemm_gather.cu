@@ -114,9 +114,14 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       int t0 = 0, h0 = 0, w0 = 0;
       const __half* xrow = x;
       if (row_ok) {
-        int wo = (int)(m % P.Wo); long long r = m / P.Wo;
-        int ho = (int)(r % P.Ho); r /= P.Ho;
-        int to = (int)(r % P.To); int n = (int)(r / P.To);
+        const uint32_t mu = (uint32_t)m;                       // M < 2^31 (checked on the host)
+        uint32_t r = mu / (uint32_t)P.Wo;
+        const int wo = (int)(mu - r * (uint32_t)P.Wo);
+        uint32_t r2 = r / (uint32_t)P.Ho;
+        const int ho = (int)(r - r2 * (uint32_t)P.Ho);
+        const uint32_t n_u = r2 / (uint32_t)P.To;
+        const int to = (int)(r2 - n_u * (uint32_t)P.To);
+        const int n = (int)n_u;
         t0 = to * P.st - P.pt; h0 = ho * P.sh - P.ph; w0 = wo * P.sw - P.pw;
         xrow = x + ((((long long)n * P.Ti + t0) * P.Hi + h0) * P.Wi + w0) * P.x_row_stride;
       }
@@ -246,7 +251,7 @@ int conv3d_gather_supported(const pv_conv3d_desc* d) {
   if (d->x_row_stride % (gbytes / 2) || d->y_row_stride % 8 || (d->has_residual && d->res_row_stride % 8)) return 0;
   if (d->dt * (d->kt - 1) > 255 || d->dh * (d->kh - 1) > 255 || d->dw * (d->kw - 1) > 65535) return 0;
   const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
-  if (M >= (1ll << 31) * 64) return 0;
+  if (M >= (1ll << 31)) return 0;
   return 1;
 }
 

@@ -48,6 +48,39 @@ __global__ void ncdhw_to_ndhwc_padw_kernel(const SrcT* __restrict__ src, DstT* _
   }
 }
 
+// f32 NCDHW -> f16 NDHWC4 with W padding, 4 consecutive pixels per thread (16-byte reads per channel
+// plane, one 32-byte write).  Requires W % 4 == 0, w_pad % 4 == 0, w_phys % 4 == 0, C <= 4, c_pad == 4.
+__global__ void __launch_bounds__(256)
+ncdhw_f32_to_ndhwc4_padw_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int T, int H,
+                                int W, int w_pad, int w_phys, long long total_quads) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // quad of 4 physical pixels
+  if (q >= total_quads) return;
+  const int qpr = w_phys >> 2;
+  const int wq = (int)(q % qpr);
+  long long r = q / qpr;                 // (n*T + t)*H + h
+  const int w = wq * 4 - w_pad;
+  uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = make_uint4(0u, 0u, 0u, 0u);
+  if (w >= 0 && w < W) {
+    const int h = (int)(r % H); long long r2 = r / H;
+    const int t = (int)(r2 % T); const long long n = r2 / T;
+    const long long thw = (long long)T * H * W;
+    const float* s = src + n * C * thw + ((long long)t * H + h) * W + w;
+    float4 c0 = *reinterpret_cast<const float4*>(s);
+    float4 c1 = C > 1 ? *reinterpret_cast<const float4*>(s + thw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 c2 = C > 2 ? *reinterpret_cast<const float4*>(s + 2 * thw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 c3 = C > 3 ? *reinterpret_cast<const float4*>(s + 3 * thw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __half2* p0 = reinterpret_cast<__half2*>(&o0);
+    __half2* p1 = reinterpret_cast<__half2*>(&o1);
+    p0[0] = __floats2half2_rn(c0.x, c1.x); p0[1] = __floats2half2_rn(c2.x, c3.x);
+    p0[2] = __floats2half2_rn(c0.y, c1.y); p0[3] = __floats2half2_rn(c2.y, c3.y);
+    p1[0] = __floats2half2_rn(c0.z, c1.z); p1[1] = __floats2half2_rn(c2.z, c3.z);
+    p1[2] = __floats2half2_rn(c0.w, c1.w); p1[3] = __floats2half2_rn(c2.w, c3.w);
+  }
+  uint4* o = reinterpret_cast<uint4*>(dst + q * 16);
+  o[0] = o0;
+  o[1] = o1;
+}
+
 template <typename SrcT>
 __global__ void ndhwc_to_ncdhw_kernel(const SrcT* __restrict__ src, long long src_row_stride,
                                       float* __restrict__ dst, int C, long long thw,
@@ -499,6 +532,34 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256)
+temporal_tap_sum_kernel(const T* __restrict__ yk, T* __restrict__ y, int Ti, int To, long long hw, int Co, int kt,
+                        int st, int pt, int dil, const float* __restrict__ scale, const float* __restrict__ bias,
+                        int act, long long irs, long long ors, long long total) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = Co >> 3;
+  const int c = (int)(e % G) * 8;
+  long long r = e / G;                      // (n*To + t)*hw + p
+  const long long p = r % hw; r /= hw;
+  const int t = (int)(r % To); const long long n = r / To;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int dt = 0; dt < kt; ++dt) {
+    const int ti = t * st + dt * dil - pt;
+    if ((unsigned)ti >= (unsigned)Ti) continue;
+    float v[8];
+    ld8<T>(yk + ((n * Ti + ti) * hw + p) * irs + (long long)dt * Co + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = apply_act(acc[i] * __ldg(scale + c + i) + __ldg(bias + c + i), act);
+  st8<T>(y + ((n * To + t) * hw + p) * ors + c, acc);
+}
+
+template <typename T>
 __global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, int C,
                                  long long ss, long long ds) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,6 +632,14 @@ extern "C" int pv_ncdhw_to_ndhwc_padw(const void* src, int src_dtype, void* dst,
   const long long total = (long long)N * T * H * w_phys;
   if (total == 0) return PV_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (src_dtype == PV_F32 && dst_dtype == PV_F16 && c_pad == 4 && C <= 4 && W % 4 == 0 && w_pad % 4 == 0 &&
+      w_phys % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const long long quads = total / 4;
+    ncdhw_f32_to_ndhwc4_padw_kernel<<<(unsigned)cdiv(quads, 256), 256, 0, s>>>((const float*)src, (__half*)dst, C, T, H,
+                                                                              W, w_pad, w_phys, quads);
+    PV_LAUNCH_OK("ncdhw_f32_to_ndhwc4_padw_kernel");
+    return PV_OK;
+  }
   dim3 grid((unsigned)cdiv(total, 256)), block(256);
 #define PV_CASE(ST, DT)                                                                         \
   ncdhw_to_ndhwc_padw_kernel<ST, DT><<<grid, block, 0, s>>>((const ST*)src, (DT*)dst, C, T, H, W, c_pad, \
@@ -582,6 +651,28 @@ extern "C" int pv_ncdhw_to_ndhwc_padw(const void* src, int src_dtype, void* dst,
   else { set_error("unsupported dtype pair %d->%d", src_dtype, dst_dtype); return PV_ERR_INVALID; }
 #undef PV_CASE
   PV_LAUNCH_OK("ncdhw_to_ndhwc_padw_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_temporal_tap_sum(const void* yk, void* y, int dtype, int N, int Ti, int To, long long hw,
+                                   int Co, int kt, int st, int pt, int dil, const float* scale,
+                                   const float* bias, int act, long long in_row_stride,
+                                   long long out_row_stride, void* stream) {
+  PV_CHECK_ARG(yk && y && scale && bias, "null pointer");
+  PV_CHECK_ARG(Co % 8 == 0 && in_row_stride % 8 == 0 && out_row_stride % 8 == 0, "Co/strides %% 8");
+  PV_CHECK_ARG(in_row_stride >= (long long)kt * Co && out_row_stride >= Co, "row stride too small");
+  const long long total = (long long)N * To * hw * (Co / 8);
+  if (total == 0) return PV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)cdiv(total, 256)), block(256);
+  if (dtype == PV_F16)
+    temporal_tap_sum_kernel<__half><<<grid, block, 0, s>>>((const __half*)yk, (__half*)y, Ti, To, hw, Co, kt, st, pt, dil,
+                                                        scale, bias, act, in_row_stride, out_row_stride, total);
+  else if (dtype == PV_F32)
+    temporal_tap_sum_kernel<float><<<grid, block, 0, s>>>((const float*)yk, (float*)y, Ti, To, hw, Co, kt, st, pt, dil,
+                                                       scale, bias, act, in_row_stride, out_row_stride, total);
+  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  PV_LAUNCH_OK("temporal_tap_sum_kernel");
   return PV_OK;
 }
 

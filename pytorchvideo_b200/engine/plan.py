@@ -195,6 +195,29 @@ class Plan:
         co_pad = PK.pad8(co)
         if residual is not None:
             self.materialize_input(residual)
+        # ---- narrow stems with a temporal extent: factor (kt,kh,kw) -> (1,kh,kw) with kt*Co channels
+        #      (all temporal taps in one tensor-core pass) + a temporal tap sum, see pv_temporal_tap_sum
+        if (x.lazy_src is not None and self.use_tcgen05 and force_algo in (None, L.ALGO_TCGEN05) and groups == 1
+                and x.Cp == 4 and kt > 1 and residual is None and co_pad * kt <= 256 and dlw == 1
+                and (sw * x.Cp * 2) % 16 == 0 and kw * x.Cp <= 64 and pw > 0 and sh <= 8):
+            w2 = torch.zeros(kt * co_pad, cig, 1, kh, kw, dtype=weight.dtype)
+            wsrc = weight.detach().cpu()
+            for j in range(kt):
+                w2[j * co_pad: j * co_pad + co] = wsrc[:, :, j:j + 1]
+            yk = self.emit_conv(x, w2, None, None, (1, sh, sw), (0, ph, pw), (1, dlh, dlw), 1, L.ACT_NONE, None,
+                                name + ".taps")
+            y = self.new_tensor(x.N, To, Ho, Wo, co, Cp=co_pad)
+            scale, bias = PK.fold_bn(conv_bias, bn, co, co_pad)
+            scale_d, bias_d = self.const(scale), self.const(bias)
+            lib = self.lib
+            hw = Ho * Wo
+
+            def fn_sum(stream):
+                L.check(lib.pv_temporal_tap_sum(yk.ptr(), y.ptr(), self.dt, x.N, x.T, To, hw, co_pad, kt, st, pt, dlt,
+                                                scale_d.data_ptr(), bias_d.data_ptr(), act, yk.row_stride,
+                                                y.row_stride, stream), "pv_temporal_tap_sum(%s)" % name)
+            self.add(name + ".tapsum", fn_sum, "other", 0.0, (x.N * x.T * hw * kt * co_pad + x.N * To * hw * co_pad) * 2)
+            return y
         # ---- network input: pick the layout its first consumer wants
         window = False
         if x.lazy_src is not None:
@@ -203,8 +226,9 @@ class Plan:
                       and st * sh <= 8 and pw > 0)
             if window:
                 win = PK.window_elems(kw, x.Cp)
-                need = max(x.W + 2 * pw, (Wo - 1) * sw + (win + x.Cp - 1) // x.Cp)
-                self.materialize_input(x, w_pad=pw, w_phys=(need + 1) // 2 * 2)
+                wp = (pw + 3) // 4 * 4          # left pad rounded up: enables the 4-pixel conversion kernel
+                need = wp - pw + max(x.W + 2 * pw, (Wo - 1) * sw + (win + x.Cp - 1) // x.Cp)
+                self.materialize_input(x, w_pad=wp, w_phys=(need + 3) // 4 * 4)
             else:
                 self.materialize_input(x)
         elif x.padw is not None:
