@@ -238,8 +238,11 @@ struct IgemmPlan {
 // x_w_pad physical zero pixels on the left (and enough on the right), written by the layout
 // conversion, which implements the W padding; H/T padding is TMA out-of-bounds fill as usual.
 static bool window_mode(const pv_conv3d_desc* d) { return d->x_w_pad > 0 && d->Ci <= 8; }
+// TMA needs a 16-byte aligned base: if the first tap of output column 0 sits at an odd pixel of a
+// 4-channel row, the window starts one pixel earlier (the packed weights carry a zero pixel there).
+static int window_lead(const pv_conv3d_desc* d) { return (((d->x_w_pad - d->pw) * d->Ci * 2) % 16) ? 1 : 0; }
 static int window_elems(const pv_conv3d_desc* d) {
-  const int run = d->kw * d->Ci;
+  const int run = (d->kw + window_lead(d)) * d->Ci;
   return run <= 16 ? 16 : (run <= 32 ? 32 : 64);
 }
 
@@ -296,7 +299,7 @@ int conv3d_tcgen05_supported(const pv_conv3d_desc* d, char* why, size_t why_len)
     if (d->dw != 1) NOPE("window mode needs dilation_w == 1");
     if (d->x_row_stride != d->Ci) NOPE("window mode needs densely packed pixels");
     if ((d->sw * d->Ci * 2) % 16) NOPE("window stride must be a multiple of 16 bytes");
-    if (d->kw * d->Ci > 64) NOPE("window run longer than 64 elements");
+    if ((d->kw + window_lead(d)) * d->Ci > 64) NOPE("window run longer than 64 elements");
     if (d->x_w_pad < d->pw) NOPE("physical W padding smaller than the conv padding");
     if (d->x_w_phys < d->x_w_pad + d->Wi + (d->pw > 0 ? d->pw : 0) || (d->x_w_phys * d->Ci * 2) % 16)
       NOPE("bad physical row width");
@@ -459,7 +462,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (!(used_maps & (1u << cls))) continue;
     int r[4], c = cls;
     for (int m = 0; m < 4; ++m) { r[m] = c % ss[m]; c /= ss[m]; }
-    long long base_off = wmode ? (long long)(d->x_w_pad - d->pw) * d->Ci * 2 : 0;   // bytes
+    long long base_off = wmode ? (long long)(d->x_w_pad - d->pw - window_lead(d)) * d->Ci * 2 : 0;   // bytes
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
     gdim[0] = (cuuint64_t)(wmode ? win : d->Ci);

@@ -75,19 +75,25 @@ def pack_dense_tcgen05(w, ci_pad64, co_pad):
     return out.contiguous()
 
 
-def window_elems(kw, ci_pad):
-    run = kw * ci_pad
+def window_lead(w_pad, pw, ci_pad):
+    """Leading zero pixels of the window so that its first byte is 16-byte aligned (see pv_igemm.cu)."""
+    return 1 if ((w_pad - pw) * ci_pad * 2) % 16 else 0
+
+
+def window_elems(kw, ci_pad, lead=0):
+    run = (kw + lead) * ci_pad
     return 16 if run <= 16 else (32 if run <= 32 else 64)
 
 
-def pack_dense_window(w, ci_pad, co_pad):
-    """Window-mode stems: [Co, Ci, kt, kh, kw] -> [co_pad, kt*kh*win] f16 with k = (dt*kh+dh)*win + dw*ci_pad + c
-    (win = 16|32|64 >= kw*ci_pad; the tail of every window multiplies junk/next-pixel data by zero)."""
+def pack_dense_window(w, ci_pad, co_pad, lead=0):
+    """Window-mode stems: [Co, Ci, kt, kh, kw] -> [co_pad, kt*kh*win] f16 with
+    k = (dt*kh+dh)*win + (lead+dw)*ci_pad + c  (win = 16|32|64; leading / trailing window elements
+    multiply neighbouring-pixel data by zero)."""
     co, ci, kt, kh, kw = w.shape
-    win = window_elems(kw, ci_pad)
+    win = window_elems(kw, ci_pad, lead)
     out = torch.zeros(co_pad, kt * kh, win, dtype=torch.float16)
     src = w.detach().cpu().permute(0, 2, 3, 4, 1).reshape(co, kt * kh, kw, ci).to(torch.float16)
     tmp = torch.zeros(co, kt * kh, kw, ci_pad, dtype=torch.float16)
     tmp[..., :ci] = src
-    out[:co, :, : kw * ci_pad] = tmp.reshape(co, kt * kh, kw * ci_pad)
+    out[:co, :, lead * ci_pad: (lead + kw) * ci_pad] = tmp.reshape(co, kt * kh, kw * ci_pad)
     return out.reshape(co_pad, kt * kh * win).contiguous()

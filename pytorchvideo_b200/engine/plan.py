@@ -222,11 +222,12 @@ class Plan:
         window = False
         if x.lazy_src is not None:
             window = (self.use_tcgen05 and force_algo in (None, L.ALGO_TCGEN05) and groups == 1 and x.Cp == 4
-                      and dlw == 1 and (sw * x.Cp * 2) % 16 == 0 and kw * x.Cp <= 64 and kt * kh <= 64
+                      and dlw == 1 and (sw * x.Cp * 2) % 16 == 0 and (kw + 1) * x.Cp <= 64 and kt * kh <= 64
                       and st * sh <= 8 and pw > 0)
             if window:
-                win = PK.window_elems(kw, x.Cp)
                 wp = (pw + 3) // 4 * 4          # left pad rounded up: enables the 4-pixel conversion kernel
+                lead = PK.window_lead(wp, pw, x.Cp)
+                win = PK.window_elems(kw, x.Cp, lead)
                 need = wp - pw + max(x.W + 2 * pw, (Wo - 1) * sw + (win + x.Cp - 1) // x.Cp)
                 self.materialize_input(x, w_pad=wp, w_phys=(need + 3) // 4 * 4)
             else:
@@ -259,7 +260,8 @@ class Plan:
         d.ci_pad64 = ci_pad64
         if window:
             d.x_w_pad, d.x_w_phys = x.padw
-            d.ci_pad64 = PK.window_elems(kw, x.Cp)
+            w_lead = PK.window_lead(x.padw[0], pw, x.Cp)
+            d.ci_pad64 = PK.window_elems(kw, x.Cp, w_lead)
 
         if depthwise:
             algo, kind = L.ALGO_DIRECT, "depthwise"
@@ -272,7 +274,7 @@ class Plan:
                 raise RuntimeError("internal: window-mode stem rejected by the library: " + L.last_error())
             if want_tc:
                 algo, kind = L.ALGO_TCGEN05, "tcgen05"
-                w_d = self.const(PK.pack_dense_window(weight, x.Cp, co_pad) if window
+                w_d = self.const(PK.pack_dense_window(weight, x.Cp, co_pad, w_lead) if window
                                  else PK.pack_dense_tcgen05(weight, ci_pad64, co_pad))
             else:
                 algo, kind = L.ALGO_DIRECT, "direct"
