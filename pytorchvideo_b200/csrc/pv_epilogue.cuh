@@ -19,7 +19,7 @@ namespace sm100 {
 
 constexpr int EPI_GROUP_COLS = 128;
 constexpr int EPI_STAGING_BYTES = 2 * 128 * 128;   // two [128 rows x 64 f16] swizzled sub-tiles
-constexpr int EPI_SB_BYTES = 2 * 256 * 4;          // scale[256] + bias[256] (fp32) for the current tile
+constexpr int EPI_SB_BYTES = 2 * 2 * 256 * 4;      // scale[256] + bias[256] (fp32), one copy per epilogue group
 constexpr int EPI_SMEM_BYTES = EPI_STAGING_BYTES + EPI_SB_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -28,6 +28,7 @@ struct EpiParams {
   CUtensorMap y_map;    // output  [Co, d1, d2, d3, d4], box [64, b1, b2, b3, b4], SWIZZLE_128B
   CUtensorMap r_map;    // residual, same geometry
   int block_n, Co, rows, act, has_residual;
+  int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip TMA stores, 2 = skip epilogue math, 4 = producers skip loads
 };
 
 __device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3,
@@ -43,7 +44,13 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// BLOCK_N <= 64 ("narrow"): the 8 epilogue warps split into two independent groups of 4 that take
+// alternate tiles, each with its own staging slot, scale/bias copy, residual barrier and named
+// barrier - the per-tile epilogue is a latency chain, so two tiles in flight double its throughput.
+__host__ __device__ inline bool epi_narrow(int block_n) { return block_n <= 64; }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -127,40 +134,45 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* _
                                               int c1, int c2, int c3, int c4, uint32_t tempty_bar,
                                               int tile_seq) {
   const int row = quarter * 32 + lane;
-  const int chalf = ewarp >> 2;
-  const int etid = ewarp * 32 + lane;
+  const bool narrow = epi_narrow(E.block_n);
+  const int group = narrow ? (ewarp >> 2) : 0;   // narrow: two groups of 4 warps on alternate tiles
+  const int chalf = narrow ? 0 : (ewarp >> 2);
+  const int etid = narrow ? ((ewarp & 3) * 32 + lane) : (ewarp * 32 + lane);
+  const int nthr = narrow ? 128 : 256;
+  const int bar_id = 1 + group;
   const bool leader = (etid == 0);
   const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
   const uint32_t rsw = (uint32_t)(row & 7);
-  float* sb = reinterpret_cast<float*>(epi_gen + EPI_STAGING_BYTES);
-  const bool narrow = E.block_n <= 64;           // one 64-col sub-tile per tile: alternate staging slots
+  float* sb = reinterpret_cast<float*>(epi_gen + EPI_STAGING_BYTES) + group * 512;
+  res_bar += 8u * (uint32_t)group;
+  (void)tile_seq;
   // stage scale / bias of this N tile (zeros beyond Co keep pad lanes at exactly zero)
-  {
-    const int c = n0 + etid;
-    const bool ok = etid < E.block_n && c < E.Co;
-    sb[etid] = ok ? __ldg(scale + c) : 0.f;
-    sb[256 + etid] = ok ? __ldg(bias + c) : 0.f;
+  for (int i = etid; i < E.block_n; i += nthr) {
+    const int c = n0 + i;
+    const bool ok = c < E.Co;
+    sb[i] = ok ? __ldg(scale + c) : 0.f;
+    sb[256 + i] = ok ? __ldg(bias + c) : 0.f;
   }
   for (int g0 = 0; g0 < E.block_n; g0 += EPI_GROUP_COLS) {
     const int gcols = min(EPI_GROUP_COLS, E.block_n - g0);
     const int nsub = (gcols + 63) >> 6;
-    const uint32_t slot = narrow ? (uint32_t)(tile_seq & 1) * 16384u : 0u;
+    const uint32_t slot = (uint32_t)group * 16384u;
     // (a) the staging slot is free once the bulk store that last used it has read it out
     if (leader) {
-      if (narrow) tma_store_wait_read1(); else tma_store_wait_read0();
+      tma_store_wait_read0();
       if (E.has_residual) {
         mbar_arrive_expect_tx(res_bar, (uint32_t)(nsub * E.rows * 128));
         for (int s = 0; s < nsub; ++s)
           tma_load_5d(epi_smem + slot + (uint32_t)s * 16384u, &E.r_map, res_bar, n0 + g0 + s * 64, c1, c2, c3, c4);
       }
     }
-    epi_bar_sync();                 // slot free + scale/bias visible
+    epi_bar_sync(bar_id, nthr);     // slot free + scale/bias visible
     if (E.has_residual) {
       mbar_wait(res_bar, res_phase);
       res_phase ^= 1u;
     }
     // (b) drain this warp's 64-column half of the group
-    if (chalf < nsub) {
+    if (chalf < nsub && !(E.dbg & 2)) {
       const int cbase = g0 + chalf * 64;
       const int ncols = min(64, gcols - chalf * 64);
       uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
@@ -180,9 +192,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* _
       if (lane == 0) mbar_arrive(tempty_bar);
     }
     // (c) publish the staged tile to the async proxy and store it
-    fence_proxy_async_smem();
-    epi_bar_sync();
-    if (leader) {
+    if (!(E.dbg & 16)) fence_proxy_async_smem();
+    epi_bar_sync(bar_id, nthr);
+    if (leader && !(E.dbg & 1)) {
       for (int s = 0; s < nsub; ++s)
         tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, n0 + g0 + s * 64, c1, c2, c3, c4);
       tma_store_commit();

@@ -21,6 +21,7 @@
 #include "pv_epilogue.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace pv {
 
@@ -30,7 +31,10 @@ constexpr int IG_BM = 128;        // UMMA M
 constexpr int IG_BK = 64;         // K per pipeline stage (one 128B swizzle row of f16)
 constexpr int IG_MAX_TAPS = 64;
 constexpr int IG_MAX_MAPS = 8;
-constexpr int IG_THREADS = (2 + EPI_WARPS) * 32;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int IG_PROD_WARPS = 4;   // TMA producer warps (one elected lane each, k-blocks round-robin)
+constexpr int IG_MMA_WARP = IG_PROD_WARPS;
+constexpr int IG_EPI_WARP0 = IG_PROD_WARPS + 1;
+constexpr int IG_THREADS = (IG_PROD_WARPS + 1 + EPI_WARPS) * 32;   // 416
 constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;   // 16 KiB
 
 struct IgemmParams {
@@ -48,7 +52,9 @@ struct IgemmParams {
   int kbytes;      // bytes of K per smem row and pipeline stage: 128 (64 ch, SW128) | 64 | 32 (window mode)
   int stages;
   int tmem_cols;
-  int acc_stride;   // TMEM columns between the two accumulator stages (block_n rounded up to 32)
+  int acc_stride;   // TMEM columns between accumulator stages (block_n rounded up to 32)
+  int nacc;         // number of accumulator stages
+  int nprod;        // active TMA producer warps (1..IG_PROD_WARPS)
   EpiParams epi;
   signed char tap_q[IG_MAX_TAPS][4];
   unsigned char tap_map[IG_MAX_TAPS];
@@ -72,9 +78,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
-  const uint32_t res_bar = bar_base + 8u * (2 * stages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 5);
+  const int nacc = P.nacc;                   // accumulator stages in TMEM (2..8)
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + nacc + s); };
+  const uint32_t res_bar = bar_base + 8u * (2 * stages + 2 * nacc);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 2 * nacc + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,15 +93,16 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < nacc; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), epi_narrow(P.block_n) ? 4 : EPI_WARPS);   // one arrive per epilogue warp of the tile's group
     }
     mbar_init(res_bar, 1);
+    mbar_init(res_bar + 8u, 1);
     prefetch_tmap(&P.epi.y_map);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == IG_MMA_WARP) {
     tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     tmem_relinquish();
   }
@@ -107,10 +115,13 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   const int total_tiles = P.n_tiles * P.m_tiles;
   const int num_kb = P.taps * P.num_kc;
 
-  if (warp == 0) {
-    // ================================ TMA producer ==========================================
+  if (warp < IG_PROD_WARPS) {
+    // ================================ TMA producers =========================================
+    // k-blocks can be dealt round-robin to up to IG_PROD_WARPS warps (PVB200_NPROD); measured on
+    // B200 this does not help (the pipeline is bound by L2->SM bandwidth / TMA latency, not by the
+    // issuing thread), so one producer warp is the default.
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, g = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)P.rows * P.kbytes + b_bytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -121,22 +132,24 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
         for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
         const int n0 = n_tile * P.block_n;
         for (int tap = 0; tap < P.taps; ++tap) {
-          const void* amap = &P.a_maps[P.tap_map[tap]];
-          const int c1 = o[0] + P.tap_q[tap][0], c2 = o[1] + P.tap_q[tap][1];
-          const int c3 = o[2] + P.tap_q[tap][2], c4 = o[3] + P.tap_q[tap][3];
-          for (int kc = 0; kc < P.num_kc; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * stage_bytes;
-            const uint32_t b_dst = a_dst + a_bytes;
-            mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_5d(a_dst, amap, full_bar(stage), kc * k_elems, c1, c2, c3, c4);
-            tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * k_elems, n0);
+          for (int kc = 0; kc < P.num_kc; ++kc, ++g) {
+            if ((g % P.nprod) == warp) {
+              const void* amap = &P.a_maps[P.tap_map[tap]];
+              const int c1 = o[0] + P.tap_q[tap][0], c2 = o[1] + P.tap_q[tap][1];
+              const int c3 = o[2] + P.tap_q[tap][2], c4 = o[3] + P.tap_q[tap][3];
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              const uint32_t b_dst = a_dst + a_bytes;
+              mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+              tma_load_5d(a_dst, amap, full_bar(stage), kc * k_elems, c1, c2, c3, c4);
+              tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * k_elems, n0);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == IG_MMA_WARP) {
     // ================================ MMA issuer ============================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(IG_BM, P.block_n);
@@ -164,16 +177,20 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
     // ================================ epilogue warps ========================================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int ewarp = warp - 2;
-    int acc = 0, tile_seq = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    const int ewarp = warp - IG_EPI_WARP0;
+    int tile_seq = 0;
+    uint32_t res_phase = 0;
+    const bool narrow = epi_narrow(P.block_n);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
+      if (narrow && (tile_seq & 1) != (ewarp >> 2)) continue;     // the other group's tile
+      const int acc = tile_seq % nacc;
+      const uint32_t acc_phase = (uint32_t)((tile_seq / nacc) & 1);
       const int n_tile = tile % P.n_tiles;
       int mt = tile / P.n_tiles;
       int o[4];
@@ -184,14 +201,13 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                     res_bar, res_phase, ewarp, quarter, lane, n_tile * P.block_n, o[0], o[1], o[2], o[3],
                     tempty_bar(acc), tile_seq);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (ewarp == 0 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
+    if ((ewarp & 3) == 0 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores (both group leaders)
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == IG_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
@@ -410,9 +426,14 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   P.epi.rows = P.rows;
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
+  { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("PVB200_NPROD"); P.nprod = e ? atoi(e) : 1; if (P.nprod < 1 || P.nprod > IG_PROD_WARPS || P.nprod > P.stages) P.nprod = 1; }
   {
     P.acc_stride = (P.block_n + 31) / 32 * 32;
-    int cols = 2 * P.acc_stride, p2 = 32;
+    P.nacc = 512 / P.acc_stride;
+    if (P.nacc > 8) P.nacc = 8;
+    if (P.nacc < 2) P.nacc = 2;
+    int cols = P.nacc * P.acc_stride, p2 = 32;
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
@@ -424,7 +445,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     P.stages = st;
   }
   const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + EPI_SMEM_BYTES +
-                            8 * (2 * P.stages + 6) + 16;
+                            8 * (2 * P.stages + 2 * 8 + 4) + 16;
 
   // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)
   // merged dims never merge a dim that has taps, so each non-trivial original dim maps to one

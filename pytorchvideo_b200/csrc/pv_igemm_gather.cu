@@ -12,6 +12,7 @@
 #include "pv_epilogue.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace pv {
 
@@ -37,8 +38,9 @@ struct GatherParams {
   int num_kb;
   long long x_row_stride;
   long long M;
-  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, acc_stride;
+  int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, acc_stride, nacc;
   EpiParams epi;
+  long long* trace;   // debug: per-tile timestamps of CTA 0 (PVB200_TRACE=1)
   int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
   unsigned int unit_d[GG_MAX_UNITS];  // packed (dt | dh<<8 | dw<<16) tap displacement (dilation applied)
 };
@@ -58,10 +60,14 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
-  const uint32_t res_bar = bar_base + 8u * (2 * stages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 5);
+  const int nacc = P.nacc;                   // accumulator stages in TMEM (2..8)
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + nacc + s); };
+  const uint32_t res_bar = bar_base + 8u * (2 * stages + 2 * nacc);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 2 * nacc + 2);
 
+  __shared__ int s_off[GG_MAX_UNITS];
+  __shared__ unsigned s_d[GG_MAX_UNITS];
+  for (int i = threadIdx.x; i < GG_MAX_UNITS; i += blockDim.x) { s_off[i] = P.unit_off[i]; s_d[i] = P.unit_d[i]; }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int MMA_WARP = GG_EPI_WARPS;          // warp 8
@@ -70,14 +76,15 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   if (warp == MMA_WARP && lane == 0) {
     prefetch_tmap(&P.b_map);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), GG_PROD_WARPS + 1);   // one arrive per producer warp + the expect_tx arrive
+      mbar_init(full_bar(s), 2);   // the owning producer warp's arrive + its expect_tx arrive
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < nacc; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), GG_EPI_WARPS);
+      mbar_init(tempty_bar(s), epi_narrow(P.block_n) ? 4 : GG_EPI_WARPS);
     }
     mbar_init(res_bar, 1);
+    mbar_init(res_bar + 8u, 1);
     prefetch_tmap(&P.epi.y_map);
     fence_mbar_init();
   }
@@ -95,84 +102,85 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
 
   if (warp >= PROD_WARP0) {
     // ================================ gather producers =======================================
-    // Fully asynchronous im2col gather: cp.async (zero-fill for padding / tails) straight into the
-    // swizzled A tile, GG_DEPTH k-blocks in flight per thread; a k-block is published to the MMA
-    // warp (proxy fence + mbarrier arrive) once its commit group has landed.
-    const int ptid = threadIdx.x - PROD_WARP0 * 32;
-    const int row = ptid & 127;
-    const int half = ptid >> 7;
-    const int per_thread = P.upk >> 1;                 // units per k-block handled by this thread
-    const uint32_t row_off = (uint32_t)row * 128u;
-    const uint32_t rsw = (uint32_t)(row & 7);
-    int stage_i = 0, stage_c = 0, inflight = 0;
-    uint32_t phase_i = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % P.n_tiles;
-      const int m_tile = tile / P.n_tiles;
-      const long long m = (long long)m_tile * GG_BM + row;
-      const bool row_ok = m < P.M;
-      int t0 = 0, h0 = 0, w0 = 0;
-      const __half* xrow = x;
-      if (row_ok) {
-        const uint32_t mu = (uint32_t)m;                       // M < 2^31 (checked on the host)
-        uint32_t r = mu / (uint32_t)P.Wo;
-        const int wo = (int)(mu - r * (uint32_t)P.Wo);
-        uint32_t r2 = r / (uint32_t)P.Ho;
-        const int ho = (int)(r - r2 * (uint32_t)P.Ho);
-        const uint32_t n_u = r2 / (uint32_t)P.To;
-        const int to = (int)(r2 - n_u * (uint32_t)P.To);
-        const int n = (int)n_u;
-        t0 = to * P.st - P.pt; h0 = ho * P.sh - P.ph; w0 = wo * P.sw - P.pw;
-        xrow = x + ((((long long)n * P.Ti + t0) * P.Hi + h0) * P.Wi + w0) * P.x_row_stride;
-      }
-      for (int kb = 0; kb < P.num_kb; ++kb) {
-        mbar_wait(empty_bar(stage_i), phase_i ^ 1u);
-        const uint32_t a_tile = smem_base + stage_i * stage_bytes;
-        if (ptid == 0) {
-          mbar_arrive_expect_tx(full_bar(stage_i), b_bytes);
-          tma_load_2d(a_tile + GG_A_BYTES, &P.b_map, full_bar(stage_i), kb * GG_BK, n_tile * P.block_n);
-        }
-        const int u0 = kb * P.upk + half * per_thread;
-        for (int i = 0; i < per_thread; ++i) {
-          const int u = u0 + i;
-          const __half* src = x;
-          uint32_t nbytes = 0;
-          if (row_ok && u < P.units_total) {
-            const unsigned int dd = P.unit_d[u];
-            const int ti = t0 + (int)(dd & 0xffu), hi = h0 + (int)((dd >> 8) & 0xffu), wi = w0 + (int)(dd >> 16);
-            if ((unsigned)ti < (unsigned)P.Ti && (unsigned)hi < (unsigned)P.Hi && (unsigned)wi < (unsigned)P.Wi) {
-              src = xrow + P.unit_off[u];
-              nbytes = (uint32_t)P.gbytes;
-            }
+    // Warp-per-k-block im2col gather.  Producer warp w owns k-blocks g = w, w+8, ... of this CTA's
+    // (tile, k-block) sequence and fills the whole 128 x 64 A tile of that k-block alone: lane l
+    // covers rows l, l+32, l+64, l+96, each unit is a zero-filling cp.async straight into the
+    // swizzled layout.  All 8 warps are in flight on different k-blocks, so the serial issue
+    // latency of one thread (measured ~1000 clk per 4 copies when every warp worked on the SAME
+    // k-block) no longer bounds the pipeline; a warp publishes its k-block (proxy fence + one
+    // mbarrier arrive) when its own copies have landed.
+    const int wprod = warp - PROD_WARP0;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_g = my_tiles * P.num_kb;
+    int cur_seq = -1;
+    int t0[4], h0[4], w0[4];
+    const __half* xrow[4];
+    bool rok[4];
+    int n_tile = 0;
+    for (int g = wprod; g < total_g; g += GG_PROD_WARPS) {
+      const int tile_seq = g / P.num_kb;
+      const int kb = g - tile_seq * P.num_kb;
+      const int stage = g % stages;
+      const uint32_t phase = (uint32_t)((g / stages) & 1);
+      if (tile_seq != cur_seq) {
+        cur_seq = tile_seq;
+        const int tile = (int)blockIdx.x + tile_seq * (int)gridDim.x;
+        n_tile = tile % P.n_tiles;
+        const int m_tile = tile / P.n_tiles;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long m = (long long)m_tile * GG_BM + lane + 32 * q;
+          rok[q] = m < P.M;
+          t0[q] = h0[q] = w0[q] = 0;
+          xrow[q] = x;
+          if (rok[q]) {
+            const uint32_t mu = (uint32_t)m;
+            uint32_t r = mu / (uint32_t)P.Wo;
+            const int wo = (int)(mu - r * (uint32_t)P.Wo);
+            uint32_t r2 = r / (uint32_t)P.Ho;
+            const int ho = (int)(r - r2 * (uint32_t)P.Ho);
+            const uint32_t n_u = r2 / (uint32_t)P.To;
+            const int to = (int)(r2 - n_u * (uint32_t)P.To);
+            t0[q] = to * P.st - P.pt; h0[q] = ho * P.sh - P.ph; w0[q] = wo * P.sw - P.pw;
+            xrow[q] = x + ((((long long)n_u * P.Ti + t0[q]) * P.Hi + h0[q]) * P.Wi + w0[q]) * P.x_row_stride;
           }
-          const uint32_t ui = (uint32_t)(half * per_thread + i);
+        }
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t a_tile = smem_base + stage * stage_bytes;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full_bar(stage), b_bytes);
+        tma_load_2d(a_tile + GG_A_BYTES, &P.b_map, full_bar(stage), kb * GG_BK, n_tile * P.block_n);
+      }
+      const int u_base = kb * P.upk;
+      for (int ui = 0; ui < P.upk; ++ui) {
+        const int u = u_base + ui;
+        const bool uok = u < P.units_total && !(P.epi.dbg & 4);
+        const int uu = uok ? u : 0;
+        const int off = s_off[uu];
+        const unsigned dd = s_d[uu];
+        const int dt_ = (int)(dd & 0xffu), dh_ = (int)((dd >> 8) & 0xffu), dw_ = (int)(dd >> 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = lane + 32 * q;
+          const bool ok = uok && rok[q] && (unsigned)(t0[q] + dt_) < (unsigned)P.Ti &&
+                          (unsigned)(h0[q] + dh_) < (unsigned)P.Hi && (unsigned)(w0[q] + dw_) < (unsigned)P.Wi;
+          const __half* src = ok ? xrow[q] + off : x;
+          const uint32_t rbase = a_tile + (uint32_t)row * 128u;
+          const uint32_t rsw = (uint32_t)(row & 7);
           if (P.gbytes == 16) {
-            const uint32_t dst = a_tile + row_off + ((ui ^ rsw) << 4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rbase + (((uint32_t)ui ^ rsw) << 4)), "l"(src),
+                         "r"(ok ? 16u : 0u) : "memory");
           } else {
-            const uint32_t dst = a_tile + row_off + (((ui >> 1) ^ rsw) << 4) + ((ui & 1u) << 3);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(rbase + ((((uint32_t)ui >> 1) ^ rsw) << 4) + (((uint32_t)ui & 1u) << 3)),
+                         "l"(src), "r"(ok ? 8u : 0u) : "memory");
           }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (++stage_i == stages) { stage_i = 0; phase_i ^= 1u; }
-        if (++inflight > GG_DEPTH) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(GG_DEPTH) : "memory");
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar(stage_c));
-          if (++stage_c == stages) stage_c = 0;
-          --inflight;
-        }
       }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    fence_proxy_async_smem();
-    __syncwarp();
-    while (inflight > 0) {
-      if (lane == 0) mbar_arrive(full_bar(stage_c));
-      if (++stage_c == stages) stage_c = 0;
-      --inflight;
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      if (!(P.epi.dbg & 8)) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ============================================
@@ -199,28 +207,36 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
             umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                      (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (kb == P.num_kb - 1) umma_commit(tfull_bar(acc));
+          if (kb == P.num_kb - 1) {
+            umma_commit(tfull_bar(acc));
+            if (P.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 64) P.trace[64 + tile / gridDim.x] = clock64();
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
     // ================================ epilogue warps ========================================
     const int quarter = warp & 3;
-    int acc = 0, tile_seq = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    int tile_seq = 0;
+    uint32_t res_phase = 0;
+    const bool narrow = epi_narrow(P.block_n);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
+      if (narrow && (tile_seq & 1) != (warp >> 2)) continue;      // the other group's tile
+      const int acc = tile_seq % nacc;
+      const uint32_t acc_phase = (uint32_t)((tile_seq / nacc) & 1);
       const int n_tile = tile % P.n_tiles;
       const int m_tile = tile / P.n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tile_seq < 64) P.trace[128 + tile_seq] = clock64();
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                     res_bar, res_phase, warp, quarter, lane, n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0,
                     tempty_bar(acc), tile_seq);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tile_seq < 64) P.trace[192 + tile_seq] = clock64();
     }
-    if (warp == 0 && lane == 0) tma_store_wait_all();
+    if ((warp & 3) == 0 && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -308,23 +324,27 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   }
   {
     P.acc_stride = (P.block_n + 31) / 32 * 32;
-    int cols = 2 * P.acc_stride, p2 = 32;
+    P.nacc = 512 / P.acc_stride;
+    if (P.nacc > 8) P.nacc = 8;
+    if (P.nacc < 2) P.nacc = 2;
+    int cols = P.nacc * P.acc_stride, p2 = 32;
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
   const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
   {
-    int st = (227 * 1024 - 2048 - EPI_SMEM_BYTES - 256) / stage_bytes;
+    int st = (227 * 1024 - 2048 - 2048 /*static tables*/ - EPI_SMEM_BYTES - 512) / stage_bytes;
     if (st > 12) st = 12;
-    if (st < GG_DEPTH + 1) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
+    if (st < 2) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
     P.stages = st;
   }
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_SMEM_BYTES + 8 * (2 * P.stages + 6) + 16;
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_SMEM_BYTES + 8 * (2 * P.stages + 2 * 8 + 4) + 16;
   P.epi.block_n = P.block_n;
   P.epi.Co = d->Co;
   P.epi.rows = GG_BM;
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
+  { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
   for (int pass = 0; pass < 2; ++pass) {     // output / residual as [Co, M, 1, 1, 1]
     if (pass == 1 && !d->has_residual) break;
     const long long rs = pass == 0 ? d->y_row_stride : d->res_row_stride;
@@ -350,13 +370,30 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   }
   if (!attr_set) {
     PV_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    227 * 1024));
+                                    225 * 1024));
     attr_set = true;
   }
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
+  static long long* trace_buf = nullptr;
+  const bool trace = getenv("PVB200_TRACE") != nullptr;
+  if (trace && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
+  P.trace = trace ? trace_buf : nullptr;
+  if (trace) cudaMemset(trace_buf, 0, 512 * sizeof(long long));
   conv3d_igemm_gather_kernel<<<grid, GG_THREADS, smem_bytes, stream>>>(P, (const __half*)x, scale, bias);
+  if (trace) {
+    long long h[512];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "TRACE tiles=%d kb=%d block_n=%d stages=%d nacc=%d\n", P.m_tiles * P.n_tiles, P.num_kb, P.block_n, P.stages, P.nacc);
+    for (int i = 0; i < 16; ++i)
+      fprintf(stderr, "  kblock %2d: loop_top %8lld  after_empty_wait %8lld  after_issue %8lld  after_waitgroup_arrive %8lld\n", i,
+              h[256 + i * 4] - h[0], h[256 + i * 4 + 1] - h[0], h[256 + i * 4 + 2] - h[0], h[256 + i * 4 + 3] - h[0]);
+    for (int i = 0; i < 6; ++i)
+      fprintf(stderr, "  tile %2d: prod_start %8lld  mma_commit %8lld  epi_start %8lld  epi_end %8lld\n", i, h[i] - h[0],
+              h[64 + i] - h[0], h[128 + i] - h[0], h[192 + i] - h[0]);
+  }
   PV_LAUNCH_OK("conv3d_igemm_gather_kernel");
   return PV_OK;
 }
