@@ -5,6 +5,7 @@
 // A CTA owns ATT_BQ query rows of one (batch, head); K/V stream through shared memory in tiles
 // of 32 keys; online softmax state (running max / sum / output) stays in registers.
 #include "pv_common.cuh"
+#include <stdlib.h>
 
 namespace pv {
 
@@ -127,6 +128,9 @@ static int launch_attention(const pv_attention_desc* d, const void* q, const voi
   return PV_OK;
 }
 
+int attention_mma_dispatch(const pv_attention_desc* d, const void* q, const void* k, const void* v, void* o,
+                           cudaStream_t s);   // pv_attention_mma.cu
+
 }  // namespace pv
 
 extern "C" int pv_attention_fwd(const pv_attention_desc* d, const void* q, const void* k,
@@ -136,6 +140,10 @@ extern "C" int pv_attention_fwd(const pv_attention_desc* d, const void* q, const
   PV_CHECK_ARG(d->B > 0 && d->H > 0 && d->Nq > 0 && d->Nk > 0, "empty attention problem");
   PV_CHECK_ARG((long long)d->B * d->H <= 65535, "B*H too large");
   cudaStream_t s = (cudaStream_t)stream;
+  if (d->dtype == PV_F16 && !getenv("PVB200_ATTN_SIMT")) {     // tensor-core path (f16 storage)
+    const int rc = pv::attention_mma_dispatch(d, q, k, v, o, s);
+    if (rc != PV_ERR_UNSUPPORTED) return rc;
+  }
 #define PV_ATT(DD)                                                                              \
   if (d->D == DD)                                                                               \
     return d->dtype == PV_F16 ? pv::launch_attention<__half, DD>(d, q, k, v, o, s)              \

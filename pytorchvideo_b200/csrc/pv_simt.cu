@@ -268,6 +268,75 @@ dwconv3d_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__
   st8<T>(y + (long long)n * ybs + mo * d.y_row_stride + c, v);
 }
 
+// Register-tiled depthwise stencil: one thread = 4 consecutive output columns x 8 channels.  For each
+// (kt,kh) filter row the KW weight vectors are converted once and every input column is loaded and
+// converted once and used by all outputs it feeds - 2.7x fewer loads and half the instructions of the
+// one-output-per-thread kernel for the 3x3x3 / stride-1 case (X3D, CSN, MViT pooling).
+template <typename T, int KW, int SW>
+__global__ void __launch_bounds__(128)
+dwconv3d_w4_kernel(pv_conv3d_desc d, const T* __restrict__ x, const T* __restrict__ w,
+                   const float* __restrict__ scale, const float* __restrict__ bias, T* __restrict__ y,
+                   long long total, int wo4) {
+  constexpr int WT = 4;
+  constexpr int NCOL = (WT - 1) * SW + KW;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = d.Co >> 3;
+  const int c = (int)(e % G) * 8;
+  long long m = e / G;
+  const int wq = (int)(m % wo4); long long r = m / wo4;
+  const int ho = (int)(r % d.Ho); r /= d.Ho;
+  const int to = (int)(r % d.To); const int n = (int)(r / d.To);
+  const int wo0 = wq * WT;
+  const int t0 = to * d.st - d.pt, h0 = ho * d.sh - d.ph, w0 = wo0 * SW - d.pw;
+  const long long xbs = d.x_batch_stride ? d.x_batch_stride : (long long)d.Ti * d.Hi * d.Wi * d.x_row_stride;
+  const long long ybs = d.y_batch_stride ? d.y_batch_stride : (long long)d.To * d.Ho * d.Wo * d.y_row_stride;
+  float acc[WT][8];
+#pragma unroll
+  for (int o = 0; o < WT; ++o)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[o][i] = 0.f;
+  for (int kt_ = 0; kt_ < d.kt; ++kt_) {
+    const int ti = t0 + kt_ * d.dt;
+    if ((unsigned)ti >= (unsigned)d.Ti) continue;
+    for (int kh_ = 0; kh_ < d.kh; ++kh_) {
+      const int hi = h0 + kh_ * d.dh;
+      if ((unsigned)hi >= (unsigned)d.Hi) continue;
+      const T* row = x + (long long)n * xbs + (((long long)ti) * d.Hi + hi) * d.Wi * d.x_row_stride + c;
+      const T* wrow = w + (long long)((kt_ * d.kh + kh_) * KW) * d.Co + c;
+      float wv[KW][8];
+#pragma unroll
+      for (int k = 0; k < KW; ++k) ld8<T>(wrow + (long long)k * d.Co, wv[k]);
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        const int wi = w0 + j;
+        if ((unsigned)wi >= (unsigned)d.Wi) continue;
+        float xv[8];
+        ld8<T>(row + (long long)wi * d.x_row_stride, xv);
+#pragma unroll
+        for (int o = 0; o < WT; ++o) {
+          const int k = j - o * SW;          // tap index this column has for output o (compile-time)
+          if (k >= 0 && k < KW) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(xv[i], wv[k][i], acc[o][i]);
+          }
+        }
+      }
+    }
+  }
+  float sc[8], bi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sc[i] = __ldg(scale + c + i); bi[i] = __ldg(bias + c + i); }
+#pragma unroll
+  for (int o = 0; o < WT; ++o) {
+    if (wo0 + o >= d.Wo) break;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = apply_act(acc[o][i] * sc[i] + bi[i], d.act);
+    st8<T>(y + (long long)n * ybs + ((((long long)to) * d.Ho + ho) * d.Wo + wo0 + o) * d.y_row_stride + c, v);
+  }
+}
+
 // =============================================================================================
 // Pooling (max / avg), NDHWC, one thread = one output position x 8 channels.
 // =============================================================================================
@@ -773,6 +842,23 @@ int conv3d_direct_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   } else {
     PV_CHECK_ARG(d->Co % 8 == 0, "depthwise conv needs C%%8==0");
     PV_CHECK_ARG(d->x_row_stride % 8 == 0 && d->y_row_stride % 8 == 0, "row strides must be multiples of 8");
+    // register-tiled variant for the common stencils (dilation_w 1, kw in {1,3}, stride_w in {1,2}, no residual)
+    if (!d->has_residual && d->dw == 1 && (d->kw == 3 || d->kw == 1) && (d->sw == 1 || d->sw == 2) && d->Wo >= 4) {
+      const int wo4 = (d->Wo + 3) / 4;
+      const long long tot4 = (long long)d->N * d->To * d->Ho * wo4 * (d->Co / 8);
+      dim3 g4((unsigned)cdiv(tot4, 128)), b4(128);
+#define PV_DW(TT, KW_, SW_) dwconv3d_w4_kernel<TT, KW_, SW_><<<g4, b4, 0, s>>>(*d, (const TT*)x, (const TT*)w, scale, bias, (TT*)y, tot4, wo4)
+      if (d->dtype == PV_F16) {
+        if (d->kw == 3 && d->sw == 1) PV_DW(__half, 3, 1); else if (d->kw == 3) PV_DW(__half, 3, 2);
+        else if (d->sw == 1) PV_DW(__half, 1, 1); else PV_DW(__half, 1, 2);
+      } else {
+        if (d->kw == 3 && d->sw == 1) PV_DW(float, 3, 1); else if (d->kw == 3) PV_DW(float, 3, 2);
+        else if (d->sw == 1) PV_DW(float, 1, 1); else PV_DW(float, 1, 2);
+      }
+#undef PV_DW
+      PV_LAUNCH_OK("dwconv3d_w4_kernel");
+      return PV_OK;
+    }
     const long long total = M * (d->Co / 8);
     dim3 grid((unsigned)cdiv(total, 256)), block(256);
     if (d->dtype == PV_F16)

@@ -13,6 +13,7 @@ import torch
 from .. import _lib as L
 
 _DT = {torch.uint8: L.PV_U8, torch.float32: L.PV_F32, torch.float16: L.PV_F16}
+_TABLE_CACHE = {}
 
 
 def temporal_indices(t, num_samples):
@@ -132,8 +133,17 @@ def clip_transform(x, frame_idx=None, resize_hw=None, window=None, mean=None, st
                         for c in range(Cc)]
                 return torch.cat(outs, 0)
     dev = x.device
-    tabs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (y0, y1, ly, x0, x1, lx)]
-    idx_d = kidx.to(torch.int32).to(dev)
+    # device-side tables are tiny but cost several H2D copies: cache them per (geometry, device)
+    ckey = (dev.index, H, W, nh, nw, top, left, oh, ow, tuple(int(i) for i in kidx.tolist()))
+    cached = _TABLE_CACHE.get(ckey)
+    if cached is None:
+        tabs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (y0, y1, ly, x0, x1, lx)]
+        idx_d = kidx.to(torch.int32).to(dev)
+        if len(_TABLE_CACHE) > 256:
+            _TABLE_CACHE.clear()
+        _TABLE_CACHE[ckey] = (tabs, idx_d)
+    else:
+        tabs, idx_d = cached
     if out is None:
         out = torch.empty((Cc, n_t, oh, ow), dtype=out_dtype, device=dev)
     else:

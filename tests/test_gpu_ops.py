@@ -116,3 +116,17 @@ def test_attention(Nq, Nk, resid):
     ref = attn @ v + (q if resid else 0)
     got = ops.attention(q.to(_dev()), k.to(_dev()), v.to(_dev()), scale, resid, "f32").cpu()
     assert torch.allclose(got, ref, rtol=1e-3, atol=1e-4), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("Nq,Nk,resid", [(50, 50, False), (393, 393, False), (130, 37, True), (1569, 393, False), (65, 129, True)])
+def test_attention_f16_tensor_core(Nq, Nk, resid):
+    from pytorchvideo_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    B, H, D = 2, 3, 96
+    q, k, v = (torch.randn(B, H, n, D, generator=g).half().float() for n in (Nq, Nk, Nk))
+    scale = D ** -0.5
+    attn = ((q * scale) @ k.transpose(-2, -1)).softmax(-1)
+    ref = attn @ v + (q if resid else 0)
+    got = ops.attention(q.to(_dev()), k.to(_dev()), v.to(_dev()), scale, resid, "f16").cpu()
+    err = (got - ref).abs()
+    assert float(err.max()) <= 4e-3 * max(1.0, float(ref.abs().max())), float(err.max())
