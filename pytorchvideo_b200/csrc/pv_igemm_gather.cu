@@ -39,6 +39,7 @@ struct GatherParams {
   long long x_row_stride;
   long long M;
   int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, acc_stride, nacc;
+  int nprod;   // active producer warps; stages is a multiple of nprod so every smem slot has ONE owner warp
   EpiParams epi;
   long long* trace;   // debug: per-tile timestamps of CTA 0 (PVB200_TRACE=1)
   int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
@@ -117,7 +118,10 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
     const __half* xrow[4];
     bool rok[4];
     int n_tile = 0;
-    for (int g = wprod; g < total_g; g += GG_PROD_WARPS) {
+    // Slot ownership: stages % nprod == 0, so slot s is only ever filled by warp s % nprod, in order;
+    // a parity wait can then never alias a completion two phases back (it could with free-running
+    // warps sharing slots).
+    for (int g = wprod; wprod < P.nprod && g < total_g; g += P.nprod) {
       const int tile_seq = g / P.num_kb;
       const int kb = g - tile_seq * P.num_kb;
       const int stage = g % stages;
@@ -334,9 +338,10 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
   {
     int st = (227 * 1024 - 2048 - 2048 /*static tables*/ - EPI_SMEM_BYTES - 512) / stage_bytes;
-    if (st > 12) st = 12;
+    if (st > 16) st = 16;
     if (st < 2) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
-    P.stages = st;
+    P.nprod = st < GG_PROD_WARPS ? st : GG_PROD_WARPS;
+    P.stages = (st / P.nprod) * P.nprod;
   }
   const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_SMEM_BYTES + 8 * (2 * P.stages + 2 * 8 + 4) + 16;
   P.epi.block_n = P.block_n;
