@@ -169,6 +169,16 @@ int pv_temporal_tap_sum(const void* yk, void* y, int dtype, int N, int Ti, int T
 int pv_conv3d_fwd(const pv_conv3d_desc* d, int algo, const void* x, const void* w,
                   const float* scale, const float* bias, const void* residual, void* y,
                   void* stream);
+/* Depthwise convolution (groups == Ci == Co) + folded BN + activation with optional fused
+ * Squeeze-Excitation statistics: when se_sums != NULL, se_sums[n][c] += sum over output positions
+ * of the PRE-activation value (caller zeroes it; feeds pv_se_gate).  f16 storage runs as a TMA-fed
+ * shared-memory stencil; other cases take the generic CUDA-core stencil (+ pv_channel_sum).
+ * Replaces conv_b -> norm_b -> SE-pool of models/x3d.py:180-198, the X3D stem conv_xy
+ * (models/x3d.py:74-82), CSN's conv_b (models/csn.py:169) and MViT's pooling convs
+ * (layers/attention.py:364-403).  w: [tap][C]. */
+int pv_dwconv3d_fwd(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                    const float* bias, void* y, float* se_sums, void* stream);
+
 /* 1 if PV_ALGO_TCGEN05 supports this descriptor (pure host-side check, no GPU needed). */
 int pv_conv3d_tcgen05_supported(const pv_conv3d_desc* d);
 

@@ -28,7 +28,14 @@ struct EpiParams {
   CUtensorMap y_map;    // output  [Co, d1, d2, d3, d4], box [64, b1, b2, b3, b4], SWIZZLE_128B
   CUtensorMap r_map;    // residual, same geometry
   int block_n, Co, rows, act, has_residual;
-  int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip TMA stores, 2 = skip epilogue math, 4 = producers skip loads
+  int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip stores, 2 = skip epilogue math, 4 = producers skip loads,
+             // 32 = MMA warp skips the MMAs, 64 = narrow tiles take the direct (register -> global) epilogue
+  // direct (register -> global) epilogue for BLOCK_N <= 64: row r of a tile decodes into box coordinates
+  // (dim 0 fastest, the order the A-operand TMA box lands in shared memory) -> element offsets
+  __half* y_ptr;
+  const __half* r_ptr;
+  long long y_str[4], r_str[4];   // element stride of +1 in merged output dim i
+  int O[4], box[4];               // merged output extents / tile box
 };
 
 __device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3,
@@ -201,6 +208,125 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* _
     }
   }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Direct epilogue for narrow tiles (BLOCK_N <= 64).  Measured on B200 (tools/narrow_probe.py): the
+// TMA-staged path is a per-tile latency chain of two TMA round trips (residual load, then the
+// store's shared-memory read that frees the staging slot; ~1500 clk each) which bounds a narrow
+// layer at ~2400 clk per 128-row tile.  A thread owns one output row; with <= 64 channels that row
+// is <= 128 contiguous bytes, so plain 16-byte global loads/stores are already full-sector
+// transfers.  The residual row is requested BEFORE the accumulator barrier is waited on (its
+// latency hides behind the MMA), the accumulator is handed back right after the last tcgen05.ld,
+// and there is no shared staging and no CTA-level barrier at all.  Called per warp; the two groups
+// of 4 epilogue warps take alternate tiles.
+// ---------------------------------------------------------------------------------------------
+template <int ACT, bool RES>
+__device__ __forceinline__ void epi_direct_row(const EpiParams& E, const float* __restrict__ scale,
+                                               const float* __restrict__ bias, uint32_t t_row, __half* yrow,
+                                               const __half* rrow, bool row_ok, int n0, uint32_t tfull_bar,
+                                               uint32_t tfull_phase, uint32_t tempty_bar, int lane) {
+  uint4 rv[8];
+  if (RES) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      rv[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (j * 8 < E.block_n && row_ok && n0 + j * 8 < E.Co) rv[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
+    }
+  }
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    if (c0 < E.block_n) {
+      uint32_t v[32];
+      tmem_ld32(t_row + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (c0 + 32 >= E.block_n) {        // accumulator fully read: hand TMEM back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int cc = c0 + h * 8;
+        const int c = n0 + cc;
+        if (cc < E.block_n && c < E.Co && row_ok && !(E.dbg & 2)) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+          float f[8];
+          f[0] = fmaf(__uint_as_float(v[h * 8 + 0]), s0.x, b0.x);
+          f[1] = fmaf(__uint_as_float(v[h * 8 + 1]), s0.y, b0.y);
+          f[2] = fmaf(__uint_as_float(v[h * 8 + 2]), s0.z, b0.z);
+          f[3] = fmaf(__uint_as_float(v[h * 8 + 3]), s0.w, b0.w);
+          f[4] = fmaf(__uint_as_float(v[h * 8 + 4]), s1.x, b1.x);
+          f[5] = fmaf(__uint_as_float(v[h * 8 + 5]), s1.y, b1.y);
+          f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), s1.z, b1.z);
+          f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), s1.w, b1.w);
+          if (RES) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv[(c0 >> 3) + h]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 r2 = __half22float2(rh[q]);
+              f[2 * q] += r2.x;
+              f[2 * q + 1] += r2.y;
+            }
+          }
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(act_t<ACT>(f[2 * q]), act_t<ACT>(f[2 * q + 1]));
+          if (!(E.dbg & 1)) *reinterpret_cast<uint4*>(yrow + cc) = ov;
+        }
+      }
+    }
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_direct_act(const EpiParams& E, const float* scale, const float* bias, uint32_t t_row,
+                                               __half* yrow, const __half* rrow, bool row_ok, int n0, uint32_t tfull_bar,
+                                               uint32_t tfull_phase, uint32_t tempty_bar, int lane) {
+  if (E.has_residual) epi_direct_row<ACT, true>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+  else epi_direct_row<ACT, false>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+}
+
+// o0..o3: tile origin in the merged output dims.  Waits on tfull itself.
+__device__ __forceinline__ void epilogue_tile_direct(const EpiParams& E, const float* __restrict__ scale,
+                                                     const float* __restrict__ bias, uint32_t t_acc, int quarter,
+                                                     int lane, int n0, int o0, int o1, int o2, int o3,
+                                                     uint32_t tfull_bar, uint32_t tfull_phase, uint32_t tempty_bar) {
+  const int row = quarter * 32 + lane;
+  bool ok = row < E.rows;
+  long long yoff = n0, roff = n0;
+  {
+    int rr = row;
+    const int og[4] = {o0, o1, o2, o3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int bi = E.box[i];
+      const int q = bi > 1 ? rr / bi : rr;
+      const int ci = bi > 1 ? rr - q * bi : 0;
+      rr = q;
+      const int gi = og[i] + ci;
+      ok = ok && gi < E.O[i];
+      yoff += (long long)gi * E.y_str[i];
+      roff += (long long)gi * E.r_str[i];
+    }
+  }
+  const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
+  __half* yrow = E.y_ptr + (ok ? yoff : 0);
+  const __half* rrow = E.has_residual ? E.r_ptr + (ok ? roff : 0) : nullptr;
+  switch (E.act) {
+    case PV_ACT_RELU: epi_direct_act<PV_ACT_RELU>(E, scale, bias, t_row, yrow, rrow, ok, n0, tfull_bar, tfull_phase, tempty_bar, lane); break;
+    case PV_ACT_NONE: epi_direct_act<PV_ACT_NONE>(E, scale, bias, t_row, yrow, rrow, ok, n0, tfull_bar, tfull_phase, tempty_bar, lane); break;
+    case PV_ACT_SWISH: epi_direct_act<PV_ACT_SWISH>(E, scale, bias, t_row, yrow, rrow, ok, n0, tfull_bar, tfull_phase, tempty_bar, lane); break;
+    case PV_ACT_GELU: epi_direct_act<PV_ACT_GELU>(E, scale, bias, t_row, yrow, rrow, ok, n0, tfull_bar, tfull_phase, tempty_bar, lane); break;
+    default: epi_direct_act<PV_ACT_SIGMOID>(E, scale, bias, t_row, yrow, rrow, ok, n0, tfull_bar, tfull_phase, tempty_bar, lane); break;
+  }
+}
+
+__host__ __device__ inline bool epi_direct(const EpiParams& E) { return epi_narrow(E.block_n) && (E.dbg & 64); }   // opt-in while under test
 
 }  // namespace sm100
 }  // namespace pv

@@ -133,16 +133,20 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
         const int n0 = n_tile * P.block_n;
         for (int tap = 0; tap < P.taps; ++tap) {
           for (int kc = 0; kc < P.num_kc; ++kc, ++g) {
-            if ((g % P.nprod) == warp) {
+            if (P.nprod == 1 || (g % P.nprod) == warp) {
               const void* amap = &P.a_maps[P.tap_map[tap]];
               const int c1 = o[0] + P.tap_q[tap][0], c2 = o[1] + P.tap_q[tap][1];
               const int c3 = o[2] + P.tap_q[tap][2], c4 = o[3] + P.tap_q[tap][3];
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * stage_bytes;
               const uint32_t b_dst = a_dst + a_bytes;
-              mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-              tma_load_5d(a_dst, amap, full_bar(stage), kc * k_elems, c1, c2, c3, c4);
-              tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * k_elems, n0);
+              if (P.epi.dbg & 4) {               // probe: pipeline skeleton without the loads
+                mbar_arrive(full_bar(stage));
+              } else {
+                mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+                tma_load_5d(a_dst, amap, full_bar(stage), kc * k_elems, c1, c2, c3, c4);
+                tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * k_elems, n0);
+              }
             }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
@@ -168,7 +172,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
           const uint64_t a_desc = make_kmajor_desc(a_addr, P.kbytes);
           const uint64_t b_desc = make_kmajor_desc(a_addr + a_bytes, P.kbytes);
           const int k16 = P.kbytes >> 5;
-          for (int k = 0; k < k16; ++k) {
+          for (int k = 0; k < k16 && !(P.epi.dbg & 32); ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in (addr>>4)
             umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                      (kb | k) != 0 ? 1u : 0u);
@@ -196,6 +200,11 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       int o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
+      if (epi_direct(P.epi)) {
+        epilogue_tile_direct(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), quarter, lane,
+                             n_tile * P.block_n, o[0], o[1], o[2], o[3], tfull_bar(acc), acc_phase, tempty_bar(acc));
+        continue;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
@@ -529,6 +538,14 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     for (int o = 0; o < 4; ++o) {
       const int m = pl.orig2m[o];
       if (!seen[m]) { seen[m] = true; ostr[m] = ostr_orig[o]; }
+    }
+    P.epi.y_ptr = (__half*)y;
+    P.epi.r_ptr = (const __half*)residual;
+    for (int m = 0; m < 4; ++m) {
+      P.epi.O[m] = P.O[m];
+      P.epi.box[m] = P.box[m];
+      P.epi.y_str[m] = seen[m] ? ostr[m] * d->y_row_stride : 0;      // filler dims have extent 1
+      P.epi.r_str[m] = seen[m] ? ostr[m] * d->res_row_stride : 0;
     }
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1 && !d->has_residual) break;

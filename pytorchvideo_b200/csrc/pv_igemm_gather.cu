@@ -35,6 +35,7 @@ struct GatherParams {
   int gbytes;        // gather unit: 8 or 16 bytes
   int units_total;   // taps * (Ci*2/gbytes)
   int upk;           // units per 64-element k-block: 128 / gbytes
+  int upt, taps;     // units per tap, taps (<= 64: one validity bit per tap)
   int num_kb;
   long long x_row_stride;
   long long M;
@@ -114,10 +115,12 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_g = my_tiles * P.num_kb;
     int cur_seq = -1;
-    int t0[4], h0[4], w0[4];
     const __half* xrow[4];
-    bool rok[4];
+    unsigned long long vmask[4];     // bit `tap` set <=> row q's input position for that tap is inside the tensor
     int n_tile = 0;
+    const unsigned Ti = (unsigned)P.Ti, Hi = (unsigned)P.Hi, Wi = (unsigned)P.Wi;
+    const uint32_t rsw = (uint32_t)(lane & 7);           // (lane + 32q) & 7
+    const uint32_t row_off = (uint32_t)lane * 128u;
     // Slot ownership: stages % nprod == 0, so slot s is only ever filled by warp s % nprod, in order;
     // a parity wait can then never alias a completion two phases back (it could with free-running
     // warps sharing slots).
@@ -127,26 +130,38 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       const int stage = g % stages;
       const uint32_t phase = (uint32_t)((g / stages) & 1);
       if (tile_seq != cur_seq) {
+        // Per tile: row corners + one validity bit per (row, tap).  Everything in the copy loop below is
+        // then branch-free (the bounds tests used to compile into divergent short-circuit branches with a
+        // constant-bank load each: ~4000 clk of exposed latency per k-block).
         cur_seq = tile_seq;
         const int tile = (int)blockIdx.x + tile_seq * (int)gridDim.x;
         n_tile = tile % P.n_tiles;
         const int m_tile = tile / P.n_tiles;
+        int t0[4], h0[4], w0[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const long long m = (long long)m_tile * GG_BM + lane + 32 * q;
-          rok[q] = m < P.M;
-          t0[q] = h0[q] = w0[q] = 0;
-          xrow[q] = x;
-          if (rok[q]) {
-            const uint32_t mu = (uint32_t)m;
-            uint32_t r = mu / (uint32_t)P.Wo;
-            const int wo = (int)(mu - r * (uint32_t)P.Wo);
-            uint32_t r2 = r / (uint32_t)P.Ho;
-            const int ho = (int)(r - r2 * (uint32_t)P.Ho);
-            const uint32_t n_u = r2 / (uint32_t)P.To;
-            const int to = (int)(r2 - n_u * (uint32_t)P.To);
-            t0[q] = to * P.st - P.pt; h0[q] = ho * P.sh - P.ph; w0[q] = wo * P.sw - P.pw;
-            xrow[q] = x + ((((long long)n_u * P.Ti + t0[q]) * P.Hi + h0[q]) * P.Wi + w0[q]) * P.x_row_stride;
+          const bool rok = m < P.M;
+          const uint32_t mu = rok ? (uint32_t)m : 0u;
+          uint32_t r = mu / (uint32_t)P.Wo;
+          const int wo = (int)(mu - r * (uint32_t)P.Wo);
+          uint32_t r2 = r / (uint32_t)P.Ho;
+          const int ho = (int)(r - r2 * (uint32_t)P.Ho);
+          const uint32_t n_u = r2 / (uint32_t)P.To;
+          const int to = (int)(r2 - n_u * (uint32_t)P.To);
+          t0[q] = to * P.st - P.pt; h0[q] = ho * P.sh - P.ph; w0[q] = wo * P.sw - P.pw;
+          if (!rok) t0[q] = -100000;        // every tap out of range -> all-zero row
+          xrow[q] = x + ((((long long)n_u * P.Ti + t0[q]) * P.Hi + h0[q]) * P.Wi + w0[q]) * P.x_row_stride;
+          vmask[q] = 0ull;
+        }
+        for (int tap = 0; tap < P.taps; ++tap) {
+          const unsigned dd = s_d[tap * P.upt];
+          const int dt_ = (int)(dd & 0xffu), dh_ = (int)((dd >> 8) & 0xffu), dw_ = (int)((dd >> 16) & 0xffu);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned ok = (unsigned)((unsigned)(t0[q] + dt_) < Ti) & (unsigned)((unsigned)(h0[q] + dh_) < Hi) &
+                                (unsigned)((unsigned)(w0[q] + dw_) < Wi);
+            vmask[q] |= (unsigned long long)ok << tap;
           }
         }
       }
@@ -157,27 +172,41 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
         tma_load_2d(a_tile + GG_A_BYTES, &P.b_map, full_bar(stage), kb * GG_BK, n_tile * P.block_n);
       }
       const int u_base = kb * P.upk;
-      for (int ui = 0; ui < P.upk; ++ui) {
-        const int u = u_base + ui;
-        const bool uok = u < P.units_total && !(P.epi.dbg & 4);
-        const int uu = uok ? u : 0;
-        const int off = s_off[uu];
-        const unsigned dd = s_d[uu];
-        const int dt_ = (int)(dd & 0xffu), dh_ = (int)((dd >> 8) & 0xffu), dw_ = (int)(dd >> 16);
+      int units_here = P.units_total - u_base;
+      if (units_here > P.upk) units_here = P.upk;
+      // zero-fill only up to the end of the last 16-element MMA step that holds data (the MMA warp issues
+      // exactly those steps); smem beyond it is never read
+      const int need = (((units_here * P.gbytes + 31) >> 5) << 5) / P.gbytes;
+      const bool live = !(P.epi.dbg & 4);
+      const uint32_t rbase = a_tile + row_off;
+      if (P.gbytes == 16) {
+        for (int ui = 0; ui < need; ++ui) {
+          const bool uok = live && ui < units_here;
+          const int uu = uok ? u_base + ui : 0;
+          const int off = s_off[uu];
+          const unsigned tap = s_d[uu] >> 24;
+          const uint32_t dst = rbase + (((uint32_t)ui ^ rsw) << 4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int row = lane + 32 * q;
-          const bool ok = uok && rok[q] && (unsigned)(t0[q] + dt_) < (unsigned)P.Ti &&
-                          (unsigned)(h0[q] + dh_) < (unsigned)P.Hi && (unsigned)(w0[q] + dw_) < (unsigned)P.Wi;
-          const __half* src = ok ? xrow[q] + off : x;
-          const uint32_t rbase = a_tile + (uint32_t)row * 128u;
-          const uint32_t rsw = (uint32_t)(row & 7);
-          if (P.gbytes == 16) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rbase + (((uint32_t)ui ^ rsw) << 4)), "l"(src),
+          for (int q = 0; q < 4; ++q) {
+            const bool ok = uok && ((vmask[q] >> tap) & 1ull);
+            const __half* src = ok ? xrow[q] + off : x;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 4096u), "l"(src),
                          "r"(ok ? 16u : 0u) : "memory");
-          } else {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(rbase + ((((uint32_t)ui >> 1) ^ rsw) << 4) + (((uint32_t)ui & 1u) << 3)),
-                         "l"(src), "r"(ok ? 8u : 0u) : "memory");
+          }
+        }
+      } else {
+        for (int ui = 0; ui < need; ++ui) {
+          const bool uok = live && ui < units_here;
+          const int uu = uok ? u_base + ui : 0;
+          const int off = s_off[uu];
+          const unsigned tap = s_d[uu] >> 24;
+          const uint32_t dst = rbase + ((((uint32_t)ui >> 1) ^ rsw) << 4) + (((uint32_t)ui & 1u) << 3);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool ok = uok && ((vmask[q] >> tap) & 1ull);
+            const __half* src = ok ? xrow[q] + off : x;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)q * 4096u), "l"(src),
+                         "r"(ok ? 8u : 0u) : "memory");
           }
         }
       }
@@ -207,7 +236,7 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
           int units_left = P.units_total - kb * P.upk;
           if (units_left > P.upk) units_left = P.upk;
           const int k16 = (units_left * P.gbytes + 31) >> 5;   // 16-element (32 B) MMA steps that hold data
-          for (int k = 0; k < k16; ++k)
+          for (int k = 0; k < k16 && !(P.epi.dbg & 32); ++k)
             umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                      (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
@@ -232,6 +261,11 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       const uint32_t acc_phase = (uint32_t)((tile_seq / nacc) & 1);
       const int n_tile = tile % P.n_tiles;
       const int m_tile = tile / P.n_tiles;
+      if (epi_direct(P.epi)) {
+        epilogue_tile_direct(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), quarter, lane,
+                             n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0, tfull_bar(acc), acc_phase, tempty_bar(acc));
+        continue;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tile_seq < 64) P.trace[128 + tile_seq] = clock64();
@@ -269,7 +303,8 @@ int conv3d_gather_supported(const pv_conv3d_desc* d) {
   const int units = d->kt * d->kh * d->kw * (d->Ci * 2 / gbytes);
   if (units > GG_MAX_UNITS) return 0;
   if (d->x_row_stride % (gbytes / 2) || d->y_row_stride % 8 || (d->has_residual && d->res_row_stride % 8)) return 0;
-  if (d->dt * (d->kt - 1) > 255 || d->dh * (d->kh - 1) > 255 || d->dw * (d->kw - 1) > 65535) return 0;
+  if (d->dt * (d->kt - 1) > 255 || d->dh * (d->kh - 1) > 255 || d->dw * (d->kw - 1) > 255) return 0;
+  if (d->kt * d->kh * d->kw > 64) return 0;   // one validity bit per tap
   const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
   if (M >= (1ll << 31)) return 0;
   return 1;
@@ -298,6 +333,7 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   const int upt = d->Ci * 2 / P.gbytes;
   const int taps = d->kt * d->kh * d->kw;
   P.units_total = taps * upt;
+  P.upt = upt; P.taps = taps;
   P.upk = 128 / P.gbytes;
   P.num_kb = (P.units_total + P.upk - 1) / P.upk;
   P.x_row_stride = d->x_row_stride;
@@ -315,7 +351,7 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
           const long long o = off + (long long)q * (P.gbytes / 2);
           if (o > 0x7fffffffll) { set_error("gather offset overflow"); return PV_ERR_UNSUPPORTED; }
           P.unit_off[u] = (int)o;
-          P.unit_d[u] = (unsigned)dt | ((unsigned)dh << 8) | ((unsigned)dw << 16);
+          P.unit_d[u] = (unsigned)dt | ((unsigned)dh << 8) | ((unsigned)dw << 16) | ((unsigned)tap << 24);
         }
       }
   {
@@ -350,6 +386,11 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
   { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
+  P.epi.y_ptr = (__half*)y;
+  P.epi.r_ptr = (const __half*)residual;
+  for (int m = 0; m < 4; ++m) { P.epi.O[m] = 1; P.epi.box[m] = 1; P.epi.y_str[m] = 0; P.epi.r_str[m] = 0; }
+  P.epi.O[0] = (int)P.M; P.epi.box[0] = GG_BM;
+  P.epi.y_str[0] = d->y_row_stride; P.epi.r_str[0] = d->res_row_stride;
   for (int pass = 0; pass < 2; ++pass) {     // output / residual as [Co, M, 1, 1, 1]
     if (pass == 1 && !d->has_residual) break;
     const long long rs = pass == 0 ? d->y_row_stride : d->res_row_stride;

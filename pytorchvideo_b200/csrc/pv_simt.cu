@@ -2,6 +2,7 @@
 // pooling, squeeze-excitation, head reduction, LayerNorm.  All are HBM-bound or serve shapes the
 // tcgen05 implicit-GEMM path does not take (3-channel stems, fp32 "parity" storage).
 #include "pv_common.cuh"
+#include <stdlib.h>
 
 namespace pv {
 
@@ -822,6 +823,9 @@ int conv3d_check(const pv_conv3d_desc* d) {
   return PV_OK;
 }
 
+int dwconv3d_tile_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                         const float* bias, void* y, float* se_sums, cudaStream_t stream);   // pv_dwconv.cu
+
 int conv3d_direct_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
                          const float* bias, const void* residual, void* y, cudaStream_t s) {
   const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
@@ -842,6 +846,11 @@ int conv3d_direct_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   } else {
     PV_CHECK_ARG(d->Co % 8 == 0, "depthwise conv needs C%%8==0");
     PV_CHECK_ARG(d->x_row_stride % 8 == 0 && d->y_row_stride % 8 == 0, "row strides must be multiples of 8");
+    // TMA-fed shared-memory stencil (pv_dwconv.cu) whenever it applies
+    if (!d->has_residual && d->dtype == PV_F16 && !getenv("PVB200_DW_SIMT")) {
+      const int rc = dwconv3d_tile_launch(d, x, w, scale, bias, y, nullptr, s);
+      if (rc != PV_ERR_UNSUPPORTED) return rc;
+    }
     // register-tiled variant for the common stencils (dilation_w 1, kw in {1,3}, stride_w in {1,2}, no residual)
     if (!d->has_residual && d->dw == 1 && (d->kw == 3 || d->kw == 1) && (d->sw == 1 || d->sw == 2) && d->Wo >= 4) {
       const int wo4 = (d->Wo + 3) / 4;

@@ -45,7 +45,7 @@ class Lowering:
         self.p = plan
 
     # ---- leaf helpers --------------------------------------------------------------------
-    def conv(self, x: TRef, conv: nn.Conv3d, bn=None, act=None, residual=None, name="conv"):
+    def conv(self, x: TRef, conv: nn.Conv3d, bn=None, act=None, residual=None, name="conv", se_sums=False):
         if type(conv).__name__ == "Conv2plus1d":
             return self.conv2plus1d(x, conv, bn, act, residual, name)
         if not isinstance(conv, nn.Conv3d):
@@ -57,7 +57,7 @@ class Lowering:
         if bn is not None and not _is_bn(bn):
             raise NotImplementedError("%s: norm %s unsupported (BatchNorm only)" % (name, type(bn).__name__))
         return self.p.emit_conv(x, conv.weight, conv.bias, bn, _t3(conv.stride), _t3(conv.padding),
-                                _t3(conv.dilation), conv.groups, _act_code(act), residual, name)
+                                _t3(conv.dilation), conv.groups, _act_code(act), residual, name, se_sums=se_sums)
 
     def conv2plus1d(self, x, m, bn, act, residual, name):
         # layers/convolutions.py:232-237: conv_t -> norm -> activation -> conv_xy
@@ -157,7 +157,7 @@ class Lowering:
         if se is None:
             h = self.conv(h, m.conv_b, norm_b, m.act_b, None, name + ".conv_b")
         else:
-            h = self.conv(h, m.conv_b, norm_b, None, None, name + ".conv_b")
+            h = self.conv(h, m.conv_b, norm_b, None, None, name + ".conv_b", se_sums=True)
             blk = se.block
             if type(blk[1]).__name__ != "ReLU" or type(blk[3]).__name__ != "Sigmoid":
                 raise NotImplementedError("SqueezeExcitation variant unsupported")
@@ -272,6 +272,11 @@ class CompiledModel:
         with torch.cuda.graph(g, stream=stream):
             self.plan.run(torch.cuda.current_stream().cuda_stream)
         self.graph = g
+
+    def pipeline(self, depth=2):
+        """Double-buffered host-in / host-out serving loop (engine/pipeline.py)."""
+        from .pipeline import ClipPipeline
+        return ClipPipeline(self, depth)
 
     def output_view(self):
         return self.out_buf.tensor[: int(torch.tensor(self.out_shape).prod())].view(*self.out_shape)

@@ -179,8 +179,10 @@ class Plan:
         return x
 
     def emit_conv(self, x, weight, conv_bias, bn, stride, padding, dilation, groups, act=L.ACT_NONE,
-                  residual=None, name="conv", force_algo=None):
-        """Conv3d (+folded BN/bias) (+residual) (+activation).  weight: [Co, Ci/g, kt, kh, kw]."""
+                  residual=None, name="conv", force_algo=None, se_sums=False):
+        """Conv3d (+folded BN/bias) (+residual) (+activation).  weight: [Co, Ci/g, kt, kh, kw].
+        se_sums (depthwise only): also accumulate the per-(sample, channel) sums of the output inside
+        the conv kernel (Squeeze-Excitation statistics); the buffer is attached as ``y.se_sums``."""
         co, cig, kt, kh, kw = weight.shape
         ci = cig * groups
         if ci != x.C:
@@ -280,6 +282,21 @@ class Plan:
                 algo, kind = L.ALGO_DIRECT, "direct"
                 w_d = self.const(PK.pack_dense_direct(weight, ci_pad, co_pad, tdt))
         lib = self.lib
+        sums = None
+        if se_sums and depthwise and residual is None and act == L.ACT_NONE:
+            sums = self.new_buf(x.N * co_pad, L.PV_F32)
+            self.zero_bufs.append(sums)
+            y.se_sums = sums
+
+            def fn_zero(stream):
+                L.check(lib.pv_zero_f32(sums.tensor.data_ptr(), x.N * co_pad, stream), "pv_zero_f32")
+            self.add(name + ".se_zero", fn_zero)
+
+        def fn_dw(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+            L.check(lib.pv_dwconv3d_fwd(C.byref(d), x.ptr(), w_d.data_ptr(), scale_d.data_ptr(), bias_d.data_ptr(),
+                                        y.ptr(), sums.tensor.data_ptr() if sums is not None else None, stream),
+                    "pv_dwconv3d_fwd(%s)" % name)
 
         def fn(stream):
             d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride   # may have been retargeted
@@ -291,7 +308,7 @@ class Plan:
         m_out = x.N * To * Ho * Wo
         flops = 2.0 * m_out * co * cig * kt * kh * kw
         nbytes = (x.N * x.npos * ci + m_out * co * (2 if residual is not None else 1)) * esz + weight.numel() * esz
-        self.add(name, fn, kind, flops, nbytes)
+        self.add(name, fn_dw if (depthwise and residual is None) else fn, kind, flops, nbytes)
         return y
 
     def emit_pool(self, x, mode, kernel, stride, padding, name="pool"):
@@ -328,9 +345,11 @@ class Plan:
         b2p = torch.zeros(Cp, dtype=torch.float32)
         b2p[:Cc] = b2.detach().float().cpu()
         w1d, b1d, w2d, b2d = self.const(w1p), self.const(b1.detach().float().cpu()), self.const(w2p), self.const(b2p)
-        sums = self.new_buf(x.N * Cp, L.PV_F32)
+        fused = getattr(x, "se_sums", None)       # already produced by the depthwise conv kernel
+        sums = fused if fused is not None else self.new_buf(x.N * Cp, L.PV_F32)
         gate = self.new_buf(x.N * Cp, L.PV_F32)
-        self.zero_bufs.append(sums)
+        if fused is None:
+            self.zero_bufs.append(sums)
         lib = self.lib
         npos = x.npos
 
@@ -347,7 +366,8 @@ class Plan:
         def fn_apply(stream):
             L.check(lib.pv_scale_act(x.ptr(), x.ptr(), x.dt, x.row_stride, x.row_stride, x.N, npos, Cp,
                                      gate.tensor.data_ptr(), act, stream), "pv_scale_act(%s)" % name)
-        self.add(name + ".sum", fn_sum)
+        if fused is None:
+            self.add(name + ".sum", fn_sum)
         self.add(name + ".gate", fn_gate)
         self.add(name + ".apply", fn_apply)
         return x

@@ -24,8 +24,9 @@ def _require_cuda(*ts):
 
 
 def conv3d_bn_act(x, weight, bias=None, bn=None, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1),
-                  groups=1, act=None, residual=None, dtype="f16", algo=None):
-    """y = act(BN(conv3d(x)) + residual); x, residual: [N,C,T,H,W] CUDA tensors; returns f32 NCDHW."""
+                  groups=1, act=None, residual=None, dtype="f16", algo=None, se_sums=False):
+    """y = act(BN(conv3d(x)) + residual); x, residual: [N,C,T,H,W] CUDA tensors; returns f32 NCDHW.
+    se_sums=True (depthwise): stats additionally carries "se_sums" = per-(n, c) output sums [N, C]."""
     _require_cuda(x, residual)
     plan = Plan(x.device, _DT[dtype], use_tcgen05=True)
     xin = x.contiguous().float()
@@ -36,12 +37,15 @@ def conv3d_bn_act(x, weight, bias=None, bn=None, stride=(1, 1, 1), padding=(0, 0
         rr = plan.emit_input_ncdhw(rin, residual.shape[1], (residual.shape[1] + 7) // 8 * 8)
     force = {None: None, "direct": L.ALGO_DIRECT, "tcgen05": L.ALGO_TCGEN05}[algo]
     y = plan.emit_conv(xr, weight, bias, bn, tuple(stride), tuple(padding), tuple(dilation), groups, _ACT[act], rr,
-                       "conv", force_algo=force)
+                       "conv", force_algo=force, se_sums=se_sums)
     out, shape = plan.emit_to_ncdhw(y)
     plan.finalize()
     plan.run(_stream(x.device))
     torch.cuda.synchronize(x.device)
-    return out.tensor[: int(torch.tensor(shape).prod())].view(*shape).clone(), plan.stats
+    stats = dict(plan.stats)
+    if se_sums:
+        stats["se_sums"] = y.se_sums.tensor.view(x.shape[0], -1)[:, : weight.shape[0]].clone()
+    return out.tensor[: int(torch.tensor(shape).prod())].view(*shape).clone(), stats
 
 
 def pool3d(x, mode, kernel, stride, padding, dtype="f16"):

@@ -93,3 +93,23 @@ def test_wrong_channels_raise_runtimeerror_on_gpu():
     model = PH.x3d_xs().eval().cuda()
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 4, 4, 160, 160, device="cuda"))
+
+
+def test_pipelined_serving_matches_direct_call():
+    """engine/pipeline.py: double-buffered host-in/host-out loop returns, in order, exactly what the
+    plain call returns for every batch (copies overlap compute; results must not be mixed up)."""
+    from pytorchvideo_b200.engine.lower import compile_model
+    model = TS.randomize_model(PH.slow_r50(), seed=11).eval()
+    batches = [TS.synthetic_clip(1, 8, 224, 224, seed=20 + i).pin_memory() for i in range(5)]
+    cm = compile_model(model, batches[0].cuda(), dtype="f16")
+    direct = [cm(b.cuda()).float().cpu().clone() for b in batches]
+    assert not torch.equal(direct[0], direct[1])
+    pipe = cm.pipeline(depth=2)
+    got = list(pipe.run(batches))
+    assert len(got) == len(batches)
+    for g, d in zip(got, direct):
+        assert torch.equal(g, d)
+    t = pipe.submit(batches[3])
+    assert torch.equal(pipe.result(t), direct[3])
+    with pytest.raises(RuntimeError):
+        pipe.result(t + 1)

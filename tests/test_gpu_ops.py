@@ -85,6 +85,50 @@ def test_conv3d_bn_act(case, dtype, algo):
         assert bool((err <= tol).all()), float(err.max())
 
 
+# depthwise stencil through pv_dwconv3d_fwd (TMA-fed shared-memory kernel for f16) incl. fused SE sums.
+# Shapes: X3D res2 / strided / stem temporal / 1x3x3, channel counts exercising the chunking (56, 216->24x9, 96->48x2)
+DW_CASES = [
+    (2, 56, 4, 20, 20, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 56, 5, 21, 19, (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+    (1, 216, 3, 9, 9, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 24, 8, 12, 12, (5, 1, 1), (1, 1, 1), (2, 0, 0)),
+    (1, 96, 4, 14, 14, (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+    (1, 64, 6, 15, 15, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (1, 128, 2, 7, 7, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 10, 3, 6, 6, (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # padded channels (10 -> 16)
+]
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("case", DW_CASES, ids=[str(i) for i in range(len(DW_CASES))])
+def test_dwconv3d_se_sums(case, dtype):
+    from pytorchvideo_b200 import ops
+    N, Cc, T, H, W, k, s, p = case
+    g = torch.Generator().manual_seed(Cc + T + H)
+    x = torch.randn(N, Cc, T, H, W, generator=g)
+    w = torch.randn(Cc, 1, *k, generator=g) * (2.0 / np.prod(k)) ** 0.5
+    bn = _bn(Cc, 7)
+    if dtype == "f16":
+        x, w = x.half().float(), w.half().float()
+    with torch.no_grad():
+        ref = _ref_conv(x, w, None, bn, s, p, (1, 1, 1), Cc, None, None)
+    got, stats = ops.conv3d_bn_act(x.to(_dev()), w, None, bn, s, p, (1, 1, 1), Cc, None, None, dtype, None,
+                                   se_sums=True)
+    got = got.cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    if dtype == "f32":
+        assert torch.allclose(got, ref, rtol=1e-3, atol=1e-4), float(err.max())
+    else:
+        tol = 1e-3 * ref.abs() + 1e-3 * float(ref.abs().max()) * 0.5 + 1e-4
+        assert bool((err <= tol).all()), float(err.max())
+    sums = stats["se_sums"].cpu()
+    ref_sums = ref.sum(dim=(2, 3, 4))
+    # sums are taken in fp32 BEFORE the f16 rounding of the stored output
+    assert torch.allclose(sums, ref_sums, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) * ref[0, 0].numel() ** 0.5), \
+        float((sums - ref_sums).abs().max())
+
+
 @pytest.mark.parametrize("mode,k,s,p", [("max", (1, 3, 3), (1, 2, 2), (0, 1, 1)), ("avg", (4, 5, 5), (1, 1, 1), (0, 0, 0)),
                                         ("max", (3, 3, 3), (1, 2, 2), (1, 1, 1)), ("avg", (2, 1, 1), (2, 1, 1), (0, 0, 0))])
 def test_pool3d(mode, k, s, p):
