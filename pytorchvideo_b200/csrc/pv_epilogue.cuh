@@ -29,7 +29,7 @@ struct EpiParams {
   CUtensorMap r_map;    // residual, same geometry
   int block_n, Co, rows, act, has_residual;
   int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip stores, 2 = skip epilogue math, 4 = producers skip loads,
-             // 32 = MMA warp skips the MMAs, 64 = narrow tiles take the direct (register -> global) epilogue
+             // 32 = MMA warp skips the MMAs, 64 = flip the direct / TMA-staged epilogue choice (see epi_direct)
   // direct (register -> global) epilogue for BLOCK_N <= 64: row r of a tile decodes into box coordinates
   // (dim 0 fastest, the order the A-operand TMA box lands in shared memory) -> element offsets
   __half* y_ptr;
@@ -221,15 +221,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* _
 // and there is no shared staging and no CTA-level barrier at all.  Called per warp; the two groups
 // of 4 epilogue warps take alternate tiles.
 // ---------------------------------------------------------------------------------------------
-template <int ACT, bool RES>
+template <int ACT, bool RES, int MAXC>     // MAXC: 16-byte chunks per row this instantiation covers (4: BLOCK_N <= 32, 8: <= 64)
 __device__ __forceinline__ void epi_direct_row(const EpiParams& E, const float* __restrict__ scale,
                                                const float* __restrict__ bias, uint32_t t_row, __half* yrow,
                                                const __half* rrow, bool row_ok, int n0, uint32_t tfull_bar,
                                                uint32_t tfull_phase, uint32_t tempty_bar, int lane) {
-  uint4 rv[8];
+  uint4 rv[MAXC];
   if (RES) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < MAXC; ++j) {
       rv[j] = make_uint4(0u, 0u, 0u, 0u);
       if (j * 8 < E.block_n && row_ok && n0 + j * 8 < E.Co) rv[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
     }
@@ -237,7 +237,7 @@ __device__ __forceinline__ void epi_direct_row(const EpiParams& E, const float* 
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 32) {
+  for (int c0 = 0; c0 < MAXC * 8; c0 += 32) {
     if (c0 < E.block_n) {
       uint32_t v[32];
       tmem_ld32(t_row + (uint32_t)c0, v);
@@ -287,8 +287,13 @@ template <int ACT>
 __device__ __forceinline__ void epi_direct_act(const EpiParams& E, const float* scale, const float* bias, uint32_t t_row,
                                                __half* yrow, const __half* rrow, bool row_ok, int n0, uint32_t tfull_bar,
                                                uint32_t tfull_phase, uint32_t tempty_bar, int lane) {
-  if (E.has_residual) epi_direct_row<ACT, true>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
-  else epi_direct_row<ACT, false>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+  if (E.block_n <= 32) {
+    if (E.has_residual) epi_direct_row<ACT, true, 4>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+    else epi_direct_row<ACT, false, 4>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+  } else {
+    if (E.has_residual) epi_direct_row<ACT, true, 8>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+    else epi_direct_row<ACT, false, 8>(E, scale, bias, t_row, yrow, rrow, row_ok, n0, tfull_bar, tfull_phase, tempty_bar, lane);
+  }
 }
 
 // o0..o3: tile origin in the merged output dims.  Waits on tfull itself.
@@ -326,7 +331,12 @@ __device__ __forceinline__ void epilogue_tile_direct(const EpiParams& E, const f
   }
 }
 
-__host__ __device__ inline bool epi_direct(const EpiParams& E) { return epi_narrow(E.block_n) && (E.dbg & 64); }   // opt-in while under test
+// Rows of <= 64 bytes (BLOCK_N <= 32) go out directly; wider rows keep the TMA-staged path (a warp-wide
+// 16-byte store then touches 32 different 128-byte lines - measured slower than the bulk store at
+// BLOCK_N = 64).  PVB200_DEBUG bit 64 flips the choice for A/B measurements.
+__host__ __device__ inline bool epi_direct(const EpiParams& E) {
+  return epi_narrow(E.block_n) && ((E.block_n <= 32) != ((E.dbg & 64) != 0));
+}
 
 }  // namespace sm100
 }  // namespace pv

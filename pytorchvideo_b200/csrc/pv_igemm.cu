@@ -54,7 +54,7 @@ struct IgemmParams {
   int tmem_cols;
   int acc_stride;   // TMEM columns between accumulator stages (block_n rounded up to 32)
   int nacc;         // number of accumulator stages
-  int nprod;        // active TMA producer warps (1..IG_PROD_WARPS)
+  int G, cpt;       // k-blocks per pipeline stage (chunk), chunks per tile
   EpiParams epi;
   signed char tap_q[IG_MAX_TAPS][4];
   unsigned char tap_map[IG_MAX_TAPS];
@@ -69,7 +69,8 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   const int stages = P.stages;
   const uint32_t a_bytes = (uint32_t)IG_BM * P.kbytes;
   const uint32_t b_bytes = (uint32_t)P.block_n * P.kbytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int G = P.G;
+  const uint32_t stage_bytes = (uint32_t)G * (a_bytes + b_bytes);   // [G x A k-block][G x B k-block]
   const int k_elems = P.kbytes >> 1;
   // epilogue staging (1024-aligned) and the barriers live after the tile ring
   const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
@@ -117,13 +118,15 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
 
   if (warp < IG_PROD_WARPS) {
     // ================================ TMA producers =========================================
-    // k-blocks can be dealt round-robin to up to IG_PROD_WARPS warps (PVB200_NPROD); measured on
-    // B200 this does not help (the pipeline is bound by L2->SM bandwidth / TMA latency, not by the
-    // issuing thread), so one producer warp is the default.
-    if (lane == 0) {
-      int stage = 0, g = 0;
+    // One producer warp: warp-uniform loop, one elected lane issues the TMA loads of a whole chunk
+    // (up to G k-blocks = 2G bulk-tensor loads on ONE mbarrier).  Measured on B200: extra producer warps
+    // do not help; what bounds narrow-N layers is the number of barrier rounds, hence the chunking.
+    if (warp == 0) {
+      int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)P.rows * P.kbytes + b_bytes;
+      const int num_kc = P.num_kc, cpt = P.cpt;
+      const bool skip_loads = (P.epi.dbg & 4) != 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % P.n_tiles;
         int mt = tile / P.n_tiles;
@@ -131,54 +134,69 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
         const int n0 = n_tile * P.block_n;
-        for (int tap = 0; tap < P.taps; ++tap) {
-          for (int kc = 0; kc < P.num_kc; ++kc, ++g) {
-            if (P.nprod == 1 || (g % P.nprod) == warp) {
-              const void* amap = &P.a_maps[P.tap_map[tap]];
-              const int c1 = o[0] + P.tap_q[tap][0], c2 = o[1] + P.tap_q[tap][1];
-              const int c3 = o[2] + P.tap_q[tap][2], c4 = o[3] + P.tap_q[tap][3];
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t a_dst = smem_base + stage * stage_bytes;
-              const uint32_t b_dst = a_dst + a_bytes;
-              if (P.epi.dbg & 4) {               // probe: pipeline skeleton without the loads
-                mbar_arrive(full_bar(stage));
-              } else {
-                mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-                tma_load_5d(a_dst, amap, full_bar(stage), kc * k_elems, c1, c2, c3, c4);
-                tma_load_2d(b_dst, &P.b_map, full_bar(stage), (tap * P.num_kc + kc) * k_elems, n0);
+        for (int ch = 0; ch < cpt; ++ch) {
+          const int kb0 = ch * G;
+          const int nsub = min(G, num_kb - kb0);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t st_base = smem_base + (uint32_t)stage * stage_bytes;
+          if (elect_one()) {
+            if (skip_loads) {               // probe: pipeline skeleton without the loads
+              mbar_arrive(full_bar(stage));
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * tx_bytes);
+              for (int j = 0; j < nsub; ++j) {
+                const int kb = kb0 + j;
+                const int tap = kb / num_kc, kc = kb - tap * num_kc;
+                const void* amap = &P.a_maps[P.tap_map[tap]];
+                tma_load_5d(st_base + (uint32_t)j * a_bytes, amap, full_bar(stage), kc * k_elems, o[0] + P.tap_q[tap][0],
+                            o[1] + P.tap_q[tap][1], o[2] + P.tap_q[tap][2], o[3] + P.tap_q[tap][3]);
+                tma_load_2d(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, full_bar(stage), kb * k_elems, n0);
               }
             }
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == IG_MMA_WARP) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
+    // The whole warp runs the loop with warp-uniform control flow and waits on the barriers; one
+    // elected lane issues the tcgen05 instructions, so their operands stay in uniform registers
+    // (inside `if (lane == 0)` every tcgen05.mma / commit became an R2UR + ELECT/BRA.U.ANY waterfall
+    // and the issuing thread cost ~800 clk per k-block - the bound of every narrow layer).
+    {
       const uint32_t idesc = make_idesc_f16(IG_BM, P.block_n);
+      const int k16 = (P.epi.dbg & 32) ? 0 : (P.kbytes >> 5);
+      const int kbytes = P.kbytes, acc_stride = P.acc_stride;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const int cpt = P.cpt;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+        for (int ch = 0; ch < cpt; ++ch) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t a_desc = make_kmajor_desc(a_addr, P.kbytes);
-          const uint64_t b_desc = make_kmajor_desc(a_addr + a_bytes, P.kbytes);
-          const int k16 = P.kbytes >> 5;
-          for (int k = 0; k < k16 && !(P.epi.dbg & 32); ++k) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in (addr>>4)
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+          const uint32_t st_base = smem_base + (uint32_t)stage * stage_bytes;
+          const int kb0 = ch * G;
+          const int nsub = min(G, num_kb - kb0);
+          if (elect_one()) {
+            for (int j = 0; j < nsub; ++j) {
+              const uint64_t a_desc = make_kmajor_desc(st_base + (uint32_t)j * a_bytes, kbytes);
+              const uint64_t b_desc = make_kmajor_desc(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, kbytes);
+              for (int k = 0; k < k16; ++k) {
+                // advance 16 elements (32 B) along K inside the swizzle row: +2 in (addr>>4)
+                umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb0 + j) | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(empty_bar(stage));                    // frees the chunk's smem when its MMAs retire
+            if (ch == cpt - 1) umma_commit(tfull_bar(acc));   // accumulator complete
           }
-          umma_commit(empty_bar(stage));            // frees the smem slot when the MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
@@ -436,7 +454,6 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
   { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
-  { const char* e = getenv("PVB200_NPROD"); P.nprod = e ? atoi(e) : 1; if (P.nprod < 1 || P.nprod > IG_PROD_WARPS || P.nprod > P.stages) P.nprod = 1; }
   {
     P.acc_stride = (P.block_n + 31) / 32 * 32;
     P.nacc = 512 / P.acc_stride;
@@ -446,13 +463,26 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
-  const int stage_bytes = (IG_BM + P.block_n) * P.kbytes;
+  // k-blocks per pipeline stage: a barrier round + commit costs the issuing thread ~500+ clk, one k-block
+  // of MMAs only k16 * N/2 clk - group k-blocks until a stage carries ~1000 clk of tensor work.
+  const int kb_bytes = (IG_BM + P.block_n) * P.kbytes;
   {
-    int st = (227 * 1024 - 2048 - EPI_SMEM_BYTES - 256) / stage_bytes;
-    if (st > 24) st = 24;
+    const int num_kb = P.taps * P.num_kc;
+    const int mma_clk = (P.kbytes >> 5) * (P.block_n < 16 ? 16 : P.block_n) / 2;
+    int G = (1000 + mma_clk - 1) / mma_clk;
+    if (G > 4) G = 4;
+    if (G > num_kb) G = num_kb;
+    { const char* e = getenv("PVB200_G"); if (e && atoi(e) >= 1 && atoi(e) <= 8) G = atoi(e) < num_kb ? atoi(e) : num_kb; }
+    const int budget = 227 * 1024 - 2048 - EPI_SMEM_BYTES - 256;
+    while (G > 1 && budget / (G * kb_bytes) < 3) --G;
+    int st = budget / (G * kb_bytes);
+    if (st > 24 / G) st = 24 / G > 2 ? 24 / G : 2;
     if (st < 2) st = 2;
+    P.G = G;
+    P.cpt = (num_kb + G - 1) / G;
     P.stages = st;
   }
+  const int stage_bytes = P.G * kb_bytes;
   const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + EPI_SMEM_BYTES +
                             8 * (2 * P.stages + 2 * 8 + 4) + 16;
 

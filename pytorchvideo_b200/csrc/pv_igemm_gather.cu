@@ -3,7 +3,7 @@
 //
 // With few input channels one filter tap is only 8..64 bytes of K, so a 64-channel TMA box per tap
 // would be mostly zero fill.  Here the GEMM K axis is the flattened (tap, ci) index and the A tile
-// (128 output positions x 64 K-elements, 128B-swizzled K-major) is assembled by 8 producer warps
+// (128 output positions x 64 K-elements, 128B-swizzled K-major) is assembled by 7 producer warps
 // with coalesced 8/16-byte global loads (im2col gather, zero fill for padding) written straight to
 // the swizzled shared-memory layout the UMMA descriptor expects; weights still arrive by TMA.
 // MMA issue, TMEM double buffering and the fused epilogue are the same as in pv_igemm.cu.
@@ -23,9 +23,9 @@ constexpr int GG_BK = 64;
 constexpr int GG_A_BYTES = GG_BM * GG_BK * 2;
 constexpr int GG_MAX_UNITS = 256;
 constexpr int GG_EPI_WARPS = EPI_WARPS;   // 8
-constexpr int GG_PROD_WARPS = 8;
+constexpr int GG_PROD_WARPS = 7;          // 16 warps in all: 4 per SM sub-partition -> 128 registers per thread
 constexpr int GG_PROD_THREADS = GG_PROD_WARPS * 32;
-constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 544
+constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 512
 constexpr int GG_DEPTH = 3;        // k-blocks of cp.async in flight per producer thread (stages > GG_DEPTH)
 
 struct GatherParams {
@@ -73,7 +73,7 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int MMA_WARP = GG_EPI_WARPS;          // warp 8
-  constexpr int PROD_WARP0 = GG_EPI_WARPS + 1;    // warps 9..16
+  constexpr int PROD_WARP0 = GG_EPI_WARPS + 1;    // warps 9..15
 
   if (warp == MMA_WARP && lane == 0) {
     prefetch_tmap(&P.b_map);
@@ -104,10 +104,10 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
 
   if (warp >= PROD_WARP0) {
     // ================================ gather producers =======================================
-    // Warp-per-k-block im2col gather.  Producer warp w owns k-blocks g = w, w+8, ... of this CTA's
+    // Warp-per-k-block im2col gather.  Producer warp w owns k-blocks g = w, w+nprod, ... of this CTA's
     // (tile, k-block) sequence and fills the whole 128 x 64 A tile of that k-block alone: lane l
     // covers rows l, l+32, l+64, l+96, each unit is a zero-filling cp.async straight into the
-    // swizzled layout.  All 8 warps are in flight on different k-blocks, so the serial issue
+    // swizzled layout.  All producer warps are in flight on different k-blocks, so the serial issue
     // latency of one thread (measured ~1000 clk per 4 copies when every warp worked on the SAME
     // k-block) no longer bounds the pipeline; a warp publishes its k-block (proxy fence + one
     // mbarrier arrive) when its own copies have landed.
@@ -167,10 +167,11 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       }
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t a_tile = smem_base + stage * stage_bytes;
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(stage), b_bytes);
         tma_load_2d(a_tile + GG_A_BYTES, &P.b_map, full_bar(stage), kb * GG_BK, n_tile * P.block_n);
       }
+      __syncwarp();
       const int u_base = kb * P.upk;
       int units_here = P.units_total - u_base;
       if (units_here > P.upk) units_here = P.upk;
@@ -213,41 +214,46 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       asm volatile("cp.async.wait_all;" ::: "memory");
       if (!(P.epi.dbg & 8)) fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (elect_one()) mbar_arrive(full_bar(stage));
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(GG_BM, P.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    // The WHOLE warp walks the (tile, k-block) sequence with warp-uniform control flow and waits on the
+    // barriers; one elected lane issues the tcgen05 instructions.  (Running the loop inside
+    // `if (lane == 0)` makes every tcgen05.mma / commit a divergent-code instruction: the compiler then
+    // moves each operand to a uniform register with R2UR inside an ELECT / BRA.U.ANY waterfall.)
+    const uint32_t idesc = make_idesc_f16(GG_BM, P.block_n);
+    const int num_kb = P.num_kb;
+    const int k16_full = (P.upk * P.gbytes) >> 5;
+    const int k16_last = (((P.units_total - (num_kb - 1) * P.upk) * P.gbytes) + 31) >> 5;   // steps that hold data
+    const bool skip_mma = (P.epi.dbg & 32) != 0;
+    const int acc_stride = P.acc_stride;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
-        for (int kb = 0; kb < P.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t a_desc = make_kmajor_desc(a_addr, 128);
-          const uint64_t b_desc = make_kmajor_desc(a_addr + GG_A_BYTES, 128);
-          int units_left = P.units_total - kb * P.upk;
-          if (units_left > P.upk) units_left = P.upk;
-          const int k16 = (units_left * P.gbytes + 31) >> 5;   // 16-element (32 B) MMA steps that hold data
-          for (int k = 0; k < k16 && !(P.epi.dbg & 32); ++k)
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+        const uint32_t a_addr = smem_base + stage * stage_bytes;
+        const uint64_t a_desc = make_kmajor_desc(a_addr, 128);
+        const uint64_t b_desc = make_kmajor_desc(a_addr + GG_A_BYTES, 128);
+        const bool last = kb == num_kb - 1;
+        const int k16 = skip_mma ? 0 : (last ? k16_last : k16_full);
+        if (elect_one()) {
+          for (int k = 0; k < k16; ++k)
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (kb == P.num_kb - 1) {
-            umma_commit(tfull_bar(acc));
-            if (P.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 64) P.trace[64 + tile / gridDim.x] = clock64();
-          }
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
+          if (last) umma_commit(tfull_bar(acc));
         }
-        if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ================================ epilogue warps ========================================
@@ -255,13 +261,14 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
     int tile_seq = 0;
     uint32_t res_phase = 0;
     const bool narrow = epi_narrow(P.block_n);
+    const bool direct = epi_direct(P.epi);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
       if (narrow && (tile_seq & 1) != (warp >> 2)) continue;      // the other group's tile
       const int acc = tile_seq % nacc;
       const uint32_t acc_phase = (uint32_t)((tile_seq / nacc) & 1);
       const int n_tile = tile % P.n_tiles;
       const int m_tile = tile / P.n_tiles;
-      if (epi_direct(P.epi)) {
+      if (direct) {
         epilogue_tile_direct(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), quarter, lane,
                              n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0, tfull_bar(acc), acc_phase, tempty_bar(acc));
         continue;
