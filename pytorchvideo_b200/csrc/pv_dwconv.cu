@@ -48,7 +48,7 @@ dwconv3d_tile_kernel(const __grid_constant__ DwParams P, const __half* __restric
   constexpr int NCOL = (WT - 1) * SW + KW;
   extern __shared__ __align__(128) uint8_t dw_smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ float se_part[64];
+  __shared__ float se_acc[256][8];     // per-thread SE partial sums (one channel group per thread, see the item loop)
   const int cc = P.cc;
   const int halo_elems = P.tt * P.hh * P.ww * cc;
   __half* xs = reinterpret_cast<__half*>(dw_smem);                       // [tt][hh][ww][cc]
@@ -68,7 +68,6 @@ dwconv3d_tile_kernel(const __grid_constant__ DwParams P, const __half* __restric
     mbar_init(bar_a, 1);
     fence_mbar_init();
   }
-  if (threadIdx.x < 64) se_part[threadIdx.x] = 0.f;
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_a, (uint32_t)halo_elems * 2u);
@@ -86,7 +85,13 @@ dwconv3d_tile_kernel(const __grid_constant__ DwParams P, const __half* __restric
   const int G = cc >> 3;
   const int wq_n = (P.bw + WT - 1) / WT;
   const int items = P.bt * P.bh * wq_n * G;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+  // The item stride is a multiple of G, so a thread keeps ONE channel group for all its items: the SE
+  // partial sums stay in registers and are combined once per CTA without shared-memory atomics.
+  const int stride = ((int)blockDim.x / G) * G;
+  float se_reg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) se_reg[i] = 0.f;
+  for (int it = threadIdx.x; it < items && (int)threadIdx.x < stride; it += stride) {
     int r = it;
     const int cg = r % G; r /= G;
     const int wq = r % wq_n; r /= wq_n;
@@ -141,14 +146,19 @@ dwconv3d_tile_kernel(const __grid_constant__ DwParams P, const __half* __restric
       }
       st8<__half>(y + (long long)n * P.y_batch_stride + (((long long)to * P.Ho + ho) * P.Wo + wo) * P.y_row_stride + c0 + c, v);
     }
-    if (se_sums) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&se_part[c + i], ssum[i]);
-    }
+    for (int i = 0; i < 8; ++i) se_reg[i] += ssum[i];
   }
   if (se_sums) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) se_acc[threadIdx.x][i] = se_reg[i];
     __syncthreads();
-    if (threadIdx.x < cc) atomicAdd(se_sums + (long long)n * P.C + c0 + threadIdx.x, se_part[threadIdx.x]);
+    if ((int)threadIdx.x < cc) {        // channel c of this chunk: threads t = (c >> 3) + k G hold its partials
+      const int cgc = (int)threadIdx.x >> 3, ci = (int)threadIdx.x & 7;
+      float tot = 0.f;
+      for (int t = cgc; t < stride; t += G) tot += se_acc[t][ci];
+      atomicAdd(se_sums + (long long)n * P.C + c0 + threadIdx.x, tot);
+    }
   }
 }
 
