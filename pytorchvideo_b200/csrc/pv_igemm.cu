@@ -134,6 +134,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
         const int n0 = n_tile * P.block_n;
+        int tap = 0, kc = 0;                  // (tap, channel chunk) of the next k-block, stepped without a divide
         for (int ch = 0; ch < cpt; ++ch) {
           const int kb0 = ch * G;
           const int nsub = min(G, num_kb - kb0);
@@ -144,17 +145,19 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
               mbar_arrive(full_bar(stage));
             } else {
               mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * tx_bytes);
+              int tp = tap, kk = kc;
               for (int j = 0; j < nsub; ++j) {
-                const int kb = kb0 + j;
-                const int tap = kb / num_kc, kc = kb - tap * num_kc;
-                const void* amap = &P.a_maps[P.tap_map[tap]];
-                tma_load_5d(st_base + (uint32_t)j * a_bytes, amap, full_bar(stage), kc * k_elems, o[0] + P.tap_q[tap][0],
-                            o[1] + P.tap_q[tap][1], o[2] + P.tap_q[tap][2], o[3] + P.tap_q[tap][3]);
-                tma_load_2d(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, full_bar(stage), kb * k_elems, n0);
+                const void* amap = &P.a_maps[P.tap_map[tp]];
+                tma_load_5d(st_base + (uint32_t)j * a_bytes, amap, full_bar(stage), kk * k_elems, o[0] + P.tap_q[tp][0],
+                            o[1] + P.tap_q[tp][1], o[2] + P.tap_q[tp][2], o[3] + P.tap_q[tp][3]);
+                tma_load_2d(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, full_bar(stage),
+                            (kb0 + j) * k_elems, n0);
+                if (++kk == num_kc) { kk = 0; ++tp; }
               }
             }
           }
           __syncwarp();
+          for (int j = 0; j < nsub; ++j) { if (++kc == num_kc) { kc = 0; ++tap; } }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
