@@ -22,6 +22,7 @@
 
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace pv {
 
@@ -112,6 +113,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+  // overlaps the tail of the previous kernel in the stream / graph; its results are only touched below.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int total_tiles = P.n_tiles * P.m_tiles;
   const int num_kb = P.taps * P.num_kc;
@@ -613,7 +618,22 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
-  conv3d_igemm_kernel<<<grid, IG_THREADS, smem_bytes, stream>>>(P, scale, bias);
+  {
+    // launched with the programmatic-stream-serialization attribute (PDL); PVB200_NO_PDL=1 falls back to a plain launch
+    static const bool use_pdl = getenv("PVB200_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(IG_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    PV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3d_igemm_kernel, P, scale, bias));
+  }
   PV_LAUNCH_OK("conv3d_igemm_kernel");
   return PV_OK;
 }

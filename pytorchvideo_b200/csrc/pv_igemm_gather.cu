@@ -13,6 +13,7 @@
 
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace pv {
 
@@ -99,6 +100,10 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+  // overlaps the tail of the previous kernel in the stream / graph; its results are only touched below.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int total_tiles = P.n_tiles * P.m_tiles;
 
@@ -434,7 +439,22 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   if (trace && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
   P.trace = trace ? trace_buf : nullptr;
   if (trace) cudaMemset(trace_buf, 0, 512 * sizeof(long long));
-  conv3d_igemm_gather_kernel<<<grid, GG_THREADS, smem_bytes, stream>>>(P, (const __half*)x, scale, bias);
+  {
+    // launched with the programmatic-stream-serialization attribute (PDL); PVB200_NO_PDL=1 falls back to a plain launch
+    static const bool use_pdl = getenv("PVB200_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GG_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    PV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3d_igemm_gather_kernel, P, (const __half*)x, scale, bias));
+  }
   if (trace) {
     long long h[512];
     cudaStreamSynchronize(stream);

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r01_bench_n2.json 2> gpurun_out/r01_bench_n2.err; echo "n2 exit $?"
+tail -1 gpurun_out/r01_bench_n2.json | cut -c1-900
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r01_bench_ref_n2.json 2> gpurun_out/r01_bench_ref_n2.err; echo "ref n2 exit $?"
+tail -1 gpurun_out/r01_bench_ref_n2.json | cut -c1-600
