@@ -51,12 +51,43 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    NVML in a thread every ~5 ms (the timed region is ~0.1 s, too short for `nvidia-smi -lms`);
+    falls back to an `nvidia-smi -lms 100` child process if pynvml is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.bits, self.mx, self.stop_flag, self.thr = [], 0, None, False, None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thr = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.thr = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -74,6 +105,13 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.thr is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=2)
+            sm = sorted(self.samples)
+            med = sm[len(sm) * 3 // 4] if sm else None     # upper-quartile ~ clocks under load (idle samples drag the median down)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+            return {"sm_mhz": med, "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -98,7 +136,7 @@ class ClockSampler:
         sm.sort()
         # median of the upper half ~ clocks under load (idle samples before/after drag the median down)
         med = sm[len(sm) * 3 // 4] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def build_model_and_inputs(workload, batch_override=None):
@@ -287,7 +325,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.02)
     launches_before = _lib.launch_count()
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
