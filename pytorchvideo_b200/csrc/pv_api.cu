@@ -28,7 +28,8 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
                          const float* bias, const void* residual, void* y, cudaStream_t s);
 // narrow inputs (C_in < 64, weights packed with the un-padded per-tap K extent) take the gather-fed
 // variant, everything else the TMA-fed one
-static bool wants_gather(const pv_conv3d_desc* d) { return d->Ci < 64 && d->ci_pad64 == d->Ci; }
+bool conv3d_tma_narrow(const pv_conv3d_desc* d);   // pv_igemm.cu: C_in = 16 / 32 go through TMA boxes of 32 / 64 bytes
+static bool wants_gather(const pv_conv3d_desc* d) { return d->Ci < 64 && d->ci_pad64 == d->Ci && !conv3d_tma_narrow(d); }
 
 }  // namespace pv
 

@@ -289,6 +289,14 @@ struct IgemmPlan {
 // x_w_pad physical zero pixels on the left (and enough on the right), written by the layout
 // conversion, which implements the W padding; H/T padding is TMA out-of-bounds fill as usual.
 static bool window_mode(const pv_conv3d_desc* d) { return d->x_w_pad > 0 && d->Ci <= 8; }
+// Narrow TMA mode: C_in = 16 / 32 with the weights packed at the un-padded per-tap K extent.  One tap is a
+// 32 / 64-byte box row (SWIZZLE_32B / 64B), one k-block per tap, several taps per pipeline stage - fewer
+// barrier rounds and no SM instructions for the A operand, which beats the cp.async gather for these
+// widths (the gather kernel keeps C_in = 4 / 8 / 24 / 40 / 48 / 56).
+bool conv3d_tma_narrow(const pv_conv3d_desc* d) {
+  static const bool off = getenv("PVB200_GATHER_ALL") != nullptr;
+  return !off && !window_mode(d) && (d->Ci == 16 || d->Ci == 32) && d->ci_pad64 == d->Ci;
+}
 // TMA needs a 16-byte aligned base: if the first tap of output column 0 sits at an odd pixel of a
 // 4-channel row, the window starts one pixel earlier (the packed weights carry a zero pixel there).
 static int window_lead(const pv_conv3d_desc* d) { return (((d->x_w_pad - d->pw) * d->Ci * 2) % 16) ? 1 : 0; }
@@ -365,7 +373,7 @@ int conv3d_tcgen05_supported(const pv_conv3d_desc* d, char* why, size_t why_len)
     NOPE("row strides must be multiples of 8 elements (16 B)");
   if (d->kt * d->kh * d->kw > IG_MAX_TAPS) NOPE("too many taps");
   if (d->st * d->sh * d->sw > IG_MAX_MAPS) NOPE("stride product > %d", IG_MAX_MAPS);
-  if (d->ci_pad64 < d->Ci || d->ci_pad64 % 64) NOPE("ci_pad64 must be a multiple of 64 >= Ci");
+  if (!conv3d_tma_narrow(d) && (d->ci_pad64 < d->Ci || d->ci_pad64 % 64)) NOPE("ci_pad64 must be a multiple of 64 >= Ci");
   const long long M = (long long)d->N * d->To * d->Ho * d->Wo;
   if (M >= (1ll << 31)) NOPE("too many output positions");
   for (int off : {d->pt, d->ph, d->pw, d->dt * (d->kt - 1), d->dh * (d->kh - 1), d->dw * (d->kw - 1)})
@@ -451,11 +459,12 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     P.n_tiles = (int)cdiv(d->Co, bn);
   }
   const bool wmode = window_mode(d);
-  const int win = wmode ? window_elems(d) : 64;
+  const bool narrow = conv3d_tma_narrow(d);
+  const int win = wmode ? window_elems(d) : (narrow ? d->Ci : 64);
   P.kbytes = 2 * win;
   P.Co = d->Co;
   P.taps = wmode ? d->kt * d->kh : d->kt * d->kh * d->kw;
-  P.num_kc = wmode ? 1 : d->ci_pad64 / 64;
+  P.num_kc = (wmode || narrow) ? 1 : d->ci_pad64 / 64;
   P.epi.block_n = P.block_n;
   P.epi.Co = d->Co;
   P.epi.rows = P.rows;
@@ -557,8 +566,9 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   }
   {
     const long long krow = (long long)P.taps * d->ci_pad64;     // window mode: ci_pad64 == window length
+    const long long kpitch = narrow ? (krow + 63) / 64 * 64 : krow;   // narrow mode shares the gather packing (row end padded to 64)
     cuuint64_t gdim[2] = {(cuuint64_t)krow, (cuuint64_t)d->Co};
-    cuuint64_t gstr[1] = {(cuuint64_t)krow * 2};
+    cuuint64_t gstr[1] = {(cuuint64_t)kpitch * 2};
     cuuint32_t box[2] = {(cuuint32_t)win, (cuuint32_t)P.block_n}, estr[2] = {1, 1};
     const CUtensorMapSwizzle swz = P.kbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                    : (P.kbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -48,6 +48,9 @@ CONV_CASES = [
     (2, 56, 4, 9, 9, 56, (3, 3, 3), (1, 1, 1), (1, 1, 1), 56, "swish", False),      # depthwise
     (2, 24, 6, 9, 9, 24, (5, 1, 1), (1, 1, 1), (2, 0, 0), 24, "relu", False),       # depthwise temporal
     (1, 16, 4, 9, 9, 16, (3, 3, 3), (2, 2, 2), (1, 1, 1), 16, None, False),         # depthwise strided (CSN)
+    (2, 32, 6, 10, 10, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, "relu", False),       # Fast-pathway conv_a: narrow TMA mode (64 B rows)
+    (1, 16, 4, 9, 9, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "relu", True),         # Fast-pathway conv_b + residual: narrow TMA (32 B rows)
+    (2, 32, 2, 9, 9, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, None, False),         # strided shortcut from a 32-wide tensor
 ]
 
 
