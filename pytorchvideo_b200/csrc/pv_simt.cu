@@ -601,6 +601,69 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int
   }
 }
 
+// Row-in-registers LayerNorm for C <= 768: a row is read ONCE (8 channels per 16-byte load, up to NCH
+// loads per lane), `lpr` lanes cooperate on a row (power of two >= ceil(C/8), so a 96-wide MViT row
+// uses 16 lanes and a warp normalises two rows), mean and centred variance are reduced with sub-warp
+// shuffles.  (The generic kernel below re-reads the row three times and keeps 12 of 32 lanes busy at C=96.)
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_reg_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int groups, int C,
+                     long long x_row_stride, long long y_row_stride, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, int lpr_log2) {
+  const int lane = threadIdx.x & 31;
+  const int lpr = 1 << lpr_log2;
+  const int sub = lane >> lpr_log2, sl = lane & (lpr - 1);
+  const long long total = rows * groups;
+  long long rg = (((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) << (5 - lpr_log2)) + sub;
+  const bool ok = rg < total;
+  if (!ok) rg = 0;
+  const long long row = rg / groups;
+  const int grp = (int)(rg - row * groups);
+  const T* xr = x + row * x_row_stride + (long long)grp * C;
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (sl + i * lpr) * 8;
+    if (ok && c < C) {
+      ld8<T>(xr + c, v[i]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[i][e];
+  }
+  for (int o = lpr >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (sl + i * lpr) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = v[i][e] - mean; q = fmaf(dlt, dlt, q); }
+    }
+  }
+  for (int o = lpr >> 1; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  T* yr = y + row * y_row_stride + (long long)grp * C;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (sl + i * lpr) * 8;
+    if (ok && c < C) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      float o8[8];
+      o8[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o8[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+      o8[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o8[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+      o8[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o8[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+      o8[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o8[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+      st8<T>(yr + c, o8);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 temporal_tap_sum_kernel(const T* __restrict__ yk, T* __restrict__ y, int Ti, int To, long long hw, int Co, int kt,
@@ -995,6 +1058,21 @@ extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, i
   PV_CHECK_ARG(x_row_stride >= (long long)groups * C && y_row_stride >= (long long)groups * C, "row stride < groups*C");
   if (rows == 0) return PV_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  const int chunks = (C + 7) / 8;
+  int lpr_log2 = 2;
+  while ((1 << lpr_log2) < chunks && lpr_log2 < 5) ++lpr_log2;
+  const int nch = (chunks + (1 << lpr_log2) - 1) >> lpr_log2;
+  const bool aligned16 = (((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  if (nch <= 3 && aligned16 && (dtype == PV_F16 || dtype == PV_F32)) {
+    const long long per_block = 8ll << (5 - lpr_log2);     // rows per 256-thread block
+    dim3 grid((unsigned)cdiv(rows * groups, per_block)), block(256);
+#define PV_LN(TT, N_) layernorm_reg_kernel<TT, N_><<<grid, block, 0, s>>>((const TT*)x, (TT*)y, rows, groups, C, x_row_stride, y_row_stride, gamma, beta, eps, lpr_log2)
+    if (dtype == PV_F16) { if (nch == 1) PV_LN(__half, 1); else if (nch == 2) PV_LN(__half, 2); else PV_LN(__half, 3); }
+    else { if (nch == 1) PV_LN(float, 1); else if (nch == 2) PV_LN(float, 2); else PV_LN(float, 3); }
+#undef PV_LN
+    PV_LAUNCH_OK("layernorm_reg_kernel");
+    return PV_OK;
+  }
   dim3 grid((unsigned)cdiv(rows * groups, 8)), block(256);
   if (dtype == PV_F16)
     layernorm_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, rows, groups, C, x_row_stride,
