@@ -501,16 +501,27 @@ scale_act_kernel(const T* __restrict__ x, T* __restrict__ y, long long x_row_str
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int G = C >> 3;
-  const int c = (int)(e % G) * 8;
-  long long m = e / G;
-  long long n = m / npos;
+  int c;
+  long long m, n;
+  if (total < 0x7fffffffll) {        // 32-bit index math (64-bit divides cost more than the memory traffic here)
+    const unsigned eu = (unsigned)e, mu = eu / (unsigned)G;
+    c = (int)(eu - mu * (unsigned)G) * 8;
+    m = mu;
+    n = mu / (unsigned)npos;
+  } else {
+    c = (int)(e % G) * 8;
+    m = e / G;
+    n = m / npos;
+  }
   float v[8];
   ld8<T>(x + m * x_row_stride + c, v);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float g = gate ? __ldg(gate + n * C + c + i) : 1.f;
-    v[i] = apply_act(v[i] * g, act);
+  if (gate) {
+    const float* gp = gate + n * C + c;     // C % 8 == 0 and cudaMalloc alignment: 32-byte aligned
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp)), g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], act);
   st8<T>(y + m * y_row_stride + c, v);
 }
 

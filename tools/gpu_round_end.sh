@@ -4,6 +4,7 @@
 mkdir -p gpurun_out
 R=r01
 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/${R}_pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/${R}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/${R}_smoke.log
 python tools/bench_transform.py > gpurun_out/${R}_transform.json 2> gpurun_out/${R}_transform.err; echo "transform exit $?"; cat gpurun_out/${R}_transform.json
 python bench.py --steps 30 --warmup 5 --dump-kernels gpurun_out/${R}_kernels_slowfast.json > gpurun_out/${R}_bench_slowfast.json 2> gpurun_out/${R}_bench_slowfast.err; echo "bench exit $?"; cut -c1-1200 gpurun_out/${R}_bench_slowfast.json
 for wl in x3d_m csn_r101 mvit_base_16x4 r2plus1d_r50 x3d_xs slow_r50; do
