@@ -179,22 +179,27 @@ def pick_cpu_threads(model, T, H, W, is_sf):
 
 
 def cpu_baseline(model, T, H, W, is_sf, budget_s=20.0):
-    """Oracle port of the reference forward on the host cores, bounded sample (1 warm-up + timed)."""
+    """Oracle port of the reference forward on the host cores: bounded sample, the faster of one clip per
+    forward and a small batch per forward (on a many-core host oneDNN's conv3d is fastest at batch 1)."""
     from oracle.interp import oracle_forward
     cores, one = pick_cpu_threads(model, T, H, W, is_sf)
-    b = 1
-    inp = make_inputs(b, T, H, W, is_sf, seed=7)
-    b = max(1, min(8, int(budget_s / max(one, 1e-3) / 2)))
-    inp = make_inputs(b, T, H, W, is_sf, seed=7)
-    best = None
-    reps = 2 if one * b * 2 < budget_s else 1
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        oracle_forward(model, inp)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": b / best, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": "%d clip(s) per forward, best of %d, torch fp32 CPU, %d threads" % (b, reps, cores)}
+    results = []
+    for b in (1, max(1, min(8, int(budget_s / max(one, 1e-3) / 4)))):
+        if results and b == results[0][1]:
+            continue
+        inp = make_inputs(b, T, H, W, is_sf, seed=7)
+        reps = 3 if one * b * 3 < budget_s / 2 else 1
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            oracle_forward(model, inp)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        results.append((b / best, b, reps))
+    v, b, reps = max(results)
+    return {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": "%d clip(s) per forward, best of %d, torch fp32 CPU, %d threads (tried batch sizes %s)" % (
+                b, reps, cores, [r[1] for r in results])}
 
 
 def run_reference(args, rank, world):
