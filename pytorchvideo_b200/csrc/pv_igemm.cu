@@ -29,14 +29,12 @@ namespace pv {
 using namespace sm100;
 
 constexpr int IG_BM = 128;        // UMMA M
-constexpr int IG_BK = 64;         // K per pipeline stage (one 128B swizzle row of f16)
 constexpr int IG_MAX_TAPS = 64;
 constexpr int IG_MAX_MAPS = 8;
 constexpr int IG_PROD_WARPS = 4;   // TMA producer warps (one elected lane each, k-blocks round-robin)
 constexpr int IG_MMA_WARP = IG_PROD_WARPS;
 constexpr int IG_EPI_WARP0 = IG_PROD_WARPS + 1;
 constexpr int IG_THREADS = (IG_PROD_WARPS + 1 + EPI_WARPS) * 32;   // 416
-constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;   // 16 KiB
 
 struct IgemmParams {
   CUtensorMap a_maps[IG_MAX_MAPS];

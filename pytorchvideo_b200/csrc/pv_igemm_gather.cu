@@ -25,9 +25,7 @@ constexpr int GG_A_BYTES = GG_BM * GG_BK * 2;
 constexpr int GG_MAX_UNITS = 256;
 constexpr int GG_EPI_WARPS = EPI_WARPS;   // 8
 constexpr int GG_PROD_WARPS = 7;          // 16 warps in all: 4 per SM sub-partition -> 128 registers per thread
-constexpr int GG_PROD_THREADS = GG_PROD_WARPS * 32;
 constexpr int GG_THREADS = (GG_EPI_WARPS + 1 + GG_PROD_WARPS) * 32;   // 512
-constexpr int GG_DEPTH = 3;        // k-blocks of cp.async in flight per producer thread (stages > GG_DEPTH)
 
 struct GatherParams {
   CUtensorMap b_map;
@@ -43,7 +41,6 @@ struct GatherParams {
   int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, acc_stride, nacc;
   int nprod;   // active producer warps; stages is a multiple of nprod so every smem slot has ONE owner warp
   EpiParams epi;
-  long long* trace;   // debug: per-tile timestamps of CTA 0 (PVB200_TRACE=1)
   int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
   unsigned int unit_d[GG_MAX_UNITS];  // packed (dt | dh<<8 | dw<<16) tap displacement (dilation applied)
 };
@@ -280,11 +277,9 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tile_seq < 64) P.trace[128 + tile_seq] = clock64();
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                     res_bar, res_phase, warp, quarter, lane, n_tile * P.block_n, m_tile * GG_BM, 0, 0, 0,
                     tempty_bar(acc), tile_seq);
-      if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tile_seq < 64) P.trace[192 + tile_seq] = clock64();
     }
     if ((warp & 3) == 0 && lane == 0) tma_store_wait_all();
   }
@@ -434,11 +429,6 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
-  static long long* trace_buf = nullptr;
-  const bool trace = getenv("PVB200_TRACE") != nullptr;
-  if (trace && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
-  P.trace = trace ? trace_buf : nullptr;
-  if (trace) cudaMemset(trace_buf, 0, 512 * sizeof(long long));
   {
     // launched with the programmatic-stream-serialization attribute (PDL); PVB200_NO_PDL=1 falls back to a plain launch
     static const bool use_pdl = getenv("PVB200_NO_PDL") == nullptr;
@@ -454,18 +444,6 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
     PV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3d_igemm_gather_kernel, P, (const __half*)x, scale, bias));
-  }
-  if (trace) {
-    long long h[512];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "TRACE tiles=%d kb=%d block_n=%d stages=%d nacc=%d\n", P.m_tiles * P.n_tiles, P.num_kb, P.block_n, P.stages, P.nacc);
-    for (int i = 0; i < 16; ++i)
-      fprintf(stderr, "  kblock %2d: loop_top %8lld  after_empty_wait %8lld  after_issue %8lld  after_waitgroup_arrive %8lld\n", i,
-              h[256 + i * 4] - h[0], h[256 + i * 4 + 1] - h[0], h[256 + i * 4 + 2] - h[0], h[256 + i * 4 + 3] - h[0]);
-    for (int i = 0; i < 6; ++i)
-      fprintf(stderr, "  tile %2d: prod_start %8lld  mma_commit %8lld  epi_start %8lld  epi_end %8lld\n", i, h[i] - h[0],
-              h[64 + i] - h[0], h[128 + i] - h[0], h[192 + i] - h[0]);
   }
   PV_LAUNCH_OK("conv3d_igemm_gather_kernel");
   return PV_OK;
