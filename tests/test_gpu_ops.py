@@ -185,3 +185,36 @@ def test_attention_f16_tensor_core(Nq, Nk, resid):
     got = ops.attention(q.to(_dev()), k.to(_dev()), v.to(_dev()), scale, resid, "f16").cpu()
     err = (got - ref).abs()
     assert float(err.max()) <= 4e-3 * max(1.0, float(ref.abs().max())), float(err.max())
+
+
+@pytest.mark.parametrize("shape", [
+    (8, 256, 8, 14, 14, 256, (1, 3, 3), (0, 1, 1)),      # SlowFast res4 conv_b at bench size (TMA-fed, N = 256)
+    (8, 32, 32, 56, 56, 8, (3, 1, 1), (1, 0, 0)),        # Fast pathway res2 conv_a at bench size (narrow TMA mode)
+    (8, 8, 32, 56, 56, 8, (1, 3, 3), (0, 1, 1)),         # Fast pathway res2 conv_b at bench size (gather-fed)
+])
+def test_full_size_conv_is_exactly_homogeneous(shape):
+    """Full-size layers are too big for the CPU oracle inside a test; a convolution without bias is
+    homogeneous, and scaling by a power of two is exact in f16/fp32 (outside the subnormal range), so
+    conv(2x) == 2 conv(x) BIT FOR BIT
+    (any dropped / duplicated tap, mis-addressed tile edge or stale shared memory breaks it); plus a
+    spot check of 64 output positions against the fp32 reference."""
+    from pytorchvideo_b200 import ops
+    N, Ci, T, H, W, Co, k, p = shape
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = (torch.randn(N, Ci, T, H, W, generator=g) * 0.5).half().float()
+    w = (torch.randn(Co, Ci, *k, generator=g) * (1.0 / (Ci * np.prod(k))) ** 0.5).half().float()
+    y1, _ = ops.conv3d_bn_act(x.to(_dev()), w, None, None, (1, 1, 1), p, (1, 1, 1), 1, None, None, "f16", "tcgen05")
+    y2, _ = ops.conv3d_bn_act((2 * x).to(_dev()), w, None, None, (1, 1, 1), p, (1, 1, 1), 1, None, None, "f16", "tcgen05")
+    big = y1.abs() > 2.0 ** -12          # below that an f16 result may be subnormal, where doubling is not exact
+    assert torch.equal(y2[big], 2 * y1[big])
+    assert torch.allclose(y2, 2 * y1, rtol=0, atol=2.0 ** -22)
+    y1 = y1.cpu()
+    idx = torch.randint(0, N * T * H * W, (64,), generator=g)
+    for j in idx.tolist():
+        n, r = divmod(j, T * H * W)
+        t, r = divmod(r, H * W)
+        h, ww = divmod(r, W)
+        xp = F.pad(x[n], (p[2], p[2], p[1], p[1], p[0], p[0]))
+        patch = xp[:, t:t + k[0], h:h + k[1], ww:ww + k[2]]
+        ref = (w * patch.unsqueeze(0)).sum(dim=(1, 2, 3, 4))
+        assert torch.allclose(y1[n, :, t, h, ww], ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) + 1e-4)
