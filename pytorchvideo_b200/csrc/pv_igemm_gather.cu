@@ -40,6 +40,8 @@ struct GatherParams {
   long long M;
   int m_tiles, n_tiles, block_n, Co, stages, tmem_cols, acc_stride, nacc;
   int nprod;   // active producer warps; stages is a multiple of nprod so every smem slot has ONE owner warp
+  int depth;   // k-blocks of cp.async a producer warp keeps in flight: 2 when it owns >= 2 slots, else 1
+  int epi_bytes;   // shared staging of the TMA-store epilogue (0 when the direct epilogue is used)
   EpiParams epi;
   int unit_off[GG_MAX_UNITS];        // element offset of the unit relative to the row's (t0,h0,w0) corner
   unsigned int unit_d[GG_MAX_UNITS];  // packed (dt | dh<<8 | dw<<16) tap displacement (dilation applied)
@@ -56,7 +58,7 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
   const uint32_t stage_bytes = GG_A_BYTES + b_bytes;
   const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
   const uint32_t staging = smem_base + staging_off;
-  const uint32_t bar_base = staging + EPI_SMEM_BYTES;
+  const uint32_t bar_base = staging + (uint32_t)P.epi_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
@@ -126,6 +128,11 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
     // Slot ownership: stages % nprod == 0, so slot s is only ever filled by warp s % nprod, in order;
     // a parity wait can then never alias a completion two phases back (it could with free-running
     // warps sharing slots).
+    // ncu source view: the producers wait on their own cp.async data and on the empty barrier about equally.
+    // Optional depth 2 (PVB200_GATHER_DEPTH2): with >= 2 slots per warp a k-block is published one iteration
+    // later (cp.async groups), i.e. two k-blocks of copies in flight per warp - measured no faster, off by default.
+    const bool deep = P.depth >= 2;
+    int pending = -1;                // stage whose copies were issued last iteration and are not yet published
     for (int g = wprod; wprod < P.nprod && g < total_g; g += P.nprod) {
       const int tile_seq = g / P.num_kb;
       const int kb = g - tile_seq * P.num_kb;
@@ -213,10 +220,28 @@ conv3d_igemm_gather_kernel(const __grid_constant__ GatherParams P, const __half*
           }
         }
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      if (!(P.epi.dbg & 8)) fence_proxy_async_smem();
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (deep) {
+        if (pending >= 0) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");     // everything but the group just committed has landed
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) mbar_arrive(full_bar(pending));
+          __syncwarp();
+        }
+        pending = stage;
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(full_bar(stage));
+      }
+    }
+    if (pending >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
       __syncwarp();
-      if (elect_one()) mbar_arrive(full_bar(stage));
+      if (elect_one()) mbar_arrive(full_bar(pending));
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ============================================
@@ -378,21 +403,26 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
     while (p2 < cols) p2 <<= 1;
     P.tmem_cols = p2;
   }
-  const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
-  {
-    int st = (227 * 1024 - 2048 - 2048 /*static tables*/ - EPI_SMEM_BYTES - 512) / stage_bytes;
-    if (st > 16) st = 16;
-    if (st < 2) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
-    P.nprod = st < GG_PROD_WARPS ? st : GG_PROD_WARPS;
-    P.stages = (st / P.nprod) * P.nprod;
-  }
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + EPI_SMEM_BYTES + 8 * (2 * P.stages + 2 * 8 + 4) + 16;
   P.epi.block_n = P.block_n;
   P.epi.Co = d->Co;
   P.epi.rows = GG_BM;
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
   { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
+  P.epi_bytes = epi_direct(P.epi) ? 0 : EPI_SMEM_BYTES;     // the direct epilogue needs no staging: more stages
+  const int stage_bytes = GG_A_BYTES + P.block_n * GG_BK * 2;
+  {
+    int st = (227 * 1024 - 2048 - 2048 /*static tables*/ - P.epi_bytes - 512) / stage_bytes;
+    if (st > 16) st = 16;
+    if (st < 2) { set_error("gather: not enough smem stages"); return PV_ERR_UNSUPPORTED; }
+    static const bool shallow = getenv("PVB200_GATHER_DEPTH2") == nullptr;   // measured: depth 2 is not faster (SlowFast 3.45 vs 3.42 ms), opt-in only
+    // prefer two slots per producer warp (two k-blocks of copies in flight) over more warps with one slot
+    P.nprod = st < GG_PROD_WARPS ? st : GG_PROD_WARPS;
+    if (!shallow && st >= 8 && st / 2 < P.nprod) P.nprod = st / 2;
+    P.stages = (st / P.nprod) * P.nprod;
+    P.depth = (!shallow && P.stages >= 2 * P.nprod) ? 2 : 1;
+  }
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 + P.epi_bytes + 8 * (2 * P.stages + 2 * 8 + 4) + 16;
   P.epi.y_ptr = (__half*)y;
   P.epi.r_ptr = (const __half*)residual;
   for (int m = 0; m < 4; ++m) { P.epi.O[m] = 1; P.epi.box[m] = 1; P.epi.y_str[m] = 0; P.epi.r_str[m] = 0; }
