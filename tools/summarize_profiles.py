@@ -155,8 +155,9 @@ def full_summary():
         for k in ta:
             out.append("| %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %s | %s |" % (k["name"].replace("pv::", ""), k["dur"], k["rd"], k["wr"], k["sm"], k["l2"], k["dram"], k["grid"], k["regs"]))
     out += ["", "Reading (details and the probe measurements behind it in DESIGN.md section 9):",
-            "* deep-K, wide-N layers (res4) keep the tensor pipe ~45-50 % active on 98 of 148 SMs (M = 12544 rows = 98 tiles); with BLOCK_N = 256 only three 48 KiB stages fit, i.e. ~144 KiB of loads in flight per SM against a ~190 KiB bandwidth-latency product - the fix is cta_group::2 / multicast (half the B bytes per CTA), not a faster issue loop;",
-            "* narrow-N layers are bound by the issue/handshake cost of the MMA warp (~400-800 clk per barrier round, tools/probe/umma_issue.cu) - several k-blocks per pipeline stage took the fast stem from 559 to ~300 us, the gather-fed fast-pathway layers are still ~50 us each;",
+            "* deep-K, wide-N layers (res4) keep the tensor pipe ~40-45 % active on 98 of 148 SMs (M = 12544 rows = 98 tiles); the execution counters of the same capture (`profiles/r01_source_counters.md`) show the producer never waiting for a free slot and the MMA warp hardly waiting for data: the single TMA-issuing warp paces these layers (~1460 clk per k-block vs 512 clk of MMAs) - round 2: split A/B issue over two warps, then cta_group::2 / multicast;",
+            "* narrow-N layers are bound by the issue/handshake cost of the warp-specialised ring (~400-800 clk per barrier round, tools/probe/umma_issue.cu) - several k-blocks per pipeline stage took the fast stem from 559 to ~290 us, the gather-fed fast-pathway layers are still ~50 us each (a latency ring, ~1 us per 128-row tile);",
+            "* res2 conv_c (+residual) is epilogue-bound (the MMA warp waits for a free accumulator 68x per tile): residual prefetch / double staging is the fix;",
             "* DRAM traffic is at or below the algorithmic bytes everywhere (activations are L2-resident across consecutive layers); no wasted re-reads."]
     open(os.path.join(P, "%s_ncu_full_summary.md" % R), "w").write("\n".join(out) + "\n")
 
