@@ -56,6 +56,32 @@ def test_tcgen05_support_predicate_is_host_only():
     assert lib.pv_conv3d_tcgen05_supported(C.byref(d)) == 0
 
 
+def _desc(ci, co, k, pad, ci_pad64, T=8, H=14, W=14, xrs=None):
+    d = L.Conv3dDesc()
+    d.dtype, d.N, d.Ti, d.Hi, d.Wi, d.Ci = L.PV_F16, 2, T, H, W, ci
+    d.kt, d.kh, d.kw = k
+    d.pt, d.ph, d.pw = pad
+    d.st = d.sh = d.sw = d.dt = d.dh = d.dw = 1
+    d.To, d.Ho, d.Wo, d.Co = T + 2 * pad[0] - k[0] + 1, H + 2 * pad[1] - k[1] + 1, W + 2 * pad[2] - k[2] + 1, co
+    d.groups, d.x_row_stride, d.y_row_stride, d.ci_pad64 = 1, xrs or ci, co, ci_pad64
+    return d
+
+
+def test_narrow_input_dispatch_is_decided_on_the_host():
+    """C_in < 64 with the weights packed at the un-padded per-tap extent: 16 / 32 go to the narrow TMA mode,
+    the other widths to the gather-fed kernel; both predicates are pure host code (no GPU here)."""
+    lib = L.load()
+    for ci, k, pad in [(32, (3, 1, 1), (1, 0, 0)), (16, (1, 3, 3), (0, 1, 1)), (8, (1, 3, 3), (0, 1, 1)),
+                       (24, (1, 1, 1), (0, 0, 0)), (56, (1, 1, 1), (0, 0, 0)), (4, (1, 7, 7), (0, 3, 3))]:
+        assert lib.pv_conv3d_tcgen05_supported(C.byref(_desc(ci, 16, k, pad, ci))) == 1, (ci, k)
+    # 5x7x7 over 8 channels: 245 taps > 64 validity bits of the gather kernel and not a narrow-TMA width
+    assert lib.pv_conv3d_tcgen05_supported(C.byref(_desc(8, 16, (5, 7, 7), (2, 3, 3), 8))) == 0
+    # a channel slice whose row stride is not a multiple of 16 bytes cannot be a TMA / 16-byte cp.async source
+    assert lib.pv_conv3d_tcgen05_supported(C.byref(_desc(32, 16, (1, 1, 1), (0, 0, 0), 32, xrs=36))) == 0
+    # 12 channels is neither 4 nor a multiple of 8
+    assert lib.pv_conv3d_tcgen05_supported(C.byref(_desc(12, 16, (1, 1, 1), (0, 0, 0), 12))) == 0
+
+
 def test_lowering_slowfast_dry_run():
     m = PH.slowfast_r50().eval()
     clip = torch.zeros(2, 3, 32, 224, 224)
