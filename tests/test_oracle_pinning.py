@@ -97,7 +97,8 @@ def test_normalize_zero_mean_unit_std_property():
 
 
 # ---- models ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["x3d_xs", "slow_r50", "r2plus1d_r50", "mvit_base_8x112"])
+@pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50",
+                                  "mvit_base_8x112", "mvit_base_16x4"])
 def test_oracle_reproduces_reference_model_goldens(case):
     g = _gold("model_%s.pt" % case)
     hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
