@@ -92,4 +92,10 @@ MODEL_CASES = {
     "mvit_base_16x4": ("mvit_base_16x4", {}, 1, 16, 224, 224, False),
     # same architecture on a 8x112x112 clip (785 tokens): cheap enough for the f32 CUDA-core parity mode
     "mvit_base_8x112": ("mvit_base_16x4", {"spatial_size": 112, "temporal_size": 8}, 2, 8, 112, 112, False),
+    # further hub entries of the same families: goldens pin the oracle / module trees (CPU); not in the GPU lists yet
+    "slowfast_r101": ("slowfast_r101", {}, 1, 32, 224, 224, True),
+    "c2d_r50": ("c2d_r50", {}, 1, 8, 224, 224, False),
+    "x3d_s": ("x3d_s", {}, 1, 13, 160, 160, False),
+    "x3d_l": ("x3d_l", {}, 1, 16, 312, 312, False),
+    "mvit_base_32x3": ("mvit_base_32x3", {}, 1, 32, 224, 224, False),
 }

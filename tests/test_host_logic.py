@@ -96,6 +96,23 @@ def test_lowering_slowfast_dry_run():
     assert "blocks.6.output_pool" in names
 
 
+@pytest.mark.parametrize("case", sorted(TS.MODEL_CASES))
+def test_every_model_case_lowers_on_the_host(case):
+    """Host-side dry run (no GPU): every hub entry that has a golden lowers to a static plan with the right
+    output shape, no CUDA-core dense convolution left in f16 mode except a 3-channel stem the window mode
+    cannot take, and a depthwise op for every depthwise conv of the tree."""
+    hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
+    m = getattr(PH, hub)(**kw).eval()
+    clip = torch.zeros(B, 3, T, H, W)
+    plan, out_shape = lower_only(m, TS.slowfast_inputs(clip) if is_sf else clip)
+    assert out_shape == (B, 400)
+    n_dw = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.Conv3d) and mod.groups > 1)
+    if "mvit" not in case:          # MViT shares one pooling conv across heads: counted per use, not per module
+        assert plan.stats["depthwise"] == n_dw
+    assert plan.stats["direct"] <= 1
+    assert plan.stats["tcgen05"] > 0
+
+
 def test_lowering_f32_mode_uses_no_tensor_core_path():
     m = PH.x3d_xs().eval()
     plan, out_shape = lower_only(m, torch.zeros(1, 3, 4, 160, 160), dtype="f32")

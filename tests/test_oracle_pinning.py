@@ -98,7 +98,8 @@ def test_normalize_zero_mean_unit_std_property():
 
 # ---- models ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50",
-                                  "mvit_base_8x112", "mvit_base_16x4"])
+                                  "mvit_base_8x112", "mvit_base_16x4", "slowfast_r101", "c2d_r50", "x3d_s", "x3d_l",
+                                  "mvit_base_32x3"])
 def test_oracle_reproduces_reference_model_goldens(case):
     g = _gold("model_%s.pt" % case)
     hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
