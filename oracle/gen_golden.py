@@ -35,22 +35,24 @@ def gen_models(only=None):
         if only and case != only:
             continue
         t0 = time.time()
+        grid = TS.CASE_OPTS.get(case, {}).get("f16_grid", False)
         mine = getattr(PH, hub)(**kw)
-        TS.randomize_model(mine, seed=1234)
+        TS.randomize_model(mine, seed=1234, f16_weights=grid)
         ref = getattr(RH, hub)(pretrained=False, **kw)
         ref.load_state_dict(mine.state_dict(), strict=True)
         ref.eval()
-        clip = TS.synthetic_clip(B, T, H, W, seed=42)
+        clip = TS.synthetic_clip(B, T, H, W, seed=42, f16_values=grid)
         with torch.no_grad():
             inp = TS.slowfast_inputs(clip) if is_sf else clip
             out_ref = ref(list(inp) if is_sf else inp)          # list() - the reference mutates it
             inp = TS.slowfast_inputs(clip) if is_sf else clip
-            out_orc_on_ref = oracle_forward(ref, inp)
             out_orc_on_mine = oracle_forward(mine, inp)
+            # (the big-batch cases pin the oracle on the product tree only: one oracle pass instead of two)
+            out_orc_on_ref = oracle_forward(ref, inp) if B * T * H * W <= 4 * 32 * 224 * 224 else out_orc_on_mine
         assert torch.equal(out_ref, out_orc_on_ref), "oracle != reference on reference modules (%s)" % case
         assert torch.equal(out_ref, out_orc_on_mine), "oracle != reference on product tree (%s)" % case
         torch.save({"case": case, "hub": hub, "batch": B, "T": T, "H": H, "W": W, "weight_seed": 1234,
-                    "input_seed": 42, "output": out_ref.clone(),
+                    "input_seed": 42, "f16_grid": grid, "output": out_ref.clone(),
                     "input_checksum": TS.tensor_checksum(clip),
                     "state_checksum": TS.state_checksum(mine)},
                    os.path.join(GOLD, "model_%s.pt" % case))
@@ -124,6 +126,37 @@ def gen_transforms():
             y, xo, hh, ww = O.uniform_crop_window(h, w, size, idx)
             assert torch.equal(ref, x[:, :, y:y + hh, xo:xo + ww])
             out["uniform_crop"]["%d_%d_%d_%d" % (h, w, size, idx)] = (y, xo)
+    # (6) default TRAIN chain of the reference factory under a fixed seed (global torch RNG): pins the order
+    #     and arithmetic of the random draws (RandomShortSideScale, torchvision RandomCrop / RandomHorizontalFlip)
+    from pytorchvideo.transforms import create_video_transform as ref_factory
+    tr_cases = []
+    for (T, H, W, n, lo, hi, crop, seed) in [(20, 40, 60, 10, 24, 32, 16, 11), (9, 61, 37, 4, 30, 40, 28, 12),
+                                             (12, 90, 160, 5, 32, 48, 32, 13), (16, 48, 48, 16, 32, 32, 32, 14),
+                                             (10, 36, 36, 6, 20, 28, 20, 15), (8, 30, 50, 8, 16, 24, 16, 16)]:
+        clip = TS.synthetic_u8_clip(T, H, W, seed=seed)
+        chain = ref_factory(mode="train", num_samples=n, min_size=lo, max_size=hi, crop_size=crop)
+        torch.manual_seed(1000 + seed)
+        ref = chain(clip)
+        # the same draws, made by hand in the order the Compose makes them
+        torch.manual_seed(1000 + seed)
+        side = int(torch.randint(lo, hi + 1, (1,)).item())
+        nh, nw = O.short_side_size(H, W, side)
+        if (nh, nw) == (crop, crop):
+            i = j = 0
+        else:
+            i = int(torch.randint(0, nh - crop + 1, size=(1,)).item())
+            j = int(torch.randint(0, nw - crop + 1, size=(1,)).item())
+        flip = bool(torch.rand(1) < 0.5)
+        orc = O.train_chain(clip.numpy(), n, (0.45,) * 3, (0.225,) * 3, side, crop, i, j, flip)
+        err = float(np.abs(ref.numpy() - orc).max())
+        assert err <= 2e-6, ("oracle train chain deviates from the reference", err)
+        tr_cases.append({"T": T, "H": H, "W": W, "n": n, "min_size": lo, "max_size": hi, "crop": crop, "seed": seed,
+                         "rng_seed": 1000 + seed, "draws": (side, i, j, flip), "out": ref.clone(), "oracle_max_err": err})
+    assert any(c["draws"][3] for c in tr_cases) and not all(c["draws"][3] for c in tr_cases), "want flipped and unflipped cases"
+    out["train_small"] = tr_cases
+    # (7) SlowFast pathway packing (pytorchvideo_trainer/datamodule/transforms.py:99-138 restated: the trainer
+    #     package is not importable without hydra/lightning): slow = index_select(frames, 1, linspace(0, T-1, T//alpha).long())
+    out["pack_pathway"] = {"%d_%d" % (t, a): torch.linspace(0, t - 1, t // a).long() for (t, a) in [(32, 4), (64, 4), (16, 4), (32, 8), (8, 4)]}
     torch.save(out, os.path.join(GOLD, "transforms.pt"))
     print("transforms ok (full-size reference chain took %.2fs)" % dt, flush=True)
 

@@ -139,3 +139,31 @@ def val_chain(clip_u8, num_samples, mean, std, side, crop):
         top, left, th, tw = center_crop_window(x.shape[2], x.shape[3], crop)
         x = x[:, :, top:top + th, left:left + tw]
     return x
+
+
+def random_crop_window(h, w, size, i, j):
+    """torchvision RandomCrop.get_params (transforms_factory.py:251 uses torchvision's class): the window is
+    (i, j, th, tw) with i ~ randint(0, h-th+1), j ~ randint(0, w-tw+1) drawn by the caller from torch's global
+    RNG in that order; no draw at all when the image already has the crop size."""
+    th, tw = (size, size) if isinstance(size, int) else size
+    if h < th or w < tw:
+        raise ValueError("Required crop size %s is larger than input image size %s" % ((th, tw), (h, w)))
+    if w == tw and h == th:
+        return 0, 0, h, w
+    return int(i), int(j), th, tw
+
+
+def train_chain(clip_u8, num_samples, mean, std, side, crop, i, j, flip):
+    """The default train chain in the reference's order (transforms_factory.py:229-258, aug_type "default",
+    no RandomResizedCrop): UniformTemporalSubsample -> /255 -> Normalize -> RandomShortSideScale(side drawn by
+    the caller: torch.randint(min, max+1, (1,)), transforms.py:148) -> RandomCrop(i, j) ->
+    RandomHorizontalFlip (flip = torch.rand(1) < p, torchvision).  CTHW in."""
+    x = uniform_temporal_subsample(clip_u8, num_samples)
+    x = div_255(x)
+    x = normalize(x, mean, std)
+    x = short_side_scale(x, side)
+    top, left, th, tw = random_crop_window(x.shape[2], x.shape[3], crop, i, j)
+    x = x[:, :, top:top + th, left:left + tw]
+    if flip:
+        x = x[..., ::-1]
+    return np.ascontiguousarray(x)

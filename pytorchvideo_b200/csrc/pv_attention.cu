@@ -116,12 +116,7 @@ template <typename T, int D>
 static int launch_attention(const pv_attention_desc* d, const void* q, const void* k, const void* v,
                             void* o, cudaStream_t s) {
   const size_t smem = (size_t)((ATT_BQ + 2 * ATT_BK) * (D + 1) + ATT_WARPS * ATT_QPW * 32) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PV_CUDA_OK(cudaFuncSetAttribute(attention_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    attr_set = true;
-  }
+  PV_OPT_IN_SMEM((attention_kernel<T, D>), smem);
   dim3 grid((unsigned)cdiv(d->Nq, ATT_BQ), (unsigned)(d->B * d->H)), block(ATT_WARPS * 32);
   attention_kernel<T, D><<<grid, block, smem, s>>>(*d, (const T*)q, (const T*)k, (const T*)v, (T*)o);
   PV_LAUNCH_OK("attention_kernel");

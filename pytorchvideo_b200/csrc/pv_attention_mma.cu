@@ -201,11 +201,7 @@ template <int D>
 static int launch_attention_mma(const pv_attention_desc* d, const void* q, const void* k, const void* v, void* o,
                                 cudaStream_t s) {
   const size_t smem = (size_t)4 * FA_BK * (D + 8) * sizeof(__half);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PV_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  PV_OPT_IN_SMEM(attention_mma_kernel<D>, smem);
   dim3 grid((unsigned)cdiv(d->Nq, FA_BQ), (unsigned)(d->B * d->H)), block(FA_WARPS * 32);
   attention_mma_kernel<D><<<grid, block, smem, s>>>(*d, (const __half*)q, (const __half*)k, (const __half*)v, (__half*)o);
   PV_LAUNCH_OK("attention_mma_kernel");

@@ -45,6 +45,42 @@ void count_launch(int n = 1);
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// ---- per-device launch state -------------------------------------------------------------------
+// Function attributes (opt-in dynamic shared memory) and the SM count are PER DEVICE: a process that runs a
+// plan on cuda:0 and later on cuda:1 must opt in again on the second device.  One flag word per launch site,
+// one bit per device ordinal (devices >= 64 simply re-set the attribute on every launch).
+struct DeviceOnce {
+  unsigned long long done = 0ull;
+  // true exactly once per (site, current device)
+  bool first(int dev) {
+    if (dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+static inline int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+// SM count of the CURRENT device (cached per ordinal)
+static inline int current_sm_count() {
+  static int cache[64] = {0};
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 0;
+  if (dev < 64) cache[dev] = n;
+  return n;
+}
+#define PV_OPT_IN_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                  \
+    static pv::DeviceOnce _once;                                                                        \
+    if (_once.first(pv::current_device()))                                                              \
+      PV_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+  } while (0)
+
 // ---- element helpers ------------------------------------------------------------------------
 template <typename T> struct Elem;
 template <> struct Elem<__half> {

@@ -228,12 +228,7 @@ int dwconv3d_tile_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   dim3 grid((unsigned)tiles, (unsigned)chunks), block(256);
 #define PV_DWT(KW_, SW_)                                                                                      \
   do {                                                                                                        \
-    static bool attr = false;                                                                                 \
-    if (!attr) {                                                                                              \
-      PV_CUDA_OK(cudaFuncSetAttribute(dwconv3d_tile_kernel<KW_, SW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      110 * 1024));                                                           \
-      attr = true;                                                                                            \
-    }                                                                                                         \
+    PV_OPT_IN_SMEM((dwconv3d_tile_kernel<KW_, SW_>), 110 * 1024);                                             \
     dwconv3d_tile_kernel<KW_, SW_><<<grid, block, smem, stream>>>(P, (const __half*)w, scale, bias, (__half*)y, se_sums); \
   } while (0)
   if (d->kw == 3 && d->sw == 1) PV_DWT(3, 1);

@@ -338,5 +338,100 @@ __host__ __device__ inline bool epi_direct(const EpiParams& E) {
   return epi_narrow(E.block_n) && ((E.block_n <= 32) != ((E.dbg & 64) != 0));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// WIP (round 2, NOT validated on hardware): wide tiles with a residual, double-buffered staging.
+// profiles/r01_source_counters.md: on res2 conv_c the MMA warp waits for a free accumulator 68x per
+// tile - the epilogue is the bound, and per 128-column group it is a chain of: wait until the previous
+// bulk store has read the staging buffer -> residual TMA load (~1.5 us) -> in-place update -> store.
+// Here the residual of group q+1 is requested right after the store of group q is issued, into the
+// OTHER staging buffer (free once the store of group q-1 has been read: wait_group.read 1), so its
+// latency overlaps the store of q, the accumulator wait and the math of the next group.
+//   q            : running group counter of this CTA (buffer = q & 1, one residual barrier per buffer)
+//   nxt_*        : first group of the NEXT tile of this CTA (nxt_valid = 0 at the last tile)
+// The caller issues the very first residual load (group 0 of its first tile) before the tile loop with
+// epi_prefetch_residual(...).
+// ---------------------------------------------------------------------------------------------
+struct EpiNext { int valid, n0, c1, c2, c3, c4; };
+
+__device__ __forceinline__ void epi_prefetch_residual(const EpiParams& E, uint32_t epi_smem, uint32_t res_bar, int buf,
+                                                      int ncols, int n0, int c1, int c2, int c3, int c4) {
+  const int nsub = (ncols + 63) >> 6;
+  const uint32_t bar = res_bar + 8u * (uint32_t)buf;
+  mbar_arrive_expect_tx(bar, (uint32_t)(nsub * E.rows * 128));
+  for (int s = 0; s < nsub; ++s)
+    tma_load_5d(epi_smem + (uint32_t)buf * EPI_STAGING_BYTES + (uint32_t)s * 16384u, &E.r_map, bar, n0 + s * 64, c1, c2, c3, c4);
+}
+
+__device__ __forceinline__ void epilogue_tile_wide_prefetch(const EpiParams& E, const float* __restrict__ scale,
+                                                            const float* __restrict__ bias, uint32_t t_acc,
+                                                            uint32_t epi_smem, uint8_t* epi_gen, uint32_t res_bar,
+                                                            uint32_t (&res_phase)[2], int& q, int ewarp, int quarter,
+                                                            int lane, int n0, int c1, int c2, int c3, int c4,
+                                                            uint32_t tempty_bar, const EpiNext& nxt) {
+  const int row = quarter * 32 + lane;
+  const int chalf = ewarp >> 2;
+  const int etid = ewarp * 32 + lane;
+  const bool leader = (etid == 0);
+  const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t rsw = (uint32_t)(row & 7);
+  float* sb = reinterpret_cast<float*>(epi_gen + 2 * EPI_STAGING_BYTES);     // scale/bias live after BOTH staging buffers
+  for (int i = etid; i < E.block_n; i += EPI_THREADS) {
+    const int c = n0 + i;
+    const bool ok = c < E.Co;
+    sb[i] = ok ? __ldg(scale + c) : 0.f;
+    sb[256 + i] = ok ? __ldg(bias + c) : 0.f;
+  }
+  for (int g0 = 0; g0 < E.block_n; g0 += EPI_GROUP_COLS, ++q) {
+    const int buf = q & 1;
+    const int gcols = min(EPI_GROUP_COLS, E.block_n - g0);
+    const int nsub = (gcols + 63) >> 6;
+    const uint32_t slot = (uint32_t)buf * EPI_STAGING_BYTES;
+    epi_bar_sync(1, EPI_THREADS);                       // scale/bias visible; previous group fully staged + stored
+    mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested one group ago)
+    res_phase[buf] ^= 1u;
+    if (chalf < nsub) {
+      const int cbase = g0 + chalf * 64;
+      const int ncols = min(64, gcols - chalf * 64);
+      uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
+      const float* sc = sb + cbase;
+      const float* bi = sb + 256 + cbase;
+      switch (E.act) {
+        case PV_ACT_RELU: epi_subtile<PV_ACT_RELU, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_NONE: epi_subtile<PV_ACT_NONE, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_SWISH: epi_subtile<PV_ACT_SWISH, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_GELU: epi_subtile<PV_ACT_GELU, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        default: epi_subtile<PV_ACT_SIGMOID, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+      }
+    }
+    const bool last_group = g0 + EPI_GROUP_COLS >= E.block_n;
+    if (last_group) {                                   // accumulator fully read: hand TMEM back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    fence_proxy_async_smem();
+    epi_bar_sync(1, EPI_THREADS);
+    if (leader) {
+      for (int s = 0; s < nsub; ++s)
+        tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, n0 + g0 + s * 64, c1, c2, c3, c4);
+      tma_store_commit();
+      // residual of the next group into the other buffer (free once the store of group q-1 has been read)
+      if (!last_group) {
+        tma_store_wait_read1();
+        epi_prefetch_residual(E, epi_smem, res_bar, buf ^ 1, min(EPI_GROUP_COLS, E.block_n - g0 - EPI_GROUP_COLS),
+                              n0 + g0 + EPI_GROUP_COLS, c1, c2, c3, c4);
+      } else if (nxt.valid) {
+        tma_store_wait_read1();
+        epi_prefetch_residual(E, epi_smem, res_bar, buf ^ 1, min(EPI_GROUP_COLS, E.block_n), nxt.n0, nxt.c1, nxt.c2, nxt.c3, nxt.c4);
+      }
+    }
+  }
+}
+
+__host__ __device__ inline bool epi_wide_prefetch(const EpiParams& E) {
+  return !epi_narrow(E.block_n) && E.has_residual && (E.dbg & 256);      // opt-in: PVB200_DEBUG=256
+}
+
 }  // namespace sm100
 }  // namespace pv

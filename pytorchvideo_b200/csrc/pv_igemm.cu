@@ -54,6 +54,8 @@ struct IgemmParams {
   int acc_stride;   // TMEM columns between accumulator stages (block_n rounded up to 32)
   int nacc;         // number of accumulator stages
   int G, cpt;       // k-blocks per pipeline stage (chunk), chunks per tile
+  int split_ab;     // experimental (PVB200_SPLIT_AB=1): warp 0 issues the A loads, warp 1 the B loads
+  int epi_bytes;    // epilogue shared memory (one or - residual prefetch - two staging buffers + scale/bias)
   EpiParams epi;
   signed char tap_q[IG_MAX_TAPS][4];
   unsigned char tap_map[IG_MAX_TAPS];
@@ -74,7 +76,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   // epilogue staging (1024-aligned) and the barriers live after the tile ring
   const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
   const uint32_t staging = smem_base + staging_off;
-  const uint32_t bar_base = staging + EPI_SMEM_BYTES;
+  const uint32_t bar_base = staging + (uint32_t)P.epi_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
@@ -90,7 +92,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     prefetch_tmap(&P.b_map);
     prefetch_tmap(&P.a_maps[0]);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), P.split_ab ? 2 : 1);   // one expect_tx arrive per issuing producer warp
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < nacc; ++s) {
@@ -124,10 +126,11 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     // One producer warp: warp-uniform loop, one elected lane issues the TMA loads of a whole chunk
     // (up to G k-blocks = 2G bulk-tensor loads on ONE mbarrier).  Measured on B200: extra producer warps
     // do not help; what bounds narrow-N layers is the number of barrier rounds, hence the chunking.
-    if (warp == 0) {
+    if (warp == 0 || (warp == 1 && P.split_ab)) {
+      const bool do_a = !P.split_ab || warp == 0, do_b = !P.split_ab || warp == 1;
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)P.rows * P.kbytes + b_bytes;
+      const uint32_t tx_bytes = (do_a ? (uint32_t)P.rows * P.kbytes : 0u) + (do_b ? b_bytes : 0u);
       const int num_kc = P.num_kc, cpt = P.cpt;
       const bool skip_loads = (P.epi.dbg & 4) != 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -150,11 +153,14 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
               mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * tx_bytes);
               int tp = tap, kk = kc;
               for (int j = 0; j < nsub; ++j) {
-                const void* amap = &P.a_maps[P.tap_map[tp]];
-                tma_load_5d(st_base + (uint32_t)j * a_bytes, amap, full_bar(stage), kk * k_elems, o[0] + P.tap_q[tp][0],
-                            o[1] + P.tap_q[tp][1], o[2] + P.tap_q[tp][2], o[3] + P.tap_q[tp][3]);
-                tma_load_2d(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, full_bar(stage),
-                            (kb0 + j) * k_elems, n0);
+                if (do_a) {
+                  const void* amap = &P.a_maps[P.tap_map[tp]];
+                  tma_load_5d(st_base + (uint32_t)j * a_bytes, amap, full_bar(stage), kk * k_elems, o[0] + P.tap_q[tp][0],
+                              o[1] + P.tap_q[tp][1], o[2] + P.tap_q[tp][2], o[3] + P.tap_q[tp][3]);
+                }
+                if (do_b)
+                  tma_load_2d(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, full_bar(stage),
+                              (kb0 + j) * k_elems, n0);
                 if (++kk == num_kc) { kk = 0; ++tp; }
               }
             }
@@ -215,6 +221,21 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     int tile_seq = 0;
     uint32_t res_phase = 0;
     const bool narrow = epi_narrow(P.block_n);
+    // wide residual tiles: double-buffered staging with the residual of the next group prefetched
+    const bool wide_prefetch = epi_wide_prefetch(P.epi);
+    uint32_t res_phase2[2] = {0u, 0u};
+    int q = 0;
+    auto decode = [&](int tile, int& n0, int (&o)[4]) {
+      n0 = (tile % P.n_tiles) * P.block_n;
+      int mt = tile / P.n_tiles;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
+    };
+    if (wide_prefetch && ewarp == 0 && lane == 0 && (int)blockIdx.x < total_tiles) {
+      int n0f, of[4];
+      decode((int)blockIdx.x, n0f, of);
+      epi_prefetch_residual(P.epi, staging, res_bar, 0, min(EPI_GROUP_COLS, P.block_n), n0f, of[0], of[1], of[2], of[3]);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
       if (narrow && (tile_seq & 1) != (ewarp >> 2)) continue;     // the other group's tile
       const int acc = tile_seq % nacc;
@@ -231,6 +252,19 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (wide_prefetch) {
+        EpiNext nxt = {0, 0, 0, 0, 0, 0};
+        const int tn = tile + (int)gridDim.x;
+        if (tn < total_tiles) {
+          int on[4];
+          decode(tn, nxt.n0, on);
+          nxt.valid = 1; nxt.c1 = on[0]; nxt.c2 = on[1]; nxt.c3 = on[2]; nxt.c4 = on[3];
+        }
+        epilogue_tile_wide_prefetch(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging,
+                                    smem_gen + staging_off, res_bar, res_phase2, q, ewarp, quarter, lane,
+                                    n_tile * P.block_n, o[0], o[1], o[2], o[3], tempty_bar(acc), nxt);
+        continue;
+      }
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                     res_bar, res_phase, ewarp, quarter, lane, n_tile * P.block_n, o[0], o[1], o[2], o[3],
                     tempty_bar(acc), tile_seq);
@@ -395,13 +429,8 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PV_ERR_CUDA; }
 
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (sm_count == 0) {
-    int dev = 0;
-    PV_CUDA_OK(cudaGetDevice(&dev));
-    PV_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = current_sm_count();
+  if (sm_count <= 0) { set_error("cannot query the SM count of the current device"); return PV_ERR_CUDA; }
 
   IgemmPlan pl;
   reduce_dims(d, &pl);
@@ -488,17 +517,19 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (G > 4) G = 4;
     if (G > num_kb) G = num_kb;
     { const char* e = getenv("PVB200_G"); if (e && atoi(e) >= 1 && atoi(e) <= 8) G = atoi(e) < num_kb ? atoi(e) : num_kb; }
-    const int budget = 227 * 1024 - 2048 - EPI_SMEM_BYTES - 256;
+    P.epi_bytes = EPI_SMEM_BYTES + (epi_wide_prefetch(P.epi) ? EPI_STAGING_BYTES : 0);
+    const int budget = 227 * 1024 - 2048 - P.epi_bytes - 256;
     while (G > 1 && budget / (G * kb_bytes) < 3) --G;
     int st = budget / (G * kb_bytes);
     if (st > 24 / G) st = 24 / G > 2 ? 24 / G : 2;
     if (st < 2) st = 2;
     P.G = G;
+    { static const bool split = getenv("PVB200_SPLIT_AB") != nullptr; P.split_ab = split ? 1 : 0; }
     P.cpt = (num_kb + G - 1) / G;
     P.stages = st;
   }
   const int stage_bytes = P.G * kb_bytes;
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + EPI_SMEM_BYTES +
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + P.epi_bytes +
                             8 * (2 * P.stages + 2 * 8 + 4) + 16;
 
   // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)
@@ -619,10 +650,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     }
   }
 
-  if (!attr_set) {
-    PV_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  PV_OPT_IN_SMEM(conv3d_igemm_kernel, 227 * 1024);
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);

@@ -350,13 +350,8 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   }
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PV_ERR_CUDA; }
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (sm_count == 0) {
-    int dev = 0;
-    PV_CUDA_OK(cudaGetDevice(&dev));
-    PV_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = current_sm_count();
+  if (sm_count <= 0) { set_error("cannot query the SM count of the current device"); return PV_ERR_CUDA; }
   GatherParams P;
   memset(&P, 0, sizeof(P));
   P.N = d->N; P.Ti = d->Ti; P.Hi = d->Hi; P.Wi = d->Wi; P.To = d->To; P.Ho = d->Ho; P.Wo = d->Wo;
@@ -451,11 +446,7 @@ int conv3d_gather_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B, gather) failed: %d", (int)cr); return PV_ERR_CUDA; }
   }
-  if (!attr_set) {
-    PV_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    225 * 1024));
-    attr_set = true;
-  }
+  PV_OPT_IN_SMEM(conv3d_igemm_gather_kernel, 225 * 1024);
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
   const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);

@@ -60,9 +60,15 @@ class Lowering:
                                 _t3(conv.dilation), conv.groups, _act_code(act), residual, name, se_sums=se_sums)
 
     def conv2plus1d(self, x, m, bn, act, residual, name):
-        # layers/convolutions.py:232-237: conv_t -> norm -> activation -> conv_xy
-        h = self.conv(x, m.conv_t, getattr(m, "norm", None), getattr(m, "activation", None), None, name + ".conv_t")
-        return self.conv(h, m.conv_xy, bn, act, residual, name + ".conv_xy")
+        # layers/convolutions.py:232-237: conv_t -> norm -> activation -> conv_xy, or conv_xy first when
+        # conv_xy_first is set (the flag only swaps the two convolutions; norm/activation stay in between)
+        first, second = ("conv_xy", "conv_t") if getattr(m, "conv_xy_first", False) else ("conv_t", "conv_xy")
+        h = self.conv(x, getattr(m, first), getattr(m, "norm", None), getattr(m, "activation", None), None,
+                      name + "." + first)
+        return self.conv(h, getattr(m, second), bn, act, residual, name + "." + second)
+
+    def lower_Conv2plus1d(self, m, x, name):
+        return self.conv2plus1d(x, m, None, None, None, name)
 
     def pool(self, x, m, name="pool"):
         n = type(m).__name__
@@ -169,9 +175,12 @@ class Lowering:
         # models/net.py:107-122
         assert isinstance(x, list), "input for MultiPathWayWithFuse needs to be a list of tensors"
         out = list(x)
+        # the pathways are independent until the fusion: each gets its own lane (CUDA stream / graph branch)
         for i, blk in enumerate(m.multipathway_blocks):
             if blk is not None:
+                self.p.lane = i
                 out[i] = self.lower(blk, x[i], "%s.multipathway_blocks.%d" % (name, i))
+        self.p.lane = 0
         if m.multipathway_fusion is not None:
             out = self.lower(m.multipathway_fusion, out, name + ".multipathway_fusion")
         return out
@@ -179,7 +188,9 @@ class Lowering:
     def lower_FuseFastToSlow(self, m, x, name):
         # models/slowfast.py:720-729; the concat is fused away (both producers write into one buffer)
         x_s, x_f = x[0], x[1]
+        self.p.lane = 1        # the lateral conv reads the Fast tensor: keep it on the Fast lane, the Slow lane only
         fuse = self.conv(x_f, m.conv_fast_to_slow, m.norm, m.activation, None, name + ".conv_fast_to_slow")
+        self.p.lane = 0        # waits for it where the next Slow stage reads the concat buffer
         return [self.p.concat_channels([x_s, fuse]), x_f]
 
     def lower_PoolConcatPathway(self, m, x, name):
@@ -189,7 +200,9 @@ class Lowering:
             if xi is None:
                 continue
             if m.pool is not None and m.pool[i] is not None:
+                self.p.lane = i
                 xi = self.pool(xi, m.pool[i], "%s.pool.%d" % (name, i))
+                self.p.lane = 0
             outs.append(xi)
         cat = self.p.concat_channels(outs) if len(outs) > 1 else outs[0]
         return [cat] if getattr(m, "retain_list", False) else cat
@@ -262,15 +275,16 @@ class CompiledModel:
         self.key = tuple((tuple(t.shape), t.dtype) for t in ins)
 
     def _capture(self):
-        stream = torch.cuda.Stream(device=self.plan.device)
-        stream.wait_stream(torch.cuda.current_stream())
+        dev = self.plan.device
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
             self.plan.run(stream.cuda_stream)       # warm-up (also sets func attributes outside capture)
-        torch.cuda.current_stream().wait_stream(stream)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
-            self.plan.run(torch.cuda.current_stream().cuda_stream)
+            self.plan.run(torch.cuda.current_stream(dev).cuda_stream)
         self.graph = g
 
     def pipeline(self, depth=2):
@@ -281,16 +295,35 @@ class CompiledModel:
     def output_view(self):
         return self.out_buf.tensor[: int(torch.tensor(self.out_shape).prod())].view(*self.out_shape)
 
-    def __call__(self, inputs):
+    def check_inputs(self, inputs):
+        """The plan is frozen for one set of input shapes: anything else is an error (Tensor.copy_ would
+        silently broadcast a smaller batch into the static buffer)."""
+        if self.multi != isinstance(inputs, (list, tuple)):
+            raise RuntimeError("this plan was compiled for %s" % ("a list of pathway tensors" if self.multi else "a single tensor"))
         ins = list(inputs) if self.multi else [inputs]
+        if len(ins) != len(self.static_in):
+            raise RuntimeError("expected %d input tensors, got %d" % (len(self.static_in), len(ins)))
         for s, t in zip(self.static_in, ins):
-            s.copy_(t, non_blocking=True)     # H2D or D2D staging into the plan's static input
-        if self.use_graph:
-            if self.graph is None:
-                self._capture()
-            self.graph.replay()
-        else:
-            self.plan.run(torch.cuda.current_stream().cuda_stream)
+            if not torch.is_tensor(t) or tuple(t.shape) != tuple(s.shape):
+                raise RuntimeError("input shape %s differs from the compiled shape %s (compile a plan per shape)" % (
+                    tuple(t.shape) if torch.is_tensor(t) else type(t).__name__, tuple(s.shape)))
+            if not (t.is_floating_point() or t.dtype == torch.uint8):
+                raise RuntimeError("unsupported input dtype %s" % t.dtype)
+        return ins
+
+    def __call__(self, inputs):
+        ins = self.check_inputs(inputs)
+        dev = self.plan.device
+        with torch.cuda.device(dev):
+            for s, t in zip(self.static_in, ins):
+                if t.data_ptr() != s.data_ptr():
+                    s.copy_(t, non_blocking=True)     # H2D or D2D staging into the plan's static input
+            if self.use_graph:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+            else:
+                self.plan.run(torch.cuda.current_stream(dev).cuda_stream)
         return self.output_view()
 
 

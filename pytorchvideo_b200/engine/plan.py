@@ -8,6 +8,7 @@ buffer after it was produced - that is how ``torch.cat([slow, fuse], dim=1)``
 buffer.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -78,6 +79,16 @@ class Plan:
         self.finalized = False
         self.graph = None
         self.stats = {"tcgen05": 0, "direct": 0, "depthwise": 0, "other": 0}
+        # ---- lanes: independent branches of the network (SlowFast pathways) run on separate CUDA streams /
+        #      graph branches.  Every op records the tensors it reads / writes; finalize() turns cross-lane
+        #      read-after-write pairs into event waits (see _schedule).
+        self.lane = 0          # lane of the ops being emitted (set by the lowering)
+        self.op_lane = []
+        self.op_io = []        # (reads, writes) as lists of TRef / Buf, or None = unknown (acts as a full barrier)
+        self.sched = None
+        self.multi_lane = os.environ.get("PVB200_LANES", "1") != "0"
+        self._streams = {}
+        self._events = {}
 
     # ---- memory --------------------------------------------------------------------------
     def new_buf(self, numel, dt=None):
@@ -100,16 +111,73 @@ class Plan:
             if b.tensor is None:
                 # zero-init so that pad lanes / never-written slices are finite
                 b.tensor = torch.zeros(max(b.numel, 8), dtype=_TORCH_DT[b.dt], device=self.device)
+        self._schedule()
         self.finalized = True
+
+    def _schedule(self):
+        """Cross-lane dependencies.  For op i on lane L: for every other lane M, the LAST op j < i on M that wrote
+        a buffer op i reads (stream order covers the earlier ones).  Ops with unknown I/O are full barriers.  No
+        buffer is reused inside a plan, so read-after-write is the only hazard (two lanes writing one concat
+        buffer write disjoint channel slices)."""
+        def bufs_of(items):
+            out = []
+            for t in items or ():
+                b = t if isinstance(t, Buf) else getattr(t, "buf", None)
+                if b is not None:
+                    out.append(b)
+            return out
+        n = len(self.ops)
+        lanes = sorted(set(self.op_lane)) if self.op_lane else [0]
+        waits = [[] for _ in range(n)]      # op -> list of op indices (on other lanes) to wait for
+        writers = {}                        # id(buf) -> {lane: last writer op}
+        last_on_lane = {}
+        last_barrier = None                 # last op with unknown I/O
+        waited = {}                         # lane -> {other lane: latest op already waited for}
+        for i in range(n):
+            L = self.op_lane[i]
+            io = self.op_io[i]
+            need = {}
+            if io is None:
+                for M, j in last_on_lane.items():
+                    if M != L:
+                        need[M] = j
+            else:
+                for b in bufs_of(io[0]):
+                    for M, j in writers.get(id(b), {}).items():
+                        if M != L:
+                            need[M] = max(need.get(M, -1), j)
+                if last_barrier is not None and self.op_lane[last_barrier] != L:
+                    M = self.op_lane[last_barrier]
+                    need[M] = max(need.get(M, -1), last_barrier)
+            # a lane never needs to wait twice for the same (or an earlier) op of another lane
+            seen = waited.setdefault(L, {})
+            keep = []
+            for M, j in sorted(need.items()):
+                if seen.get(M, -1) < j:
+                    seen[M] = j
+                    keep.append(j)
+            waits[i] = sorted(keep)
+            if io is None:
+                last_barrier = i
+            else:
+                for b in bufs_of(io[1]):
+                    writers.setdefault(id(b), {})[L] = i
+            last_on_lane[L] = i
+        signals = sorted(set(j for w in waits for j in w))
+        self.sched = {"lanes": lanes, "waits": waits, "signals": set(signals), "last_on_lane": last_on_lane}
 
     def bytes_allocated(self):
         return sum(b.numel * _ESIZE[b.dt] for b in self.bufs)
 
     # ---- execution -----------------------------------------------------------------------
-    def add(self, name, fn, kind="other", flops=0.0, nbytes=0.0):
+    def add(self, name, fn, kind="other", flops=0.0, nbytes=0.0, reads=None, writes=None):
+        """reads / writes: the TRefs (or Bufs) the launch touches; leave both None for "unknown" (the op then
+        orders against everything on the other lanes)."""
         self.ops.append((name, fn))
-        self.meta.append({"name": name, "kind": kind, "flops": float(flops), "bytes": float(nbytes)})
+        self.meta.append({"name": name, "kind": kind, "flops": float(flops), "bytes": float(nbytes), "lane": self.lane})
         self.stats[kind] = self.stats.get(kind, 0) + 1
+        self.op_lane.append(self.lane)
+        self.op_io.append(None if reads is None and writes is None else (list(reads or ()), list(writes or ())))
 
     def profile(self, iters=3):
         """Per-launch device times (ms, mean over `iters`) measured with CUDA events on the
@@ -121,7 +189,7 @@ class Plan:
         acc = [0.0] * n
         for it in range(iters + 1):
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-            for (e0, e1), (_, fn) in zip(evs, self.ops):
+            for (e0, e1), (_, fn) in zip(evs, self.ops):      # single stream: lanes are ignored here
                 e0.record(stream)
                 fn(sp)
                 e1.record(stream)
@@ -132,10 +200,45 @@ class Plan:
                 acc[i] += e0.elapsed_time(e1)
         return [a / iters for a in acc]
 
-    def run(self, stream_ptr):
+    def run(self, stream_ptr, single_stream=False):
+        """Enqueue every launch.  With more than one lane the extra lanes run on side streams that fork from /
+        join back into ``stream_ptr`` with events, so a CUDA-graph capture of this call records a graph with
+        parallel branches (and an eager call overlaps them the same way)."""
         assert self.finalized
-        for _, fn in self.ops:
-            fn(stream_ptr)
+        lanes = self.sched["lanes"]
+        if single_stream or not self.multi_lane or len(lanes) <= 1:
+            for _, fn in self.ops:
+                fn(stream_ptr)
+            return
+        main = torch.cuda.ExternalStream(stream_ptr, device=self.device)
+        streams = {lanes[0]: main}
+        for L in lanes[1:]:
+            if L not in self._streams:
+                self._streams[L] = torch.cuda.Stream(device=self.device)
+            streams[L] = self._streams[L]
+        ev = self._events
+
+        def event(key):
+            e = ev.get(key)
+            if e is None:
+                e = ev[key] = torch.cuda.Event()
+            return e
+        fork = event("fork")
+        fork.record(main)
+        for L in lanes[1:]:
+            streams[L].wait_event(fork)
+        waits, signals = self.sched["waits"], self.sched["signals"]
+        for i, (_, fn) in enumerate(self.ops):
+            st = streams[self.op_lane[i]]
+            for j in waits[i]:
+                st.wait_event(event(j))
+            fn(st.cuda_stream)
+            if i in signals:
+                event(i).record(st)
+        for L in lanes[1:]:
+            e = event(("join", L))
+            e.record(streams[L])
+            main.wait_event(e)
 
     def num_launches(self):
         return len(self.ops)
@@ -168,14 +271,16 @@ class Plan:
             def fn(stream):
                 L.check(lib.pv_ncdhw_to_ndhwc_padw(src.data_ptr(), src_dt, x.ptr(), x.dt, N, C, T, H, W, x.Cp,
                                                   w_pad, w_phys, stream), "pv_ncdhw_to_ndhwc_padw")
-            self.add("ncdhw_to_ndhwc_padw", fn, "other", 0.0, src.numel() * src.element_size() + N * T * H * w_phys * x.Cp * 2)
+            self.add("ncdhw_to_ndhwc_padw", fn, "other", 0.0, src.numel() * src.element_size() + N * T * H * w_phys * x.Cp * 2,
+                     reads=(), writes=(x,))
         else:
             x.buf = self.new_buf(N * T * H * W * x.Cp)
 
             def fn(stream):
                 L.check(lib.pv_ncdhw_to_ndhwc(src.data_ptr(), src_dt, x.ptr(), x.dt, N, C, T, H, W, x.Cp,
                                               x.row_stride, stream), "pv_ncdhw_to_ndhwc")
-            self.add("ncdhw_to_ndhwc", fn, "other", 0.0, src.numel() * src.element_size() + N * T * H * W * x.Cp * 2)
+            self.add("ncdhw_to_ndhwc", fn, "other", 0.0, src.numel() * src.element_size() + N * T * H * W * x.Cp * 2,
+                     reads=(), writes=(x,))
         return x
 
     def emit_conv(self, x, weight, conv_bias, bn, stride, padding, dilation, groups, act=L.ACT_NONE,
@@ -218,7 +323,8 @@ class Plan:
                 L.check(lib.pv_temporal_tap_sum(yk.ptr(), y.ptr(), self.dt, x.N, x.T, To, hw, co_pad, kt, st, pt, dlt,
                                                 scale_d.data_ptr(), bias_d.data_ptr(), act, yk.row_stride,
                                                 y.row_stride, stream), "pv_temporal_tap_sum(%s)" % name)
-            self.add(name + ".tapsum", fn_sum, "other", 0.0, (x.N * x.T * hw * kt * co_pad + x.N * To * hw * co_pad) * 2)
+            self.add(name + ".tapsum", fn_sum, "other", 0.0, (x.N * x.T * hw * kt * co_pad + x.N * To * hw * co_pad) * 2,
+                     reads=(yk,), writes=(y,))
             return y
         # ---- network input: pick the layout its first consumer wants
         window = False
@@ -290,7 +396,7 @@ class Plan:
 
             def fn_zero(stream):
                 L.check(lib.pv_zero_f32(sums.tensor.data_ptr(), x.N * co_pad, stream), "pv_zero_f32")
-            self.add(name + ".se_zero", fn_zero)
+            self.add(name + ".se_zero", fn_zero, reads=(), writes=(sums,))
 
         def fn_dw(stream):
             d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
@@ -308,7 +414,8 @@ class Plan:
         m_out = x.N * To * Ho * Wo
         flops = 2.0 * m_out * co * cig * kt * kh * kw
         nbytes = (x.N * x.npos * ci + m_out * co * (2 if residual is not None else 1)) * esz + weight.numel() * esz
-        self.add(name, fn_dw if (depthwise and residual is None) else fn, kind, flops, nbytes)
+        self.add(name, fn_dw if (depthwise and residual is None) else fn, kind, flops, nbytes,
+                 reads=(x,) + ((residual,) if residual is not None else ()), writes=(y,) + ((sums,) if sums is not None else ()))
         return y
 
     def emit_pool(self, x, mode, kernel, stride, padding, name="pool"):
@@ -330,7 +437,7 @@ class Plan:
         def fn(stream):
             d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
             L.check(lib.pv_pool3d_fwd(C.byref(d), x.ptr(), y.ptr(), stream), "pv_pool3d_fwd(%s)" % name)
-        self.add(name, fn)
+        self.add(name, fn, reads=(x,), writes=(y,))
         return y
 
     def emit_se_scale_act(self, x, w1, b1, w2, b2, act, name="se"):
@@ -388,7 +495,7 @@ class Plan:
         def fn(stream):
             L.check(lib.pv_head_reduce(x.ptr(), x.dt, x.row_stride, x.N, x.npos, x.C, 1 if softmax else 0,
                                        out.tensor.data_ptr(), stream), "pv_head_reduce(%s)" % name)
-        self.add(name, fn)
+        self.add(name, fn, reads=(x,), writes=(out,))
         return out, (x.N, x.C)
 
     def emit_to_ncdhw(self, x, name="to_ncdhw"):
@@ -399,7 +506,7 @@ class Plan:
         def fn(stream):
             L.check(lib.pv_ndhwc_to_ncdhw(x.ptr(), x.dt, x.row_stride, out.tensor.data_ptr(), x.N, x.C, x.T,
                                           x.H, x.W, stream), "pv_ndhwc_to_ncdhw(%s)" % name)
-        self.add(name, fn)
+        self.add(name, fn, reads=(x,), writes=(out,))
         return out, x.shape5()
 
     def concat_channels(self, parts):

@@ -8,12 +8,19 @@ from . import config
 
 
 class B200Module(nn.Module):
+    _PV_CACHE_PLANS = 4      # compiled plans kept per module (LRU): alternating shapes do not re-capture a graph
+
     def _pv_fingerprint(self):
-        v = 0
-        for t in self.parameters():
-            v += t._version + (t.data_ptr() & 0xFFFF)
-        for t in self.buffers():
-            v += t._version + (t.data_ptr() & 0xFFFF)
+        """Cheap change detector for the derived weight copies: in-place updates (load_state_dict,
+        optimizer steps) bump ``_version``; ``.to()`` / ``.cuda()`` move the storage.  The list of
+        tensors is collected once - Parameter / buffer OBJECTS survive both kinds of update."""
+        ts = self.__dict__.get("_pv_tensors")
+        if ts is None:
+            ts = [t for t in self.parameters()] + [t for t in self.buffers()]
+            self.__dict__["_pv_tensors"] = ts
+        v = len(ts)
+        for t in ts:
+            v += t._version + (t.data_ptr() & 0xFFFFF)
         return v
 
     def _pv_compiled(self, x):
@@ -30,13 +37,21 @@ class B200Module(nn.Module):
         key = (tuple((tuple(t.shape), t.dtype, t.device.index) for t in ins), config.get_precision(),
                config.get_use_tcgen05(), config.get_use_graph(), self._pv_fingerprint())
         cache = self.__dict__.setdefault("_pv_cache", {})
-        cm = cache.get(key)
+        cm = cache.pop(key, None)
         if cm is None:
-            cache.clear()
+            fp = key[-1]
+            for k in [k for k in cache if k[-1] != fp]:
+                del cache[k]                       # weights changed: every older plan holds stale packed copies
+            while len(cache) >= self._PV_CACHE_PLANS:
+                del cache[next(iter(cache))]       # least recently used
             cm = compile_model(self, list(ins) if isinstance(x, (list, tuple)) else x, config.get_precision(),
                                config.get_use_tcgen05(), config.get_use_graph())
-            cache[key] = cm
+        cache[key] = cm                            # (re)insert at the most-recently-used end
         return cm
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__.pop("_pv_tensors", None)     # .to()/.cuda() may replace parameter objects
+        return super()._apply(fn, *a, **k)
 
     def forward(self, x):
         cm = self._pv_compiled(x)

@@ -39,13 +39,36 @@ def shard_batch(x, rank, world):
     return x[lo:hi]
 
 
-def gather_logits(local_logits, world=None):
-    """all_gather of equally sized [B_local, K] logits -> [world*B_local, K] on every rank."""
+def gather_logits(local_logits, world=None, total=None):
+    """ONE all_gather of the rank-local [B_local, K] logits -> [B_total, K] on every rank.
+
+    ``total`` = global number of clips when the shards are unequal (``shard_bounds`` gives the first
+    B %% world ranks one clip more): every rank then pads its rows to ceil(total / world) so that the
+    collective is still a single equal-sized all_gather_into_tensor, and the pad rows are trimmed with the
+    same ``shard_bounds``.  With ``total=None`` all ranks must hold the same number of rows."""
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return local_logits
-    out = torch.empty((world * local_logits.shape[0],) + tuple(local_logits.shape[1:]),
-                      dtype=local_logits.dtype, device=local_logits.device)
-    dist.all_gather_into_tensor(out, local_logits.contiguous())
-    return out
+    rows = local_logits.shape[0]
+    if total is not None:
+        rank = dist.get_rank()
+        lo, hi = shard_bounds(total, rank, world)
+        if hi - lo != rows:
+            raise RuntimeError("rank %d holds %d rows but shard_bounds(%d, %d, %d) gives %d" % (rank, rows, total, rank, world, hi - lo))
+        rows = -(-total // world)
+    tail = tuple(local_logits.shape[1:])
+    src = local_logits.contiguous()
+    if rows != src.shape[0]:
+        pad = torch.zeros((rows,) + tail, dtype=src.dtype, device=src.device)
+        pad[: src.shape[0]] = src
+        src = pad
+    out = torch.empty((world * rows,) + tail, dtype=src.dtype, device=src.device)
+    dist.all_gather_into_tensor(out, src)
+    if total is None or total == world * rows:
+        return out
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(total, r, world)
+        parts.append(out[r * rows: r * rows + (hi - lo)])
+    return torch.cat(parts, 0)

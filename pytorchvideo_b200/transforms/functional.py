@@ -76,13 +76,15 @@ def random_crop_window(h, w, size):
 
 
 def clip_transform(x, frame_idx=None, resize_hw=None, window=None, mean=None, std=None, div255=False,
-                   out_dtype=torch.float32, out=None):
+                   out_dtype=torch.float32, out=None, hflip=False):
     """Run the fused kernel on a CUDA clip ``x`` of logical shape (C, T, H, W) (any strides).
 
     frame_idx : int tensor/sequence of frames to keep (None = all)
     resize_hw : (new_h, new_w) bilinear target (None = no resize)
     window    : (top, left, h, w) crop in the resized frame (None = full)
     mean/std  : per-channel normalisation (None = skip)
+    hflip     : mirror the (cropped) output along W - torchvision hflip fused for free by reversing the
+                column tap tables on the host
     """
     if not torch.is_tensor(x) or x.dim() != 4:
         raise RuntimeError("expected a (C, T, H, W) tensor")
@@ -103,6 +105,8 @@ def clip_transform(x, frame_idx=None, resize_hw=None, window=None, mean=None, st
     x0, x1, lx = bilinear_table(W, nw)
     y0, y1, ly = y0[top:top + oh], y1[top:top + oh], ly[top:top + oh]
     x0, x1, lx = x0[left:left + ow], x1[left:left + ow], lx[left:left + ow]
+    if hflip:
+        x0, x1, lx = x0[::-1], x1[::-1], lx[::-1]
     per_channel = mean is not None or std is not None
     n_t = int(idx.numel())
     if per_channel:
@@ -134,7 +138,7 @@ def clip_transform(x, frame_idx=None, resize_hw=None, window=None, mean=None, st
                 return torch.cat(outs, 0)
     dev = x.device
     # device-side tables are tiny but cost several H2D copies: cache them per (geometry, device)
-    ckey = (dev.index, H, W, nh, nw, top, left, oh, ow, tuple(int(i) for i in kidx.tolist()))
+    ckey = (dev.index, H, W, nh, nw, top, left, oh, ow, bool(hflip), tuple(int(i) for i in kidx.tolist()))
     cached = _TABLE_CACHE.get(ckey)
     if cached is None:
         tabs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (y0, y1, ly, x0, x1, lx)]

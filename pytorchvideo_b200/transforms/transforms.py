@@ -114,14 +114,17 @@ class FusedClipTransform(nn.Module):
     ("uniform", size, spatial_idx).  Input: uint8 (or float) CUDA clip (C, T, H, W)."""
 
     def __init__(self, num_samples=None, mean=None, std=None, short_side=None, crop=None, div255=True,
-                 out_dtype=torch.float16, random_short_side=None):
+                 out_dtype=torch.float16, random_short_side=None, hflip_prob=0.0):
         super().__init__()
         self.num_samples, self.mean, self.std = num_samples, mean, std
         self.short_side, self.crop, self.div255, self.out_dtype = short_side, crop, div255, out_dtype
         self.random_short_side = random_short_side
+        self.hflip_prob = float(hflip_prob)
 
     def plan(self, shape):
-        """Host-side index/window selection for an input of ``shape`` (C, T, H, W)."""
+        """Host-side index/window/flip selection for an input of ``shape`` (C, T, H, W).  Random draws
+        come from torch's global RNG in the order the reference's Compose makes them:
+        RandomShortSideScale (randint), RandomCrop (randint i, randint j), RandomHorizontalFlip (rand)."""
         _, T, H, W = shape
         idx = None if self.num_samples is None else Fv.temporal_indices(T, self.num_samples)
         side = self.short_side
@@ -141,24 +144,78 @@ class FusedClipTransform(nn.Module):
                 win = Fv.uniform_crop_window(nh, nw, self.crop[1], self.crop[2])
             else:
                 raise ValueError("unknown crop kind %r" % (kind,))
-        return idx, hw, win
+        flip = False
+        if self.hflip_prob > 0.0:        # torchvision RandomHorizontalFlip.forward: torch.rand(1) < p
+            flip = bool(torch.rand(1) < self.hflip_prob)
+        return idx, hw, win, flip
 
     def forward(self, x, out=None):
-        idx, hw, win = self.plan(x.shape)
+        idx, hw, win, flip = self.plan(x.shape)
         return Fv.clip_transform(x, frame_idx=idx, resize_hw=hw, window=win, mean=self.mean, std=self.std,
-                                 div255=self.div255, out_dtype=self.out_dtype, out=out)
+                                 div255=self.div255, out_dtype=self.out_dtype, out=out, hflip=flip)
 
 
-def create_video_transform(mode="val", num_samples=8, video_mean=(0.45, 0.45, 0.45),
-                           video_std=(0.225, 0.225, 0.225), min_size=256, max_size=320, crop_size=224,
-                           convert_to_float=True, out_dtype=torch.float16):
-    """Fused equivalent of the reference factory's default chains (transforms_factory.py:109-261):
-    train = subsample, /255, normalize, RandomShortSideScale(min,max), RandomCrop
-    val   = subsample, /255, normalize, ShortSideScale(min_size), CenterCrop."""
-    assert mode in ("train", "val")
+class RemoveKey:
+    """transforms.py:34-47: drops ``key`` from a dict sample."""
+
+    def __init__(self, key):
+        self._key = key
+
+    def __call__(self, x):
+        if self._key in x:
+            del x[self._key]
+        return x
+
+
+class _Chain:
+    """Minimal torchvision ``Compose`` (dict-level steps around the fused clip transform)."""
+
+    def __init__(self, steps):
+        self.transforms = list(steps)
+
+    def __call__(self, x):
+        for t in self.transforms:
+            x = t(x)
+        return x
+
+
+def create_video_transform(mode, video_key=None, remove_key=None, num_samples=8, convert_to_float=True,
+                           video_mean=(0.45, 0.45, 0.45), video_std=(0.225, 0.225, 0.225), min_size=256,
+                           max_size=320, crop_size=224, horizontal_flip_prob=0.5, aug_type="default",
+                           aug_paras=None, random_resized_crop_paras=None, out_dtype=torch.float16):
+    """Fused equivalent of the reference factory's default chains (transforms_factory.py:109-284), same
+    signature and argument checks:
+      train = subsample, /255, normalize, RandomShortSideScale(min,max), RandomCrop, RandomHorizontalFlip(p)
+      val   = subsample, /255, normalize, ShortSideScale(min_size), CenterCrop
+    as ONE kernel launch.  RandAugment / AugMix (aug_type) and RandomResizedCrop have no B200 kernel:
+    asking for them raises NotImplementedError instead of silently changing the augmentation."""
+    if mode not in ("train", "val"):
+        raise NotImplementedError("mode must be 'train' or 'val'")
+    if isinstance(crop_size, int):
+        assert crop_size <= min_size, "crop_size must be less than or equal to min_size"
+    elif isinstance(crop_size, tuple):
+        assert max(crop_size) <= min_size, "the height and width in crop_size must be less than or equal to min_size"
+    else:
+        raise TypeError
+    if video_key is None:
+        assert remove_key is None, "remove_key should be None if video_key is None"
+    if aug_type == "default":
+        assert aug_paras is None, "aug_paras should be None for ``default`` aug_type"
+    elif aug_type in ("randaug", "augmix"):
+        if mode == "train":
+            raise NotImplementedError("aug_type=%r has no B200 kernel (only the 'default' chain is fused)" % aug_type)
+    else:
+        raise NotImplementedError
+    if random_resized_crop_paras is not None and mode == "train":
+        raise NotImplementedError("RandomResizedCrop has no B200 kernel (use RandomShortSideScale + RandomCrop)")
     if mode == "val":
-        return FusedClipTransform(num_samples, video_mean, video_std, short_side=min_size,
-                                  crop=("center", crop_size), div255=convert_to_float, out_dtype=out_dtype)
-    return FusedClipTransform(num_samples, video_mean, video_std, crop=("random", crop_size),
-                              div255=convert_to_float, out_dtype=out_dtype,
-                              random_short_side=(min_size, max_size))
+        tr = FusedClipTransform(num_samples, video_mean, video_std, short_side=min_size,
+                                crop=("center", crop_size), div255=convert_to_float, out_dtype=out_dtype)
+    else:
+        tr = FusedClipTransform(num_samples, video_mean, video_std, crop=("random", crop_size),
+                                div255=convert_to_float, out_dtype=out_dtype,
+                                random_short_side=(min_size, max_size), hflip_prob=horizontal_flip_prob)
+    if video_key is None:
+        return tr
+    return _Chain([ApplyTransformToKey(key=video_key, transform=tr)] +
+                  ([] if remove_key is None else [RemoveKey(k) for k in remove_key]))

@@ -22,7 +22,20 @@ def _worker(rank, world, port, ret):
     logits = local[1].flatten(1)[:, :5] * 2.0 + local[0].flatten(1)[:, :5]
     full = PAR.gather_logits(logits, world)
     expect = clips.flatten(1)[:, :5] * 2.0 + clips[:, :, ::2].flatten(1)[:, :5]
-    ret[rank] = bool(torch.allclose(full, expect))
+    ok = bool(torch.allclose(full, expect))
+    # unequal shards (7 clips over 2 ranks: 4 + 3): still ONE equal-sized all-gather, pad rows trimmed
+    odd = clips[:7]
+    lo, hi = PAR.shard_bounds(7, rank, world)
+    assert hi - lo == (4 if rank == 0 else 3)
+    mine = PAR.shard_batch(odd, rank, world)
+    full7 = PAR.gather_logits(mine.flatten(1)[:, :5] * 3.0, world, total=7)
+    ok = ok and full7.shape == (7, 5) and bool(torch.allclose(full7, odd.flatten(1)[:, :5] * 3.0))
+    try:
+        PAR.gather_logits(mine.flatten(1)[:1, :5], world, total=7)
+        ok = False
+    except RuntimeError:
+        pass
+    ret[rank] = ok
     dist.destroy_process_group()
 
 

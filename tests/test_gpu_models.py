@@ -5,9 +5,8 @@ Tolerances (also in DESIGN.md):
   f32 storage ("parity mode", CUDA-core kernels): |d| <= 1e-3*|ref| + 1e-4*max(1, max|ref|)
       i.e. the north-star rtol=1e-3 / atol=1e-4 with atol expressed relative to the logit scale
       (synthetic weights give logits of magnitude 10..500).
-  f16 storage (tensor-core path): every stored activation is rounded to 11 significant bits, and
-      there are 50-100 layers; the asserted bound is max|d| <= 2e-2 * max|ref| and the fraction of
-      logits inside rtol=1e-3/atol=1e-4*scale is reported.
+  f16 storage (tensor-core path, the benchmarked one): per-case MEASURED bounds are asserted - the
+      fraction of logits inside rtol=1e-3/atol=1e-4*scale and max|d|/max|ref| (F16_BOUNDS below).
 """
 import os
 
@@ -22,24 +21,15 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _setup(case):
-    g = torch.load(os.path.join(GOLD, "model_%s.pt" % case), weights_only=False)
-    hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
-    model = TS.randomize_model(getattr(PH, hub)(**kw), seed=g["weight_seed"]).eval()
-    clip = TS.synthetic_clip(B, T, H, W, seed=g["input_seed"])
-    inp = TS.slowfast_inputs(clip) if is_sf else clip
-    return g, model, inp, is_sf
-
-
 def _to_dev(inp):
     return [t.cuda() for t in inp] if isinstance(inp, list) else inp.cuda()
 
 
 @pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50",
-                                  "mvit_base_8x112"])
+                                  "mvit_base_8x112", "mvit_base_16x4", "c2d_r50", "x3d_s", "c1_x3d_xs"])
 def test_model_f32_parity_mode(case):
     from pytorchvideo_b200 import config
-    g, model, inp, _ = _setup(case)
+    g, model, inp, _ = _setup_case(case)
     ref = g["output"]
     config.set_precision("f32")
     try:
@@ -55,27 +45,66 @@ def test_model_f32_parity_mode(case):
     assert bool((err <= tol).all()), "max err %.3e (scale %.3g)" % (float(err.max()), scale)
 
 
-@pytest.mark.parametrize("case", ["x3d_xs", "x3d_m", "slowfast_r50", "slow_r50", "csn_r101", "r2plus1d_r50", "i3d_r50",
-                                  "mvit_base_8x112", "mvit_base_16x4"])
+# ---- f16 tensor-core path (the benchmarked configuration) -------------------------------------------------
+# Asserted per case: (minimum fraction of logits inside rtol 1e-3 / atol 1e-4*max(1,max|ref|), maximum
+# max|d|/max|ref|).  The numbers are the values MEASURED on B200 (profiles/r02_parity.md) with a small
+# margin, so a numerical regression fails the suite; they are not aspirations.
+#  * arbitrary fp32 weights: rounding the WEIGHTS to f16 operands alone moves 8-25 % of the logits out of
+#    the band even in the reference's own fp32 arithmetic (tests/test_oracle_pinning.py::
+#    test_f16_operand_floor_of_the_reference_arithmetic) - no f16-operand tensor-core path can do better;
+#  * "f16 grid" cases (weights and clip exactly representable in f16, so reference and engine multiply
+#    IDENTICAL operands, BASELINE batch sizes): what is left is activation rounding + summation order.
+F16_BOUNDS = {
+    # case: (min in-band fraction, max |d|/max|ref|)
+    "x3d_xs": (0.78, 1.0e-3), "x3d_m": (0.73, 1.2e-3), "slowfast_r50": (0.85, 9e-4), "slow_r50": (0.83, 1.1e-3),
+    "csn_r101": (0.84, 8e-4), "i3d_r50": (0.83, 9e-4), "mvit_base_8x112": (0.54, 1.9e-3),
+    "mvit_base_16x4": (0.62, 1.5e-3),
+    # softmax head: the outputs are probabilities, |d p| ~ p * |d logit| - the relative error of the largest
+    # probability is the ABSOLUTE logit error (~5e-4 * |logit| scale 15), in-band fraction 0.99
+    "r2plus1d_r50": (0.97, 1.2e-2),
+    # hub entries added in round 2 (first GPU measurement: profiles/r02_parity.md)
+    "slowfast_r101": (None, 2e-3), "c2d_r50": (None, 2e-3), "x3d_s": (None, 2e-3), "x3d_l": (None, 2e-3),
+    "mvit_base_32x3": (None, 2e-3),
+    # f16-grid weights / inputs, BASELINE configs at their real batch sizes
+    "c1_x3d_xs": (None, 2e-3), "c2_slowfast_r50_b8": (None, 2e-3), "c3_mvit_base_16x4_b8": (None, 2e-3),
+    "c4_x3d_m_b32": (None, 2e-3), "slow_r50_f16w": (None, 2e-3), "mvit_base_8x112_f16w": (None, 2e-3),
+}
+_BIG = ("c2_slowfast_r50_b8", "c3_mvit_base_16x4_b8", "c4_x3d_m_b32", "x3d_l", "mvit_base_32x3", "slowfast_r101")
+
+
+def _setup_case(case):
+    g = torch.load(os.path.join(GOLD, "model_%s.pt" % case), weights_only=False)
+    model, inp, is_sf = TS.build_case(case, PH, weight_seed=g["weight_seed"], input_seed=g["input_seed"])
+    assert abs(TS.state_checksum(model) - g["state_checksum"]) <= 1e-6 * abs(g["state_checksum"]), "weights differ from the golden's"
+    return g, model, inp, is_sf
+
+
+@pytest.mark.parametrize("case", sorted(F16_BOUNDS))
 def test_model_f16_tensor_core_path(case):
-    g, model, inp, _ = _setup(case)
+    g, model, inp, _ = _setup_case(case)
     ref = g["output"]
     model.cuda()
     out = model(_to_dev(inp)).float().cpu()
     out2 = model(_to_dev(inp)).float().cpu()           # cached plan + graph replay is deterministic
     model.cpu()
-    if case.startswith("x3d"):   # SE channel sums use fp32 atomics -> run-to-run rounding differences
+    if "x3d" in case:   # SE channel sums use fp32 atomics -> run-to-run rounding differences
         assert torch.allclose(out, out2, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
     else:
         assert torch.equal(out, out2)
+    assert out.shape == ref.shape
     scale = float(ref.abs().max())
     err = (out - ref).abs()
     inside = float((err <= 1e-3 * ref.abs() + 1e-4 * max(1.0, scale)).float().mean())
-    print("%s f16: max|d|/max|ref| = %.3e, fraction within rtol1e-3/atol1e-4 = %.3f" % (case, float(err.max()) / scale, inside))
-    assert float(err.max()) <= 2e-2 * scale
-    # the oracle re-run here agrees with the golden (same arithmetic, this box's CPU)
-    orc = oracle_forward(model, inp)
-    assert float((orc - ref).abs().max()) <= 1e-4 * max(1.0, scale)
+    rel = float(err.max()) / scale
+    print("PARITY %s f16: max|d|/max|ref| = %.3e, fraction within rtol1e-3/atol1e-4 = %.3f" % (case, rel, inside))
+    lo, hi = F16_BOUNDS[case]
+    assert rel <= hi, "max|d|/max|ref| = %.3e > %.1e" % (rel, hi)
+    if lo is not None:
+        assert inside >= lo, "only %.3f of the logits inside the band (floor %.2f)" % (inside, lo)
+    if case not in _BIG:
+        # the oracle re-run here agrees with the golden (same arithmetic, this box's CPU)
+        orc = oracle_forward(model, inp)
+        assert float((orc - ref).abs().max()) <= 1e-4 * max(1.0, scale)
 
 
 def test_batch_shards_are_independent():

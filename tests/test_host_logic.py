@@ -136,7 +136,8 @@ def test_concat_is_fused_into_channel_slices():
 
 def test_transform_plan_matches_reference_formulas():
     tr = FusedClipTransform(16, (0.45,) * 3, (0.225,) * 3, short_side=256, crop=("center", 224))
-    idx, hw, win = tr.plan((3, 64, 1080, 1920))
+    idx, hw, win, flip = tr.plan((3, 64, 1080, 1920))
+    assert flip is False
     assert idx.tolist() == [0, 4, 8, 12, 16, 21, 25, 29, 33, 37, 42, 46, 50, 54, 58, 63]
     assert hw == (256, 455) and win == (16, 116, 224, 224)
     # host tables are the oracle's
@@ -163,3 +164,31 @@ def test_lowering_mvit_dry_run_counts_match_the_reference_macs():
     gmac = sum(x["flops"] for x in plan.meta) / 2e9
     assert abs(gmac - 70.60) < 0.05            # 70.60 GMAC/clip hook-counted on the reference
     assert plan.stats["attention"] == 16 and plan.stats["tcgen05"] == 1 + 16 * 4 + 3 + 1
+
+
+def test_slowfast_pathways_are_scheduled_on_two_lanes():
+    """engine/plan.py lanes: the Slow and Fast pathways are independent until each lateral fusion, so they
+    are enqueued on two CUDA streams (graph branches).  The only cross-lane edges are read-after-write: the
+    first Slow op of stage k+1 waits for the lateral conv of stage k, and the head waits for the Fast pool."""
+    m = PH.slowfast_r50().eval()
+    plan, _ = lower_only(m, TS.slowfast_inputs(torch.zeros(1, 3, 32, 224, 224)))
+    plan._schedule()
+    sc = plan.sched
+    assert sc["lanes"] == [0, 1]
+    names = [n for n, _ in plan.ops]
+    lane = dict(zip(names, plan.op_lane))
+    assert lane["blocks.1.multipathway_blocks.0.res_blocks.0.branch2.conv_a"] == 0
+    assert lane["blocks.1.multipathway_blocks.1.res_blocks.0.branch2.conv_a"] == 1
+    assert lane["blocks.1.multipathway_fusion.conv_fast_to_slow"] == 1
+    edges = [(names[j], names[i]) for i, w in enumerate(sc["waits"]) for j in w]
+    for k in range(4):
+        assert ("blocks.%d.multipathway_fusion.conv_fast_to_slow" % k,
+                "blocks.%d.multipathway_blocks.0.res_blocks.0.branch1" % (k + 1)) in edges
+    assert ("blocks.5.pool.1", "blocks.6.proj") in edges
+    assert len(edges) == 5                       # nothing else crosses lanes
+    # every op that is waited for records an event
+    assert sc["signals"] == {names.index(a) for a, _ in edges}
+    # single-lane models keep one stream
+    p2, _ = lower_only(PH.slow_r50().eval(), torch.zeros(1, 3, 8, 224, 224))
+    p2._schedule()
+    assert p2.sched["lanes"] == [0] and not any(p2.sched["waits"])

@@ -115,6 +115,65 @@ def test_oracle_reproduces_reference_model_goldens(case):
     assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("case", ["c1_x3d_xs", "slow_r50_f16w", "mvit_base_8x112_f16w"])
+def test_oracle_reproduces_f16_grid_goldens(case):
+    """Goldens whose weights and clip lie on the f16 grid (reference and engine multiply identical operands).
+    The BASELINE-batch ones (c2/c3/c4) are pinned by the generator run and used by the GPU suite only - a
+    CPU re-run costs minutes."""
+    g = _gold("model_%s.pt" % case)
+    assert g["f16_grid"]
+    model, inp, _ = TS.build_case(case, PH, g["weight_seed"], g["input_seed"])
+    assert abs(TS.state_checksum(model) - g["state_checksum"]) <= 1e-6 * abs(g["state_checksum"])
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Conv3d, torch.nn.Linear)):
+            assert torch.equal(m.weight, m.weight.half().float())
+    out = oracle_forward(model, inp)
+    ref = g["output"]
+    assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_f16_operand_floor_of_the_reference_arithmetic():
+    """Why the f16 tensor-core path cannot sit inside rtol 1e-3 / atol 1e-4 on ARBITRARY fp32 weights: round
+    only the conv / linear WEIGHTS to f16 (everything else, including every activation, stays in the
+    reference's own fp32 CPU arithmetic) and a large share of the logits already leaves the band - the
+    per-weight error is the same for every output position, so it does not average out in the pooled
+    logits.  Activation rounding alone costs far less.  (X3D-XS, 1 clip; numbers for the other families in
+    profiles/r02_parity.md.)"""
+    import torch.nn.functional as RF
+    import oracle.interp as OI
+
+    class Shim:
+        def __init__(self, rw, rx):
+            self.rw, self.rx = rw, rx
+
+        def __getattr__(self, k):
+            return getattr(RF, k)
+
+        def conv3d(self, x, w, b=None, *a, **k):
+            return RF.conv3d(x.half().float() if self.rx else x, w.half().float() if self.rw else w, b, *a, **k)
+
+        def linear(self, x, w, b=None):
+            return RF.linear(x.half().float() if self.rx else x, w.half().float() if self.rw else w, b)
+
+    hub, kw, B, T, H, W, _ = TS.MODEL_CASES["x3d_xs"]
+    model = TS.randomize_model(getattr(PH, hub)(**kw), seed=1234).eval()
+    clip = TS.synthetic_clip(1, T, H, W, seed=42)
+    ref = oracle_forward(model, clip)
+    scale = max(1.0, float(ref.abs().max()))
+
+    def inside(rw, rx):
+        OI.F = Shim(rw, rx)
+        try:
+            out = oracle_forward(model, clip)
+        finally:
+            OI.F = RF
+        return float(((out - ref).abs() <= 1e-3 * ref.abs() + 1e-4 * scale).float().mean())
+
+    w_only, x_only = inside(True, False), inside(False, True)
+    assert w_only < 0.95, w_only           # f16 weights alone: well outside "all logits in band"
+    assert x_only > w_only                 # activation rounding is the smaller term
+
+
 def test_state_dict_keys_follow_the_reference_naming():
     m = PH.slowfast_r50()
     keys = set(m.state_dict())
