@@ -161,15 +161,75 @@ def gen_transforms():
     print("transforms ok (full-size reference chain took %.2fs)" % dt, flush=True)
 
 
+def gen_layers():
+    """Layer-level goldens from the REAL reference classes (same constructor arguments, weights copied with
+    load_state_dict(strict=True)): ConvReduce3D, Conv2plus1d (both orders), Mlp, MultiScaleAttention,
+    MultiScaleBlock, positional encoding, PatchEmbed, ViT head.  Also pins the oracle on each of them."""
+    import pytorchvideo.layers as RL
+    import pytorchvideo.layers.convolutions as RC
+    import pytorchvideo.models.head as RHd
+    import pytorchvideo.models.stem as RSt
+    from functools import partial
+    import torch.nn as nn
+    from pytorchvideo_b200 import testing as TS
+    from oracle.interp import oracle_forward
+    ln = partial(nn.LayerNorm, eps=1e-6)
+    ref_make = {
+        "conv_reduce_sum": lambda: RC.ConvReduce3D(in_channels=16, out_channels=32, kernel_size=((1, 1, 1), (3, 3, 3), (1, 3, 3)),
+                                                   stride=((1, 1, 1), (1, 1, 1), None), padding=((0, 0, 0), (1, 1, 1), (0, 1, 1)),
+                                                   bias=(False, True, None), reduction_method="sum"),
+        "conv_reduce_cat": lambda: RC.ConvReduce3D(in_channels=16, out_channels=24, kernel_size=((1, 1, 1), (3, 1, 1)),
+                                                   padding=((0, 0, 0), (1, 0, 0)), reduction_method="cat"),
+        "conv2plus1d_xy_first": lambda: RC.create_conv_2plus1d(in_channels=16, out_channels=32, inner_channels=24,
+                                                               conv_xy_first=True, stride=(1, 2, 2)),
+        "conv2plus1d": lambda: RC.create_conv_2plus1d(in_channels=16, out_channels=32, stride=(2, 1, 1)),
+        "mlp": lambda: RL.Mlp(in_features=96, hidden_features=384, out_features=192),
+        "attention_pool_qkv": lambda: RL.MultiScaleAttention(192, num_heads=2, qkv_bias=True, kernel_q=(3, 3, 3), kernel_kv=(3, 3, 3),
+                                                             stride_q=(1, 2, 2), stride_kv=(1, 4, 4), norm_layer=ln, residual_pool=False),
+        "attention_residual_pool_nocls": lambda: RL.MultiScaleAttention(64, num_heads=2, kernel_kv=(3, 3, 3), stride_kv=(1, 2, 2),
+                                                                        has_cls_embed=False, norm_layer=ln, residual_pool=True),
+        "block_widen_pool": lambda: RL.MultiScaleBlock(96, 192, 1, qkv_bias=True, norm_layer=ln, attn_norm_layer=ln,
+                                                       kernel_q=(3, 3, 3), kernel_kv=(3, 3, 3), stride_q=(1, 2, 2), stride_kv=(1, 2, 2)),
+        "block_dim_mul_in_att": lambda: RL.MultiScaleBlock(64, 128, 2, qkv_bias=True, norm_layer=ln, attn_norm_layer=ln,
+                                                           dim_mul_in_att=True, kernel_kv=(3, 3, 3), stride_kv=(1, 2, 2)),
+        "posenc": lambda: RL.SpatioTemporalClsPositionalEncoding(96, (4, 7, 7), sep_pos_embed=True, has_cls=True),
+        "patch_embed": lambda: RSt.create_conv_patch_embed(in_channels=3, out_channels=96, conv_kernel_size=(3, 7, 7),
+                                                           conv_stride=(2, 4, 4), conv_padding=(1, 3, 3)),
+        "vit_head": lambda: RHd.create_vit_basic_head(in_features=192, out_features=40, seq_pool_type="cls"),
+    }
+    out = {}
+    for name in TS.LAYER_CASES:
+        mine, x, thw = TS.build_layer_case(name)
+        ref = ref_make[name]()
+        ref.load_state_dict(mine.state_dict(), strict=True)
+        ref.eval()
+        with torch.no_grad():
+            if thw is None:
+                y_ref, thw_ref = ref(x), None
+                y_orc, thw_orc = oracle_forward(mine, x), None
+            else:
+                y_ref, thw_ref = ref(x, list(thw))
+                y_orc, thw_orc = oracle_forward(mine, x, thw)
+        assert torch.equal(y_ref, y_orc), "oracle != reference on layer case %s" % name
+        assert thw_ref is None or list(thw_ref) == list(thw_orc)
+        out[name] = {"output": y_ref.clone(), "thw_out": None if thw_ref is None else list(thw_ref),
+                     "state_checksum": TS.state_checksum(mine), "input_checksum": TS.tensor_checksum(x)}
+        print("layer %-30s ok  out %s  thw %s" % (name, tuple(y_ref.shape), out[name]["thw_out"]), flush=True)
+    torch.save(out, os.path.join(GOLD, "layers.pt"))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--skip-models", action="store_true")
     ap.add_argument("--skip-transforms", action="store_true")
+    ap.add_argument("--skip-layers", action="store_true")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     if not a.skip_transforms:
         gen_transforms()
+    if not a.skip_layers and not a.only:
+        gen_layers()
     if not a.skip_models:
         gen_models(a.only)

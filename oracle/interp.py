@@ -122,6 +122,12 @@ class Oracle:
         x = self.run(m.activation, x) if m.activation else x
         return self.run(second, x)
 
+    def f_ConvReduce3D(self, m, x):              # layers/convolutions.py:77-85
+        outs = [self.run(c, x) for c in m.convs]
+        if m.reduction_method == "sum":
+            return torch.stack(outs, dim=0).sum(dim=0, keepdim=False)
+        return torch.cat(outs, dim=1)
+
     def f_BottleneckBlock(self, m, x):           # models/resnet.py:1345-1365
         x = self.run(m.act_a, self.run(m.norm_a, self.run(m.conv_a, x)))
         x = self.run(m.act_b, self.run(m.norm_b, self.run(m.conv_b, x)))
@@ -279,11 +285,16 @@ class Oracle:
         return self.run(m.activation, x)
 
 
-def oracle_forward(model, x):
-    """Eval-mode fp32 CPU forward of ``model`` (a module tree, read only) on ``x``."""
+def oracle_forward(model, x, *extra):
+    """Eval-mode fp32 CPU forward of ``model`` (a module tree, read only) on ``x``.  ``extra``: the
+    non-tensor forward arguments of the MViT layer modules (thw_shape); those return (tensor, thw)."""
     with torch.no_grad():
         if isinstance(x, (list, tuple)):
             x = [t.detach().float().cpu() for t in x]
         else:
             x = x.detach().float().cpu()
+        if extra:
+            fn = getattr(Oracle(), "f_" + type(model).__name__)
+            y, thw = fn(model, x, list(extra[0]))
+            return y, list(thw)
         return Oracle().run(model, x)

@@ -41,8 +41,10 @@ def _is_bn(m):
 
 
 class Lowering:
-    def __init__(self, plan: Plan):
+    def __init__(self, plan: Plan, extra=()):
         self.p = plan
+        self.extra = tuple(extra)     # non-tensor forward arguments of the root module (thw_shape)
+        self.aux_out = None           # host-side second result of the root module (pooled thw)
 
     # ---- leaf helpers --------------------------------------------------------------------
     def conv(self, x: TRef, conv: nn.Conv3d, bn=None, act=None, residual=None, name="conv", se_sums=False):
@@ -69,6 +71,43 @@ class Lowering:
 
     def lower_Conv2plus1d(self, m, x, name):
         return self.conv2plus1d(x, m, None, None, None, name)
+
+    def lower_Conv3d(self, m, x, name):
+        return self.conv(x, m, None, None, None, name or "conv")
+
+    def lower_ConvReduce3D(self, m, x, name):
+        # layers/convolutions.py:77-85: parallel convolutions of one input, summed (stack().sum(0)) or
+        # concatenated along channels.  sum: every conv after the first takes the running sum as the fused
+        # residual of its epilogue (fp32 add on the accumulator); cat: producers write channel slices.
+        outs = []
+        acc = None
+        for i, c in enumerate(m.convs):
+            if m.reduction_method == "sum":
+                acc = self.conv(x, c, None, None, acc, "%s.convs.%d" % (name, i))
+            else:
+                outs.append(self.conv(x, c, None, None, None, "%s.convs.%d" % (name, i)))
+        if m.reduction_method == "sum":
+            return acc
+        for o in outs[:-1]:
+            if o.C != o.Cp:
+                raise NotImplementedError("ConvReduce3D(cat): out_channels must be a multiple of 8 for the fused concat")
+        return self.p.concat_channels(outs) if len(outs) > 1 else outs[0]
+
+    def lower_Swish(self, m, x, name):
+        self.p.materialize_input(x)
+        return self.p.emit_act(x, L.ACT_SWISH, name or "swish")
+
+    def lower_ReLU(self, m, x, name):
+        self.p.materialize_input(x)
+        return self.p.emit_act(x, L.ACT_RELU, name or "relu")
+
+    def lower_SqueezeExcitation(self, m, x, name):
+        blk = m.block
+        if type(blk[1]).__name__ != "ReLU" or type(blk[3]).__name__ != "Sigmoid":
+            raise NotImplementedError("SqueezeExcitation variant unsupported")
+        self.p.materialize_input(x)
+        return self.p.emit_se_scale_act(x, blk[0].weight, blk[0].bias, blk[2].weight, blk[2].bias, L.ACT_NONE,
+                                        name or "se")
 
     def pool(self, x, m, name="pool"):
         n = type(m).__name__
@@ -243,15 +282,19 @@ class Lowering:
 
 
 class CompiledModel:
-    """A frozen (model, input shapes) plan: static input/output buffers + one CUDA graph."""
+    """A frozen (model, input shapes) plan: static input/output buffers + one CUDA graph.
 
-    def __init__(self, model, example_inputs, dtype="f16", use_tcgen05=True, use_graph=True):
+    Inputs are 5-D clips (B, C, T, H, W) - or, for the MViT layer modules, token tensors (B, N, C) / (B, C).
+    ``extra`` carries non-tensor forward arguments (the ``thw_shape`` of MultiScaleBlock / MultiScaleAttention);
+    a lowering handler may leave a second, host-side result in ``Lowering.aux_out`` (the pooled thw)."""
+
+    def __init__(self, model, example_inputs, dtype="f16", use_tcgen05=True, use_graph=True, extra=()):
         L.require_device()
         multi = isinstance(example_inputs, (list, tuple))
         ins = list(example_inputs) if multi else [example_inputs]
         for t in ins:
-            if t.dim() != 5:
-                raise RuntimeError("expected 5-D (B, C, T, H, W) input, got %s" % (tuple(t.shape),))
+            if t.dim() not in (2, 3, 5):
+                raise RuntimeError("expected a 5-D (B, C, T, H, W) clip or a (B, N, C) token tensor, got %s" % (tuple(t.shape),))
         device = ins[0].device
         if device.type != "cuda":
             raise RuntimeError("pytorchvideo_b200 has no CPU path: inputs must be CUDA tensors")
@@ -260,15 +303,12 @@ class CompiledModel:
         self.plan = Plan(device, dt, use_tcgen05)
         self.static_in = [torch.empty(t.shape, dtype=t.dtype if t.dtype in (torch.float16, torch.float32) else torch.float32,
                                       device=device) for t in ins]
-        low = Lowering(self.plan)
-        xs = [self.plan.emit_input_ncdhw(s, s.shape[1], 4 if s.shape[1] <= 4 else (s.shape[1] + 7) // 8 * 8)
-              for s in self.static_in]
+        low = Lowering(self.plan, extra)
+        xs = [_emit_input(self.plan, s) for s in self.static_in]
         out = low.lower(model, xs if multi else xs[0], "")
-        if isinstance(out, TRef):
-            out = self.plan.emit_to_ncdhw(out, "output.to_ncdhw")
-        if isinstance(out, list):
-            raise NotImplementedError("models returning a list are unsupported")
+        out = _emit_output(self.plan, out, tokens=ins[0].dim() != 5)
         self.out_buf, self.out_shape = out
+        self.aux = low.aux_out
         self.plan.finalize()
         self.graph = None
         self.use_graph = use_graph
@@ -327,22 +367,38 @@ class CompiledModel:
         return self.output_view()
 
 
-def compile_model(model, example_inputs, dtype="f16", use_tcgen05=True, use_graph=True):
-    return CompiledModel(model, example_inputs, dtype, use_tcgen05, use_graph)
+def _emit_input(plan, t):
+    if t.dim() == 5:
+        return plan.emit_input_ncdhw(t, t.shape[1], 4 if t.shape[1] <= 4 else (t.shape[1] + 7) // 8 * 8)
+    return plan.emit_input_tokens(t)
 
 
-def lower_only(model, example_inputs, dtype="f16", use_tcgen05=True):
+def _emit_output(plan, out, tokens):
+    if isinstance(out, TRef):
+        if tokens or (out.T == 1 and out.H == 1 and getattr(out, "is_tokens", False)):
+            return plan.emit_to_tokens(out, "output.to_tokens", squeeze=getattr(out, "squeeze", False))
+        return plan.emit_to_ncdhw(out, "output.to_ncdhw")
+    if isinstance(out, list):
+        raise NotImplementedError("models returning a list are unsupported")
+    return out
+
+
+def compile_model(model, example_inputs, dtype="f16", use_tcgen05=True, use_graph=True, extra=()):
+    return CompiledModel(model, example_inputs, dtype, use_tcgen05, use_graph, extra)
+
+
+def lower_only(model, example_inputs, dtype="f16", use_tcgen05=True, extra=()):
     """Host-side dry run (works without a GPU): build the plan on the CPU and return
     (plan, output_shape).  Nothing can be executed; used by the CPU test-suite to check the
     lowering, shape inference, channel padding, concat fusion and algorithm selection."""
     multi = isinstance(example_inputs, (list, tuple))
     ins = list(example_inputs) if multi else [example_inputs]
     plan = Plan("cpu", {"f16": L.PV_F16, "f32": L.PV_F32}[dtype], use_tcgen05)
-    xs = [plan.emit_input_ncdhw(torch.empty(t.shape, dtype=torch.float32), t.shape[1],
-                                4 if t.shape[1] <= 4 else (t.shape[1] + 7) // 8 * 8) for t in ins]
-    out = Lowering(plan).lower(model, xs if multi else xs[0], "")
-    if isinstance(out, TRef):
-        out = plan.emit_to_ncdhw(out, "output.to_ncdhw")
+    xs = [_emit_input(plan, torch.empty(t.shape, dtype=torch.float32)) for t in ins]
+    low = Lowering(plan, extra)
+    out = low.lower(model, xs if multi else xs[0], "")
+    out = _emit_output(plan, out, tokens=ins[0].dim() != 5)
+    plan.aux = low.aux_out
     return plan, out[1]
 
 
@@ -352,59 +408,77 @@ def lower_only(model, example_inputs, dtype="f16", use_tcgen05=True):
 from . import plan as PL  # noqa: E402
 
 
-def _lower_mvit_block(low, blk, x, thw, name):
+def _check_thw(x, thw, has_cls, name):
+    T, H, W = (int(v) for v in thw)
+    if x.npos != (1 if has_cls else 0) + T * H * W:
+        raise RuntimeError("%s: %d tokens do not match thw_shape %s%s" % (name, x.npos, (T, H, W), " + cls" if has_cls else ""))
+    return (T, H, W)
+
+
+def _lower_mvit_attention(low, attn, xn, thw, name, residual=None):
+    """MultiScaleAttention.forward (layers/attention.py:467-544) on normalised tokens ``xn``:
+    returns (proj(attention) [+ residual fused into the GEMM epilogue], pooled q thw)."""
     p = low.p
-    attn = blk.attn
     if attn.pool_first:
         raise NotImplementedError("pool_first=True is not used by any hub MViT and has no B200 lowering")
-    if getattr(blk, "norm1_is_batchnorm_1d", False) or getattr(blk, "norm2_is_batchnorm_1d", False):
-        raise NotImplementedError("batchnorm MViT variant unsupported")
     has_cls = attn.has_cls_embed
     heads, dim_att = attn.num_heads, attn.dim_out
-    xn = PL.emit_layernorm(p, x, blk.norm1, name + ".norm1")
+    thw = _check_thw(xn, thw, has_cls, name)
     # q/k/v projections as ONE GEMM over concatenated weights; q, k, v are channel slices of its output
     if attn.separate_qkv:
         w = torch.cat([attn.q.weight, attn.k.weight, attn.v.weight], 0)
         b = None if attn.q.bias is None else torch.cat([attn.q.bias, attn.k.bias, attn.v.bias], 0)
     else:
         w, b = attn.qkv.weight, attn.qkv.bias
-    qkv = PL.emit_linear(p, xn, w, b, L.ACT_NONE, None, name + ".attn.qkv")
+    qkv = PL.emit_linear(p, xn, w, b, L.ACT_NONE, None, name + ".qkv")
     q, k, v = (PL.channel_slice(qkv, i * dim_att, dim_att) for i in range(3))
     thw_q = thw
     if getattr(attn, "pool_q", None) is not None:
-        q, thw_q = PL.emit_token_pool(p, q, thw, attn.pool_q, getattr(attn, "norm_q", None), heads, has_cls, name + ".attn.pool_q")
+        q, thw_q = PL.emit_token_pool(p, q, thw, attn.pool_q, getattr(attn, "norm_q", None), heads, has_cls, name + ".pool_q")
     if getattr(attn, "pool_k", None) is not None:
-        k, _ = PL.emit_token_pool(p, k, thw, attn.pool_k, getattr(attn, "norm_k", None), heads, has_cls, name + ".attn.pool_k")
+        k, _ = PL.emit_token_pool(p, k, thw, attn.pool_k, getattr(attn, "norm_k", None), heads, has_cls, name + ".pool_k")
     if getattr(attn, "pool_v", None) is not None:
-        v, _ = PL.emit_token_pool(p, v, thw, attn.pool_v, getattr(attn, "norm_v", None), heads, has_cls, name + ".attn.pool_v")
-    o = PL.emit_attention(p, q, k, v, heads, attn.scale, attn.residual_pool, name + ".attn.core")
+        v, _ = PL.emit_token_pool(p, v, thw, attn.pool_v, getattr(attn, "norm_v", None), heads, has_cls, name + ".pool_v")
+    o = PL.emit_attention(p, q, k, v, heads, attn.scale, attn.residual_pool, name + ".core")
+    x = PL.emit_linear(p, o, attn.proj.weight, attn.proj.bias, L.ACT_NONE, residual, name + ".proj")
+    return x, thw_q
+
+
+def _lower_mlp(low, mlp, xn, name, residual=None):
+    # layers/attention.py:102-114: fc1 -> act -> fc2 (dropout = identity in eval)
+    act = _act_code(mlp.act)
+    if act == L.ACT_GELU and getattr(mlp.act, "approximate", "none") != "none":
+        raise NotImplementedError("Mlp activation must be the exact (erf) GELU")
+    h = PL.emit_linear(low.p, xn, mlp.fc1.weight, mlp.fc1.bias, act, None, name + ".fc1")
+    return PL.emit_linear(low.p, h, mlp.fc2.weight, mlp.fc2.bias, L.ACT_NONE, residual, name + ".fc2")
+
+
+def _lower_mvit_block(low, blk, x, thw, name):
+    """MultiScaleBlock.forward (layers/attention.py:729-757); DropPath is the identity in eval."""
+    p = low.p
+    attn = blk.attn
+    if getattr(blk, "norm1_is_batchnorm_1d", False) or getattr(blk, "norm2_is_batchnorm_1d", False):
+        raise NotImplementedError("batchnorm MViT variant unsupported")
+    has_cls = attn.has_cls_embed
+    thw = _check_thw(x, thw, has_cls, name)
+    xn = PL.emit_layernorm(p, x, blk.norm1, name + ".norm1")
     widen = blk.dim != blk.dim_out
     if blk.dim_mul_in_att and widen:
         x = PL.emit_linear(p, xn, blk.proj.weight, blk.proj.bias, L.ACT_NONE, None, name + ".proj")
     x_res = x
     if getattr(blk, "pool_skip", None) is not None:
         x_res, _ = PL.emit_token_pool(p, x, thw, blk.pool_skip, None, 1, has_cls, name + ".pool_skip")
-    x = PL.emit_linear(p, o, attn.proj.weight, attn.proj.bias, L.ACT_NONE, x_res, name + ".attn.proj")
+    x, thw_q = _lower_mvit_attention(low, attn, xn, thw, name + ".attn", residual=x_res)
     xn2 = PL.emit_layernorm(p, x, blk.norm2, name + ".norm2")
-    if type(blk.mlp.act).__name__ != "GELU" or getattr(blk.mlp.act, "approximate", "none") != "none":
-        raise NotImplementedError("Mlp activation must be exact GELU")
-    h = PL.emit_linear(p, xn2, blk.mlp.fc1.weight, blk.mlp.fc1.bias, L.ACT_GELU, None, name + ".mlp.fc1")
     if (not blk.dim_mul_in_att) and widen:
         x = PL.emit_linear(p, xn2, blk.proj.weight, blk.proj.bias, L.ACT_NONE, None, name + ".proj")
-    x = PL.emit_linear(p, h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, L.ACT_NONE, x, name + ".mlp.fc2")
+    x = _lower_mlp(low, blk.mlp, xn2, name + ".mlp", residual=x)
     return x, thw_q
 
 
-def _lower_mvit(self, m, x, name):
-    p = self.p
-    pe = m.patch_embed
-    if type(pe).__name__ != "PatchEmbed":
-        raise NotImplementedError("MViT without a conv patch embedding is unsupported")
-    x = self.conv(x, pe.patch_model, None, None, None, "patch_embed.patch_model")
-    enc = m.cls_positional_encoding
-    T, H, W = enc.patch_embed_shape()
-    if (x.T, x.H, x.W) != (T, H, W):
-        raise RuntimeError("input clip gives a %s patch grid but the model was built for %s" % ((x.T, x.H, x.W), (T, H, W)))
+def _pos_table(enc):
+    """Rows of the additive table of SpatioTemporalClsPositionalEncoding.forward
+    (layers/positional_encoding.py:112-136); row 0 also carries the cls token itself."""
     has_cls = bool(enc.cls_embed_on)
     with torch.no_grad():
         if enc.sep_pos_embed:
@@ -417,6 +491,44 @@ def _lower_mvit(self, m, x, name):
         pos = pos[0].clone()
         if has_cls:
             pos[0] += enc.cls_token.detach().float().cpu()[0, 0]
+    return pos, has_cls
+
+
+def _lower_vit_head(low, head, x, name="head"):
+    """VisionTransformerBasicHead.forward (models/head.py:521-535) on (already normalised) tokens."""
+    p = low.p
+    mode = head.sequence_pool.mode if head.sequence_pool is not None else None
+    if mode == "cls":
+        if x.npos > 1:
+            x = TRef(x.buf, x.N, 1, 1, 1, x.C, Cp=x.C, ch_off=x.ch_off, row_stride=x.npos * x.row_stride)
+    elif mode == "mean":
+        x = p.emit_pool(x, L.POOL_AVG, (1, 1, x.W), (1, 1, x.W), (0, 0, 0), name + ".sequence_pool")
+    else:
+        raise NotImplementedError("sequence_pool=None MViT heads are unsupported")
+    x = PL.emit_linear(p, x, head.proj.weight, head.proj.bias, L.ACT_NONE, None, name + ".proj")
+    act = head.activation
+    softmax = False
+    if act is not None:
+        if type(act).__name__ == "Softmax":
+            softmax = True
+        elif type(act).__name__ == "Sigmoid":
+            x = p.emit_act(x, L.ACT_SIGMOID, name + ".activation")
+        else:
+            raise NotImplementedError("head activation unsupported")
+    return p.emit_head_reduce(x, softmax, name + ".output")
+
+
+def _lower_mvit(self, m, x, name):
+    p = self.p
+    pe = m.patch_embed
+    if type(pe).__name__ != "PatchEmbed":
+        raise NotImplementedError("MViT without a conv patch embedding is unsupported")
+    x = self.conv(x, pe.patch_model, None, None, None, "patch_embed.patch_model")
+    enc = m.cls_positional_encoding
+    T, H, W = enc.patch_embed_shape()
+    if (x.T, x.H, x.W) != (T, H, W):
+        raise RuntimeError("input clip gives a %s patch grid but the model was built for %s" % ((x.T, x.H, x.W), (T, H, W)))
+    pos, has_cls = _pos_table(enc)
     x = PL.emit_pos_cls(p, x, pos, has_cls, "cls_positional_encoding")
     thw = (T, H, W)
     for i, blk in enumerate(m.blocks):
@@ -428,29 +540,73 @@ def _lower_mvit(self, m, x, name):
         raise NotImplementedError("MViT head %s unsupported" % type(head).__name__)
     mode = head.sequence_pool.mode if head.sequence_pool is not None else None
     ne = m.norm_embed
-    if mode == "cls":
-        # only the cls row reaches the head: normalise just those B rows
-        if type(ne).__name__ == "LayerNorm":
+    if type(ne).__name__ == "LayerNorm":
+        if mode == "cls":      # only the cls row reaches the head: normalise just those B rows
             x = PL.emit_layernorm(p, x, ne, "norm_embed", rows_stride=x.npos * x.row_stride, rows=x.N)
         else:
-            x = TRef(x.buf, x.N, 1, 1, 1, x.C, Cp=x.C, ch_off=x.ch_off, row_stride=x.npos * x.row_stride)
-    elif mode == "mean":
-        if type(ne).__name__ == "LayerNorm":
             x = PL.emit_layernorm(p, x, ne, "norm_embed")
-        x = p.emit_pool(x, L.POOL_AVG, (1, 1, x.W), (1, 1, x.W), (0, 0, 0), "head.sequence_pool")
+    return _lower_vit_head(self, head, x, "head")
+
+
+# ---- layer-level entry points: the MViT building blocks as stand-alone modules (token tensors in / out) ----
+def _tok_out(x, squeeze=False):
+    x.is_tokens = True
+    x.squeeze = squeeze
+    return x
+
+
+def _lower_block_module(self, m, x, name):
+    if len(self.extra) != 1:
+        raise RuntimeError("MultiScaleBlock.forward(x, thw_shape): thw_shape is required")
+    y, thw = _lower_mvit_block(self, m, x, self.extra[0], name or "block")
+    self.aux_out = list(thw)
+    return _tok_out(y)
+
+
+def _lower_attention_module(self, m, x, name):
+    if len(self.extra) != 1:
+        raise RuntimeError("MultiScaleAttention.forward(x, thw_shape): thw_shape is required")
+    y, thw = _lower_mvit_attention(self, m, x, self.extra[0], name or "attn")
+    self.aux_out = list(thw)
+    return _tok_out(y)
+
+
+def _lower_mlp_module(self, m, x, name):
+    return _tok_out(_lower_mlp(self, m, x, name or "mlp"), squeeze=True)
+
+
+def _lower_posenc_module(self, m, x, name):
+    pos, has_cls = _pos_table(m)
+    T, H, W = m.patch_embed_shape()
+    if x.npos != T * H * W:
+        raise RuntimeError("expected %d patch tokens, got %d" % (T * H * W, x.npos))
+    return _tok_out(PL.emit_pos_cls(self.p, x, pos, has_cls, name or "cls_positional_encoding"))
+
+
+def _lower_patch_embed_module(self, m, x, name):
+    # stem.py:289-292: conv then flatten(2).transpose(1, 2) - the NDHWC conv output already is (B, THW, C)
+    y = self.conv(x, m.patch_model, None, None, None, (name + "." if name else "") + "patch_model")
+    t = TRef(y.buf, y.N, 1, 1, y.npos, y.C, Cp=y.Cp, ch_off=y.ch_off, row_stride=y.row_stride)
+    return _tok_out(t)
+
+
+def _lower_vit_head_module(self, m, x, name):
+    return _lower_vit_head(self, m, x, name or "head")
+
+
+def _lower_sequence_pool_module(self, m, x, name):
+    if m.mode == "cls":
+        t = TRef(x.buf, x.N, 1, 1, 1, x.C, Cp=x.C, ch_off=x.ch_off, row_stride=x.npos * x.row_stride)
     else:
-        raise NotImplementedError("sequence_pool=None MViT heads are unsupported")
-    x = PL.emit_linear(p, x, head.proj.weight, head.proj.bias, L.ACT_NONE, None, "head.proj")
-    act = head.activation
-    softmax = False
-    if act is not None:
-        if type(act).__name__ == "Softmax":
-            softmax = True
-        elif type(act).__name__ == "Sigmoid":
-            x = p.emit_act(x, L.ACT_SIGMOID, "head.activation")
-        else:
-            raise NotImplementedError("head activation unsupported")
-    return p.emit_head_reduce(x, softmax, "head.output")
+        t = self.p.emit_pool(x, L.POOL_AVG, (1, 1, x.W), (1, 1, x.W), (0, 0, 0), name or "sequence_pool")
+    return _tok_out(t, squeeze=True)
 
 
+Lowering.lower_MultiScaleBlock = _lower_block_module
+Lowering.lower_MultiScaleAttention = _lower_attention_module
+Lowering.lower_Mlp = _lower_mlp_module
+Lowering.lower_SpatioTemporalClsPositionalEncoding = _lower_posenc_module
+Lowering.lower_PatchEmbed = _lower_patch_embed_module
+Lowering.lower_VisionTransformerBasicHead = _lower_vit_head_module
+Lowering.lower_SequencePool = _lower_sequence_pool_module
 Lowering.lower_MultiscaleVisionTransformers = _lower_mvit

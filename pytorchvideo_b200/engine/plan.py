@@ -509,6 +509,47 @@ class Plan:
         self.add(name, fn, reads=(x,), writes=(out,))
         return out, x.shape5()
 
+    def emit_input_tokens(self, static_in):
+        """static_in: torch tensor [B, N, C] (or [B, C]) f32|f16, contiguous: token-major network input
+        (the layout MViT blocks exchange).  One cast/copy launch into the plan's dtype."""
+        shp = tuple(static_in.shape)
+        B, N, Cc = (shp[0], 1, shp[1]) if len(shp) == 2 else shp
+        if Cc % 8 and self.dt == L.PV_F16:
+            raise RuntimeError("token width %d is not a multiple of 8 (16-byte rows are required in f16 mode)" % Cc)
+        x = self.new_tensor(B, 1, 1, N, Cc, Cp=Cc)
+        src_dt = L.PV_F32 if static_in.dtype == torch.float32 else L.PV_F16
+        total = B * N * Cc
+        lib = self.lib
+
+        def fn(stream):
+            # a [1, 1, 1, 1, total] "clip" with one channel: the layout conversion degenerates to a cast
+            L.check(lib.pv_ncdhw_to_ndhwc(static_in.data_ptr(), src_dt, x.ptr(), x.dt, 1, 1, 1, 1, total, 1, 1, stream),
+                    "pv_ncdhw_to_ndhwc(tokens)")
+        self.add("tokens_in", fn, "other", 0.0, total * (static_in.element_size() + _ESIZE[self.dt]), reads=(), writes=(x,))
+        return x
+
+    def emit_to_tokens(self, x, name="to_tokens", squeeze=False):
+        """Token TRef [B, N, C] -> f32 output buffer laid out (B, N, C) (or (B, C) with squeeze)."""
+        self.materialize_input(x)
+        lib = self.lib
+        if x.row_stride != x.C or x.Cp != x.C:
+            dense = self.new_tensor(x.N, 1, 1, x.npos, x.C, Cp=x.C)
+            src = x
+
+            def fn_c(stream):
+                L.check(lib.pv_copy_rows(src.ptr(), dense.ptr(), src.dt, src.N * src.npos, src.C, src.row_stride,
+                                         dense.row_stride, stream), "pv_copy_rows(%s)" % name)
+            self.add(name + ".dense", fn_c, reads=(src,), writes=(dense,))
+            x = dense
+        total = x.N * x.npos * x.C
+        out = self.new_buf(total, L.PV_F32)
+
+        def fn(stream):
+            L.check(lib.pv_ndhwc_to_ncdhw(x.ptr(), x.dt, 1, out.tensor.data_ptr(), 1, 1, 1, 1, total, stream),
+                    "pv_ndhwc_to_ncdhw(%s)" % name)
+        self.add(name, fn, reads=(x,), writes=(out,))
+        return out, ((x.N, x.C) if squeeze and x.npos == 1 else (x.N, x.npos, x.C))
+
     def concat_channels(self, parts):
         """Fuse torch.cat(parts, dim=1): retarget every part into one wide buffer (no copy)."""
         p0 = parts[0]

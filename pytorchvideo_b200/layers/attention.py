@@ -1,4 +1,6 @@
-"""MViT building blocks as parameter containers (reference layers/attention.py).
+"""MViT building blocks (reference layers/attention.py): parameter containers whose ``forward`` runs the
+B200 engine - ``Mlp(x)``, ``MultiScaleAttention(x, thw_shape) -> (x, thw)``, ``MultiScaleBlock(x, thw_shape)
+-> (x, thw)`` on CUDA token tensors (B, N, C), lowered by engine/lower.py (no ATen forward).
 
 Attribute names / registration order follow the reference so state_dict keys match, including the
 ``_attention_pool_{q,k,v}`` wrappers that re-register the pool conv and norm of each branch (the
@@ -6,10 +8,11 @@ same Parameter appears under ``attn.pool_k.weight`` and ``attn._attention_pool_k
 import numpy
 import torch.nn as nn
 
+from ..module import B200Module
 from .drop_path import DropPath
 
 
-class Mlp(nn.Module):
+class Mlp(B200Module):
     """fc1 -> act (exact-erf GELU) -> fc2 (attention.py:51-114)."""
 
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, dropout_rate=0.0,
@@ -49,7 +52,7 @@ def _prod(v):
     return p
 
 
-class MultiScaleAttention(nn.Module):
+class MultiScaleAttention(B200Module):
     """Pooled multi-head attention (attention.py:215-544)."""
     _version = 3
 
@@ -120,7 +123,7 @@ class MultiScaleAttention(nn.Module):
                                       error_msgs)
 
 
-class MultiScaleBlock(nn.Module):
+class MultiScaleBlock(B200Module):
     """norm1 -> attention (+ pooled skip) -> norm2 -> Mlp (+ skip / dim-expanding proj), attention.py:578-757."""
 
     def __init__(self, dim, dim_out, num_heads, mlp_ratio=4.0, qkv_bias=False, dropout_rate=0.0, droppath_rate=0.0,

@@ -5,8 +5,10 @@ from typing import Tuple
 import torch
 import torch.nn as nn
 
+from ..module import B200Module
 
-class SpatioTemporalClsPositionalEncoding(nn.Module):
+
+class SpatioTemporalClsPositionalEncoding(B200Module):
     """Parameters: cls_token, pos_embed_spatial [1,HW,C], pos_embed_temporal [1,T,C],
     pos_embed_class [1,1,C] (or one pos_embed when sep_pos_embed=False).  On device the engine adds
     spatial[i % HW] + temporal[i // HW] to patch token i and prepends cls_token + pos_embed_class."""

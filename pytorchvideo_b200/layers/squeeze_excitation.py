@@ -1,7 +1,9 @@
 import torch.nn as nn
 
+from ..module import B200Module
 
-class SqueezeExcitation(nn.Module):
+
+class SqueezeExcitation(B200Module):
     """Parameter container for the fvcore SqueezeExcitation used by X3D
     (reference models/x3d.py:190-198; fvcore is not vendored - its structure is pinned by
     layers/accelerator/mobile_cpu/attention.py:62-104 and by hub checkpoint keys

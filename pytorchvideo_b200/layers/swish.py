@@ -1,9 +1,7 @@
-import torch.nn as nn
+from ..module import B200Module
 
 
-class Swish(nn.Module):
-    """x * sigmoid(x) (reference layers/swish.py:7-28).  A marker module: the engine fuses it
-    into the producing kernel's epilogue (PV_ACT_SWISH); it owns no parameters."""
-
-    def forward(self, x):
-        raise RuntimeError("Swish is fused by the B200 engine; call the enclosing block instead")
+class Swish(B200Module):
+    """x * sigmoid(x) (reference layers/swish.py:7-28).  Inside a block the engine fuses it into the
+    producing kernel's epilogue (PV_ACT_SWISH); called on its own it is one elementwise launch
+    (engine/lower.py lower_Swish).  It owns no parameters."""

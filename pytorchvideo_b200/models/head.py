@@ -41,7 +41,7 @@ def create_res_basic_head(*, in_features, out_features, pool=nn.AvgPool3d, outpu
     )
 
 
-class SequencePool(nn.Module):
+class SequencePool(B200Module):
     """'cls': first token, 'mean': token average (head.py:11-36)."""
 
     def __init__(self, mode):

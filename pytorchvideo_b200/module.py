@@ -23,7 +23,7 @@ class B200Module(nn.Module):
             v += t._version + (t.data_ptr() & 0xFFFFF)
         return v
 
-    def _pv_compiled(self, x):
+    def _pv_compiled(self, x, extra=()):
         from .engine import compile_model
         ins = x if isinstance(x, (list, tuple)) else [x]
         for t in ins:
@@ -35,7 +35,7 @@ class B200Module(nn.Module):
         if self.training:
             raise RuntimeError("pytorchvideo_b200 is an eval-mode forward engine: call model.eval() first")
         key = (tuple((tuple(t.shape), t.dtype, t.device.index) for t in ins), config.get_precision(),
-               config.get_use_tcgen05(), config.get_use_graph(), self._pv_fingerprint())
+               config.get_use_tcgen05(), config.get_use_graph(), tuple(extra), self._pv_fingerprint())
         cache = self.__dict__.setdefault("_pv_cache", {})
         cm = cache.pop(key, None)
         if cm is None:
@@ -45,7 +45,7 @@ class B200Module(nn.Module):
             while len(cache) >= self._PV_CACHE_PLANS:
                 del cache[next(iter(cache))]       # least recently used
             cm = compile_model(self, list(ins) if isinstance(x, (list, tuple)) else x, config.get_precision(),
-                               config.get_use_tcgen05(), config.get_use_graph())
+                               config.get_use_tcgen05(), config.get_use_graph(), extra=extra)
         cache[key] = cm                            # (re)insert at the most-recently-used end
         return cm
 
@@ -53,6 +53,10 @@ class B200Module(nn.Module):
         self.__dict__.pop("_pv_tensors", None)     # .to()/.cuda() may replace parameter objects
         return super()._apply(fn, *a, **k)
 
-    def forward(self, x):
-        cm = self._pv_compiled(x)
-        return cm(x).clone()
+    def forward(self, x, *extra):
+        """``extra``: non-tensor forward arguments (MViT blocks: ``thw_shape``).  Modules with a second,
+        host-side result (the pooled thw) return ``(tensor, aux)`` like the reference."""
+        extra = tuple(tuple(int(v) for v in e) if isinstance(e, (list, tuple)) else e for e in extra)
+        cm = self._pv_compiled(x, extra)
+        out = cm(x).clone()
+        return out if cm.aux is None else (out, list(cm.aux))

@@ -139,3 +139,60 @@ def build_case(case, hub_module, weight_seed=1234, input_seed=42):
     model = randomize_model(getattr(hub_module, hub)(**kw), seed=weight_seed, f16_weights=grid).eval()
     clip = synthetic_clip(B, T, H, W, seed=input_seed, f16_values=grid)
     return model, (slowfast_inputs(clip) if is_sf else clip), is_sf
+
+
+
+# ---- layer-level cases (tests/golden/layers.pt): name -> (builder, input shape, thw or None) --------------------
+def _layer_builders():
+    import torch.nn as nn
+    from functools import partial
+    from .layers.attention import Mlp, MultiScaleAttention, MultiScaleBlock
+    from .layers.convolutions import ConvReduce3D, create_conv_2plus1d
+    from .layers.positional_encoding import SpatioTemporalClsPositionalEncoding
+    from .models.head import create_vit_basic_head
+    from .models.stem import create_conv_patch_embed
+    ln = partial(nn.LayerNorm, eps=1e-6)
+    return {
+        "conv_reduce_sum": (lambda: ConvReduce3D(in_channels=16, out_channels=32, kernel_size=((1, 1, 1), (3, 3, 3), (1, 3, 3)),
+                                                 stride=((1, 1, 1), (1, 1, 1), None), padding=((0, 0, 0), (1, 1, 1), (0, 1, 1)),
+                                                 bias=(False, True, None), reduction_method="sum"), (2, 16, 4, 12, 12), None),
+        "conv_reduce_cat": (lambda: ConvReduce3D(in_channels=16, out_channels=24, kernel_size=((1, 1, 1), (3, 1, 1)),
+                                                 padding=((0, 0, 0), (1, 0, 0)), reduction_method="cat"), (2, 16, 4, 12, 12), None),
+        "conv2plus1d_xy_first": (lambda: create_conv_2plus1d(in_channels=16, out_channels=32, inner_channels=24, conv_xy_first=True,
+                                                             stride=(1, 2, 2)), (2, 16, 4, 12, 12), None),
+        "conv2plus1d": (lambda: create_conv_2plus1d(in_channels=16, out_channels=32, stride=(2, 1, 1)), (2, 16, 4, 12, 12), None),
+        "mlp": (lambda: Mlp(in_features=96, hidden_features=384, out_features=192), (2, 50, 96), None),
+        # MViT-B block 1 geometry at a small grid: Q pooled (1,2,2), K/V pooled (1,4,4), 2 heads of 96
+        "attention_pool_qkv": (lambda: MultiScaleAttention(192, num_heads=2, qkv_bias=True, kernel_q=(3, 3, 3), kernel_kv=(3, 3, 3),
+                                                           stride_q=(1, 2, 2), stride_kv=(1, 4, 4), norm_layer=ln,
+                                                           residual_pool=False), (2, 1 + 4 * 8 * 8, 192), (4, 8, 8)),
+        "attention_residual_pool_nocls": (lambda: MultiScaleAttention(64, num_heads=2, kernel_kv=(3, 3, 3), stride_kv=(1, 2, 2),
+                                                                      has_cls_embed=False, norm_layer=ln, residual_pool=True),
+                                          (2, 2 * 8 * 8, 64), (2, 8, 8)),
+        "block_widen_pool": (lambda: MultiScaleBlock(96, 192, 1, qkv_bias=True, norm_layer=ln, attn_norm_layer=ln,
+                                                     kernel_q=(3, 3, 3), kernel_kv=(3, 3, 3), stride_q=(1, 2, 2),
+                                                     stride_kv=(1, 2, 2)), (2, 1 + 4 * 8 * 8, 96), (4, 8, 8)),
+        "block_dim_mul_in_att": (lambda: MultiScaleBlock(64, 128, 2, qkv_bias=True, norm_layer=ln, attn_norm_layer=ln,
+                                                         dim_mul_in_att=True, kernel_kv=(3, 3, 3), stride_kv=(1, 2, 2)),
+                                 (2, 1 + 2 * 8 * 8, 64), (2, 8, 8)),
+        "posenc": (lambda: SpatioTemporalClsPositionalEncoding(96, (4, 7, 7), sep_pos_embed=True, has_cls=True), (2, 4 * 7 * 7, 96), None),
+        "patch_embed": (lambda: create_conv_patch_embed(in_channels=3, out_channels=96, conv_kernel_size=(3, 7, 7),
+                                                        conv_stride=(2, 4, 4), conv_padding=(1, 3, 3)), (2, 3, 8, 56, 56), None),
+        "vit_head": (lambda: create_vit_basic_head(in_features=192, out_features=40, seq_pool_type="cls"), (3, 17, 192), None),
+    }
+
+
+LAYER_CASES = tuple(sorted(["conv_reduce_sum", "conv_reduce_cat", "conv2plus1d_xy_first", "conv2plus1d", "mlp",
+                            "attention_pool_qkv", "attention_residual_pool_nocls", "block_widen_pool",
+                            "block_dim_mul_in_att", "posenc", "patch_embed", "vit_head"]))
+
+
+def build_layer_case(name, seed=77):
+    """(module, input, thw) with weights AND input on the f16 grid (same operands for reference and engine)."""
+    make, shape, thw = _layer_builders()[name]
+    torch.manual_seed(seed)
+    m = randomize_model(make(), seed=seed, f16_weights=True).eval()
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + 1)
+    x = f16_exact(torch.randn(shape, generator=g) if len(shape) == 3 else torch.rand(shape, generator=g))
+    return m, x, thw

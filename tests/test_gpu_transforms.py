@@ -76,3 +76,43 @@ def test_single_ops_and_properties():
     # identity resize is exact
     same = T.ShortSideScale(10)(xd).cpu()
     assert torch.equal(same, x)
+
+
+def test_train_chain_matches_reference_goldens_under_fixed_seed():
+    """create_video_transform(mode="train") = ONE kernel launch; random short side, crop offsets and the flip are
+    drawn on the host from torch's global RNG in the reference's order, so under the reference's seed the fused
+    output equals the REAL reference chain's (tests/golden/transforms.pt["train_small"])."""
+    from pytorchvideo_b200.transforms import create_video_transform
+    for c in torch.load(os.path.join(GOLD, "transforms.pt"), weights_only=False)["train_small"]:
+        clip = TS.synthetic_u8_clip(c["T"], c["H"], c["W"], seed=c["seed"]).cuda()
+        for dt, rtol, atol in ((torch.float32, 1e-5, 2e-6), (torch.float16, 1e-3, 1e-4)):
+            tr = create_video_transform(mode="train", num_samples=c["n"], min_size=c["min_size"], max_size=c["max_size"],
+                                        crop_size=c["crop"], out_dtype=dt)
+            torch.manual_seed(c["rng_seed"])
+            out = tr(clip).float().cpu()
+            assert out.shape == c["out"].shape
+            assert torch.allclose(out, c["out"], rtol=rtol, atol=atol), (c["draws"], float((out - c["out"]).abs().max()))
+
+
+def test_random_crop_and_short_side_modules_follow_torchvision_under_seed():
+    import torchvision.transforms as TV
+    from pytorchvideo_b200 import transforms as T
+    x = torch.rand(3, 5, 40, 60, generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(123)
+    ref = TV.RandomCrop(24)(x)
+    torch.manual_seed(123)
+    got = T.RandomCropVideo(24)(x.cuda()).cpu()
+    assert torch.equal(got, ref)
+    torch.manual_seed(7)
+    size = torch.randint(20, 31, (1,)).item()
+    torch.manual_seed(7)
+    got = T.RandomShortSideScale(20, 30)(x.cuda()).cpu()
+    np.testing.assert_allclose(got.numpy(), O.short_side_scale(x.numpy(), size), rtol=1e-5, atol=1e-6)
+    # dict-level factory output (video_key / remove_key) like transforms_factory.py:262-284
+    tr = T.create_video_transform(mode="val", video_key="video", remove_key=["audio"], num_samples=4, min_size=32, crop_size=24,
+                                  out_dtype=torch.float32)
+    sample = {"video": TS.synthetic_u8_clip(8, 40, 60, seed=1).cuda(), "audio": 1, "label": 3}
+    out = tr(sample)
+    assert "audio" not in out and out["label"] == 3 and out["video"].shape == (3, 4, 24, 24)
+    with pytest.raises(NotImplementedError):
+        T.create_video_transform(mode="train", aug_type="randaug")

@@ -1,5 +1,6 @@
 """CPU: host-side logic of the engine (packing, BN folding, lowering dry-run, sharding)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -192,3 +193,13 @@ def test_slowfast_pathways_are_scheduled_on_two_lanes():
     p2, _ = lower_only(PH.slow_r50().eval(), torch.zeros(1, 3, 8, 224, 224))
     p2._schedule()
     assert p2.sched["lanes"] == [0] and not any(p2.sched["waits"])
+
+
+@pytest.mark.parametrize("name", TS.LAYER_CASES)
+def test_layer_modules_lower_on_the_host(name):
+    """Every `pytorchvideo.layers` / stem / head module has a lowering (no ``NotImplementedError`` forward)."""
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layers.pt"), weights_only=False)[name]
+    m, x, thw = TS.build_layer_case(name)
+    plan, shape = lower_only(m, torch.zeros(x.shape), extra=() if thw is None else (tuple(thw),))
+    assert tuple(shape) == tuple(g["output"].shape)
+    assert (plan.aux if thw is not None else None) == g["thw_out"]

@@ -87,6 +87,42 @@ def test_transform_chain_small_goldens():
         np.testing.assert_allclose(out, c["out"].numpy(), rtol=0, atol=2e-6)
 
 
+def test_train_chain_goldens_and_rng_draw_order():
+    """tests/golden/transforms.pt["train_small"]: outputs of the REAL reference
+    create_video_transform(mode="train") (RandomShortSideScale -> torchvision RandomCrop -> RandomHorizontalFlip)
+    under a fixed global seed.  (a) the numpy restatement reproduces them from the recorded draws; (b) the
+    product's host-side planner makes the SAME draws in the same order from the same seed; (c) the crop
+    offsets equal torchvision.transforms.RandomCrop.get_params under that seed."""
+    import torchvision.transforms as TV
+    from pytorchvideo_b200.transforms import create_video_transform
+    flips = 0
+    for c in _gold("transforms.pt")["train_small"]:
+        clip = TS.synthetic_u8_clip(c["T"], c["H"], c["W"], seed=c["seed"])
+        side, i, j, flip = c["draws"]
+        out = O.train_chain(clip.numpy(), c["n"], (0.45,) * 3, (0.225,) * 3, side, c["crop"], i, j, flip)
+        np.testing.assert_allclose(out, c["out"].numpy(), rtol=0, atol=2e-6)
+        tr = create_video_transform(mode="train", num_samples=c["n"], min_size=c["min_size"], max_size=c["max_size"],
+                                    crop_size=c["crop"])
+        torch.manual_seed(c["rng_seed"])
+        idx, hw, win, pflip = tr.plan(tuple(clip.shape))
+        assert hw == O.short_side_size(c["H"], c["W"], side)
+        assert win == O.random_crop_window(hw[0], hw[1], c["crop"], i, j) and pflip == flip
+        # torchvision's own parameter draw after the short-side draw
+        torch.manual_seed(c["rng_seed"])
+        torch.randint(c["min_size"], c["max_size"] + 1, (1,))
+        ti, tj, th, tw = TV.RandomCrop.get_params(torch.empty(3, hw[0], hw[1]), (c["crop"], c["crop"]))
+        assert (ti, tj, th, tw) == win
+        flips += int(flip)
+    assert 0 < flips < len(_gold("transforms.pt")["train_small"])
+
+
+def test_slowfast_pack_pathway_indices():
+    # pytorchvideo_trainer/datamodule/transforms.py:129-136: slow = index_select(frames, 1, linspace(0, T-1, T//alpha).long())
+    for key, idx in _gold("transforms.pt")["pack_pathway"].items():
+        t, a = (int(v) for v in key.split("_"))
+        assert np.array_equal(O.linspace_indices(t, t // a), idx.numpy()), key
+
+
 def test_normalize_zero_mean_unit_std_property():
     # tests/test_transforms.py:324-332 style property: normalising by the clip's own stats
     x = np.random.RandomState(0).rand(3, 4, 8, 8).astype(np.float32)
@@ -130,6 +166,23 @@ def test_oracle_reproduces_f16_grid_goldens(case):
     out = oracle_forward(model, inp)
     ref = g["output"]
     assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("name", TS.LAYER_CASES)
+def test_oracle_reproduces_reference_layer_goldens(name):
+    """tests/golden/layers.pt: outputs of the REAL reference layer classes (ConvReduce3D, Conv2plus1d in both
+    orders, Mlp, MultiScaleAttention, MultiScaleBlock, positional encoding, PatchEmbed, ViT head)."""
+    g = _gold("layers.pt")[name]
+    m, x, thw = TS.build_layer_case(name)
+    assert abs(TS.state_checksum(m) - g["state_checksum"]) <= 1e-6 * abs(g["state_checksum"])
+    np.testing.assert_allclose(TS.tensor_checksum(x), g["input_checksum"], rtol=1e-12)
+    out = oracle_forward(m, x, thw) if thw is not None else oracle_forward(m, x)
+    if thw is not None:
+        out, thw_out = out
+        assert list(thw_out) == g["thw_out"]
+    ref = g["output"]
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
 
 
 def test_f16_operand_floor_of_the_reference_arithmetic():
