@@ -97,6 +97,31 @@ int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void* src,
                           const int32_t* x0, const int32_t* x1, const float* lx,
                           void* dst, void* stream);
 
+/* Batched chain: n_clips clips per launch (same source geometry), taps computed in the kernel with ATen's
+ * arithmetic (no tables), optional per-clip geometry for the train chain, optional SECOND output = the SlowFast
+ * slow pathway (pytorchvideo_trainer/datamodule/transforms.py:99-138 SlowFastPackPathway), uint8 pass-through
+ * for pure frame selection (transforms/functional.py:19-41 keeps the dtype; :134-160 _repeated).
+ *   src[clip*s_clip + c*sc + idx_t[j]*st + h*sh + w*sw]  ->  dst[clip*d_clip + ((c*n_t + j)*out_h + y)*out_w + x]
+ *   slow_pos[j] >= 0: the same pixel is also written to dst_slow[clip*d_slow_clip + ((c*n_slow + slow_pos[j])*out_h + y)*out_w + x]
+ *   geom (device, optional): per clip {new_h, new_w, top, left, hflip} overriding the descriptor's values
+ * idx_t / slow_pos / geom are DEVICE int32 arrays; src/dst device pointers (src may be pinned host memory
+ * mapped into the device address space: decoder frames are read exactly once).                            */
+typedef struct pv_clip_batch_desc {
+  int C, n_clips, n_t, n_slow;
+  int in_h, in_w, new_h, new_w;     /* source frame, resize target (== source for no resize)      */
+  int top, left, out_h, out_w;      /* crop window inside the resized frame                       */
+  int hflip;                        /* mirror the cropped output along W                          */
+  long long sc, st, sh, sw, s_clip; /* source strides in ELEMENTS (channel, frame, row, col, clip) */
+  long long d_clip, d_slow_clip;    /* destination strides between clips, in elements             */
+  float mean[4], stdv[4];
+  int div255, normalize;            /* 1: x/255 first; 1: (x-mean)/std                             */
+  int src_dtype, dst_dtype;         /* src: PV_U8|PV_F32|PV_F16, dst: PV_F16|PV_F32|PV_U8 (pass-through) */
+} pv_clip_batch_desc;
+
+int pv_clip_transform_batch(const pv_clip_batch_desc* d, const void* src, const int32_t* idx_t,
+                            const int32_t* slow_pos, const int32_t* geom, void* dst, void* dst_slow,
+                            void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Layout / dtype conversion at the API boundary.
  * NCDHW (reference model input, models/net.py:41-44) -> NDHWC with C padded to c_pad (zeros).

@@ -24,6 +24,17 @@ class ClipTransformDesc(C.Structure):
                 ("src_dtype", C.c_int), ("dst_dtype", C.c_int), ("div255", C.c_int)]
 
 
+class ClipBatchDesc(C.Structure):
+    _fields_ = [("C", C.c_int), ("n_clips", C.c_int), ("n_t", C.c_int), ("n_slow", C.c_int),
+                ("in_h", C.c_int), ("in_w", C.c_int), ("new_h", C.c_int), ("new_w", C.c_int),
+                ("top", C.c_int), ("left", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
+                ("hflip", C.c_int),
+                ("sc", c_ll), ("st", c_ll), ("sh", c_ll), ("sw", c_ll), ("s_clip", c_ll),
+                ("d_clip", c_ll), ("d_slow_clip", c_ll),
+                ("mean", C.c_float * 4), ("stdv", C.c_float * 4),
+                ("div255", C.c_int), ("normalize", C.c_int), ("src_dtype", C.c_int), ("dst_dtype", C.c_int)]
+
+
 class Conv3dDesc(C.Structure):
     _fields_ = [("dtype", C.c_int),
                 ("N", C.c_int), ("Ti", C.c_int), ("Hi", C.c_int), ("Wi", C.c_int), ("Ci", C.c_int),
@@ -68,6 +79,7 @@ SIGNATURES = {
     "pv_launch_count": (c_ll, []),
     "pv_clip_transform_fwd": (C.c_int, [C.POINTER(ClipTransformDesc), c_vp, c_vp, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pv_clip_transform_batch": (C.c_int, [C.POINTER(ClipBatchDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pv_ncdhw_to_ndhwc": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_ll, c_vp]),
     "pv_ncdhw_to_ndhwc_padw": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const float* _
     if (g0 + EPI_GROUP_COLS >= E.block_n) {   // accumulator fully read: hand TMEM back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive_cluster(tempty_bar);   // shared::cluster address: own CTA, or the pair's leader
     }
     // (c) publish the staged tile to the async proxy and store it
     if (!(E.dbg & 16)) fence_proxy_async_smem();
@@ -245,7 +245,7 @@ __device__ __forceinline__ void epi_direct_row(const EpiParams& E, const float* 
       if (c0 + 32 >= E.block_n) {        // accumulator fully read: hand TMEM back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar);
+        if (lane == 0) mbar_arrive_cluster(tempty_bar);   // shared::cluster address: own CTA, or the pair's leader
       }
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
@@ -408,7 +408,7 @@ __device__ __forceinline__ void epilogue_tile_wide_prefetch(const EpiParams& E, 
     if (last_group) {                                   // accumulator fully read: hand TMEM back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive_cluster(tempty_bar);   // shared::cluster address: own CTA, or the pair's leader
     }
     fence_proxy_async_smem();
     epi_bar_sync(1, EPI_THREADS);

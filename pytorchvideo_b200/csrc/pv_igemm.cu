@@ -56,11 +56,16 @@ struct IgemmParams {
   int G, cpt;       // k-blocks per pipeline stage (chunk), chunks per tile
   int split_ab;     // experimental (PVB200_SPLIT_AB=1): warp 0 issues the A loads, warp 1 the B loads
   int epi_bytes;    // epilogue shared memory (one or - residual prefetch - two staging buffers + scale/bias)
+  int pair;         // 1: CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256 per MMA), see pv_sm100.cuh
+  int pair_tiles;   // pair mode: n_tiles * ceil(m_tiles / 2) units of work (one per cluster and iteration)
   EpiParams epi;
   signed char tap_q[IG_MAX_TAPS][4];
   unsigned char tap_map[IG_MAX_TAPS];
 };
 
+// PAIR is a template parameter, not a run-time flag: a cubin that contains cta_group::2 instructions can only be
+// launched as a cluster of two ("cluster misconfiguration" otherwise), so the single-CTA kernel must not carry them.
+template <bool PAIR>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restrict__ scale,
                     const float* __restrict__ bias) {
@@ -68,8 +73,12 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = P.stages;
+  constexpr bool pair = PAIR;
+  const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int b_rows = pair ? (P.block_n >> 1) : P.block_n;       // B rows THIS CTA keeps in shared memory
   const uint32_t a_bytes = (uint32_t)IG_BM * P.kbytes;
-  const uint32_t b_bytes = (uint32_t)P.block_n * P.kbytes;
+  const uint32_t b_bytes = (uint32_t)b_rows * P.kbytes;
   const int G = P.G;
   const uint32_t stage_bytes = (uint32_t)G * (a_bytes + b_bytes);   // [G x A k-block][G x B k-block]
   const int k_elems = P.kbytes >> 1;
@@ -92,12 +101,15 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     prefetch_tmap(&P.b_map);
     prefetch_tmap(&P.a_maps[0]);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), P.split_ab ? 2 : 1);   // one expect_tx arrive per issuing producer warp
+      // one expect_tx arrive per issuing producer warp; pair mode: the leader's barrier counts the leader's
+      // expect_tx arrive plus the peer's plain (remote) arrive, and the bytes of BOTH CTAs' loads
+      mbar_init(full_bar(s), (P.split_ab || pair) ? 2 : 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < nacc; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), epi_narrow(P.block_n) ? 4 : EPI_WARPS);   // one arrive per epilogue warp of the tile's group
+      // one arrive per epilogue warp of the tile's group (pair mode: from both CTAs, on the leader's barrier)
+      mbar_init(tempty_bar(s), (epi_narrow(P.block_n) ? 4 : EPI_WARPS) * (pair ? 2 : 1));
     }
     mbar_init(res_bar, 1);
     mbar_init(res_bar + 8u, 1);
@@ -105,11 +117,17 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     fence_mbar_init();
   }
   if (warp == IG_MMA_WARP) {
-    tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
-    tmem_relinquish();
+    if (pair) {       // both CTAs, same warp id, same shared-memory slot
+      tmem_alloc_pair(tmem_slot, (uint32_t)P.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (pair) cluster_sync_all();     // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -118,8 +136,22 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int total_tiles = P.n_tiles * P.m_tiles;
+  // Work units: a tile (n_tile, m_tile) per CTA, or - pair mode - two M-adjacent tiles (2*mp + rank) per cluster.
+  const int total_tiles = pair ? P.pair_tiles : P.n_tiles * P.m_tiles;
+  const int unit0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = P.taps * P.num_kc;
+  // unit -> (n0 tile index, merged output coordinates of this CTA's 128-row tile); a missing second tile of the
+  // last pair gets coordinates outside the tensor: its loads are zero-filled and its stores clipped by TMA
+  auto tile_coords = [&](int unit, int& n_tile, int (&o)[4]) {
+    n_tile = unit % P.n_tiles;
+    int mt = unit / P.n_tiles;
+    if (pair) mt = 2 * mt + (int)cta_rank;
+    const bool valid = mt < P.m_tiles;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
+    if (!valid) o[3] = P.O[3] + 128;
+  };
 
   if (warp < IG_PROD_WARPS) {
     // ================================ TMA producers =========================================
@@ -133,13 +165,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       const uint32_t tx_bytes = (do_a ? (uint32_t)P.rows * P.kbytes : 0u) + (do_b ? b_bytes : 0u);
       const int num_kc = P.num_kc, cpt = P.cpt;
       const bool skip_loads = (P.epi.dbg & 4) != 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % P.n_tiles;
-        int mt = tile / P.n_tiles;
-        int o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
-        const int n0 = n_tile * P.block_n;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        int n_tile, o[4];
+        tile_coords(tile, n_tile, o);
+        const int n0 = n_tile * P.block_n + (int)cta_rank * b_rows;     // pair: this CTA's half of the B rows
         int tap = 0, kc = 0;                  // (tap, channel chunk) of the next k-block, stepped without a divide
         for (int ch = 0; ch < cpt; ++ch) {
           const int kb0 = ch * G;
@@ -147,7 +176,21 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t st_base = smem_base + (uint32_t)stage * stage_bytes;
           if (elect_one()) {
-            if (skip_loads) {               // probe: pipeline skeleton without the loads
+            if (pair) {
+              // data -> own shared memory, transaction bytes -> the LEADER's full barrier
+              const uint32_t fb = mapa_shared(full_bar(stage), 0);
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * (uint32_t)nsub * tx_bytes);
+              else mbar_arrive_cluster(fb);
+              int tp = tap, kk = kc;
+              for (int j = 0; j < nsub; ++j) {
+                const void* amap = &P.a_maps[P.tap_map[tp]];
+                tma_load_5d_pair(st_base + (uint32_t)j * a_bytes, amap, fb, kk * k_elems, o[0] + P.tap_q[tp][0],
+                                 o[1] + P.tap_q[tp][1], o[2] + P.tap_q[tp][2], o[3] + P.tap_q[tp][3]);
+                tma_load_2d_pair(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, fb,
+                                 (kb0 + j) * k_elems, n0);
+                if (++kk == num_kc) { kk = 0; ++tp; }
+              }
+            } else if (skip_loads) {               // probe: pipeline skeleton without the loads
               mbar_arrive(full_bar(stage));
             } else {
               mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * tx_bytes);
@@ -177,8 +220,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     // elected lane issues the tcgen05 instructions, so their operands stay in uniform registers
     // (inside `if (lane == 0)` every tcgen05.mma / commit became an R2UR + ELECT/BRA.U.ANY waterfall
     // and the issuing thread cost ~800 clk per k-block - the bound of every narrow layer).
-    {
-      const uint32_t idesc = make_idesc_f16(IG_BM, P.block_n);
+    // Pair mode: only the leader CTA issues (M = 256 over both CTAs' A rows / accumulator lanes); its
+    // commits arrive on the barriers of BOTH CTAs.
+    if (leader) {
+      const uint32_t idesc = make_idesc_f16(pair ? 2 * IG_BM : IG_BM, P.block_n);
       const int k16 = (P.epi.dbg & 32) ? 0 : (P.kbytes >> 5);
       const int kbytes = P.kbytes, acc_stride = P.acc_stride;
       int stage = 0;
@@ -186,7 +231,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       int acc = 0;
       uint32_t acc_phase = 0;
       const int cpt = P.cpt;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
@@ -202,11 +247,18 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
               const uint64_t b_desc = make_kmajor_desc(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, kbytes);
               for (int k = 0; k < k16; ++k) {
                 // advance 16 elements (32 B) along K inside the swizzle row: +2 in (addr>>4)
-                umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb0 + j) | k) != 0 ? 1u : 0u);
+                const uint32_t accum = ((kb0 + j) | k) != 0 ? 1u : 0u;
+                if (pair) umma_f16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+                else umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
               }
             }
-            umma_commit(empty_bar(stage));                    // frees the chunk's smem when its MMAs retire
-            if (ch == cpt - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+            if (pair) {
+              umma_commit_pair(empty_bar(stage));
+              if (ch == cpt - 1) umma_commit_pair(tfull_bar(acc));
+            } else {
+              umma_commit(empty_bar(stage));                    // frees the chunk's smem when its MMAs retire
+              if (ch == cpt - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+            }
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -221,62 +273,57 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     int tile_seq = 0;
     uint32_t res_phase = 0;
     const bool narrow = epi_narrow(P.block_n);
+    // the accumulator is handed back on the MMA issuer's barrier: the leader CTA's (a shared::cluster address)
+    auto tempty_addr = [&](int a) { return pair ? mapa_shared(tempty_bar(a), 0) : tempty_bar(a); };
     // wide residual tiles: double-buffered staging with the residual of the next group prefetched
     const bool wide_prefetch = epi_wide_prefetch(P.epi);
     uint32_t res_phase2[2] = {0u, 0u};
     int q = 0;
-    auto decode = [&](int tile, int& n0, int (&o)[4]) {
-      n0 = (tile % P.n_tiles) * P.block_n;
-      int mt = tile / P.n_tiles;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
-    };
-    if (wide_prefetch && ewarp == 0 && lane == 0 && (int)blockIdx.x < total_tiles) {
-      int n0f, of[4];
-      decode((int)blockIdx.x, n0f, of);
-      epi_prefetch_residual(P.epi, staging, res_bar, 0, min(EPI_GROUP_COLS, P.block_n), n0f, of[0], of[1], of[2], of[3]);
+    if (wide_prefetch && ewarp == 0 && lane == 0 && unit0 < total_tiles) {
+      int ntf, of[4];
+      tile_coords(unit0, ntf, of);
+      epi_prefetch_residual(P.epi, staging, res_bar, 0, min(EPI_GROUP_COLS, P.block_n), ntf * P.block_n, of[0], of[1], of[2], of[3]);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_seq) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tile_seq) {
       if (narrow && (tile_seq & 1) != (ewarp >> 2)) continue;     // the other group's tile
       const int acc = tile_seq % nacc;
       const uint32_t acc_phase = (uint32_t)((tile_seq / nacc) & 1);
-      const int n_tile = tile % P.n_tiles;
-      int mt = tile / P.n_tiles;
-      int o[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { o[i] = (mt % P.nt[i]) * P.box[i]; mt /= P.nt[i]; }
+      int n_tile, o[4];
+      tile_coords(tile, n_tile, o);
       if (epi_direct(P.epi)) {
         epilogue_tile_direct(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), quarter, lane,
-                             n_tile * P.block_n, o[0], o[1], o[2], o[3], tfull_bar(acc), acc_phase, tempty_bar(acc));
+                             n_tile * P.block_n, o[0], o[1], o[2], o[3], tfull_bar(acc), acc_phase, tempty_addr(acc));
         continue;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (wide_prefetch) {
         EpiNext nxt = {0, 0, 0, 0, 0, 0};
-        const int tn = tile + (int)gridDim.x;
+        const int tn = tile + unit_step;
         if (tn < total_tiles) {
-          int on[4];
-          decode(tn, nxt.n0, on);
-          nxt.valid = 1; nxt.c1 = on[0]; nxt.c2 = on[1]; nxt.c3 = on[2]; nxt.c4 = on[3];
+          int on[4], nn;
+          tile_coords(tn, nn, on);
+          nxt.valid = 1; nxt.n0 = nn * P.block_n; nxt.c1 = on[0]; nxt.c2 = on[1]; nxt.c3 = on[2]; nxt.c4 = on[3];
         }
         epilogue_tile_wide_prefetch(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging,
                                     smem_gen + staging_off, res_bar, res_phase2, q, ewarp, quarter, lane,
-                                    n_tile * P.block_n, o[0], o[1], o[2], o[3], tempty_bar(acc), nxt);
+                                    n_tile * P.block_n, o[0], o[1], o[2], o[3], tempty_addr(acc), nxt);
         continue;
       }
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                     res_bar, res_phase, ewarp, quarter, lane, n_tile * P.block_n, o[0], o[1], o[2], o[3],
-                    tempty_bar(acc), tile_seq);
+                    tempty_addr(acc), tile_seq);
     }
     if ((ewarp & 3) == 0 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores (both group leaders)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (pair) cluster_sync_all();      // the peer may still be reading this CTA's shared memory / signalling its barriers
+  else __syncthreads();
   if (warp == IG_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    if (pair) tmem_dealloc_pair(tmem_base, (uint32_t)P.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
 }
 
@@ -489,6 +536,18 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   const bool narrow = conv3d_tma_narrow(d);
   const int win = wmode ? window_elems(d) : (narrow ? d->Ci : 64);
   P.kbytes = 2 * win;
+  // CTA pair (cta_group::2): full 64-channel k-blocks, N a multiple of 16 and at least two M tiles.  Each CTA then
+  // stages A (16 KiB) + HALF of B per k-block.  PVB200_PAIR=0 disables, =2 forces it for every eligible layer.
+  {
+    static const int pair_env = getenv("PVB200_PAIR") ? atoi(getenv("PVB200_PAIR")) : 0;
+    const long long k_total = (long long)d->kt * d->kh * d->kw * d->ci_pad64;
+    const bool eligible = !wmode && !narrow && P.kbytes == 128 && P.block_n % 16 == 0 && P.block_n >= 32 && P.m_tiles >= 2 &&
+                          sm_count >= 2;
+    // worth it where the mainloop dominates: deep K with a wide tile (shallow pointwise layers are epilogue-bound)
+    const bool wanted = pair_env == 2 || (pair_env == 1 && P.block_n >= 128 && k_total >= 512);
+    P.pair = (eligible && wanted) ? 1 : 0;
+    P.pair_tiles = P.n_tiles * (int)cdiv(P.m_tiles, 2);
+  }
   P.Co = d->Co;
   P.taps = wmode ? d->kt * d->kh : d->kt * d->kh * d->kw;
   P.num_kc = (wmode || narrow) ? 1 : d->ci_pad64 / 64;
@@ -509,7 +568,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   }
   // k-blocks per pipeline stage: a barrier round + commit costs the issuing thread ~500+ clk, one k-block
   // of MMAs only k16 * N/2 clk - group k-blocks until a stage carries ~1000 clk of tensor work.
-  const int kb_bytes = (IG_BM + P.block_n) * P.kbytes;
+  const int kb_bytes = (IG_BM + (P.pair ? P.block_n / 2 : P.block_n)) * P.kbytes;
   {
     const int num_kb = P.taps * P.num_kc;
     const int mma_clk = (P.kbytes >> 5) * (P.block_n < 16 ? 16 : P.block_n) / 2;
@@ -524,7 +583,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (st > 24 / G) st = 24 / G > 2 ? 24 / G : 2;
     if (st < 2) st = 2;
     P.G = G;
-    { static const bool split = getenv("PVB200_SPLIT_AB") != nullptr; P.split_ab = split ? 1 : 0; }
+    { static const bool split = getenv("PVB200_SPLIT_AB") != nullptr; P.split_ab = (split && !P.pair) ? 1 : 0; }
     P.cpt = (num_kb + G - 1) / G;
     P.stages = st;
   }
@@ -598,7 +657,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     const long long kpitch = narrow ? (krow + 63) / 64 * 64 : krow;   // narrow mode shares the gather packing (row end padded to 64)
     cuuint64_t gdim[2] = {(cuuint64_t)krow, (cuuint64_t)d->Co};
     cuuint64_t gstr[1] = {(cuuint64_t)kpitch * 2};
-    cuuint32_t box[2] = {(cuuint32_t)win, (cuuint32_t)P.block_n}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {(cuuint32_t)win, (cuuint32_t)(P.pair ? P.block_n / 2 : P.block_n)}, estr[2] = {1, 1};
     const CUtensorMapSwizzle swz = P.kbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                    : (P.kbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult cr = encode(&P.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, gdim, gstr, box, estr,
@@ -650,10 +709,15 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     }
   }
 
-  PV_OPT_IN_SMEM(conv3d_igemm_kernel, 227 * 1024);
+  PV_OPT_IN_SMEM(conv3d_igemm_kernel<false>, 227 * 1024);
+  PV_OPT_IN_SMEM(conv3d_igemm_kernel<true>, 227 * 1024);
   const long long total_tiles = (long long)P.m_tiles * P.n_tiles;
   if (total_tiles == 0) return PV_OK;
-  const int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
+  int grid = (int)(total_tiles < sm_count ? total_tiles : sm_count);
+  if (P.pair) {          // one cluster of two CTAs per TPC
+    const int clusters = P.pair_tiles < sm_count / 2 ? P.pair_tiles : sm_count / 2;
+    grid = 2 * clusters;
+  }
   {
     // launched with the programmatic-stream-serialization attribute (PDL); PVB200_NO_PDL=1 falls back to a plain launch
     static const bool use_pdl = getenv("PVB200_NO_PDL") == nullptr;
@@ -663,12 +727,24 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     cfg.blockDim = dim3(IG_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (P.pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
-    PV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3d_igemm_kernel, P, scale, bias));
+    cfg.numAttrs = na;
+    if (P.pair) PV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3d_igemm_kernel<true>, P, scale, bias));
+    else PV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3d_igemm_kernel<false>, P, scale, bias));
   }
   PV_LAUNCH_OK("conv3d_igemm_kernel");
   return PV_OK;

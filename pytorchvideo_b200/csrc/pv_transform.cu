@@ -62,6 +62,114 @@ clip_transform_kernel(pv_clip_transform_desc d, const SrcT* __restrict__ src,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batched chain (pv_clip_transform_batch): ONE launch over a batch of clips, no tap tables.
+//   * the bilinear taps are computed in the kernel with ATen's own arithmetic
+//       scale = float(in) / float(out);  src = fma(scale, dst + 0.5, -0.5);  src = max(src, 0)
+//       i0 = min(floor(src), in - 1);  l1 = clamp(src - i0, 0, 1);  i1 = i0 + (i0 < in - 1)
+//     (area_pixel_compute_source_index / guard_index_and_lambda; bit-equal to the host tables of the
+//     single-clip entry point, tests/test_gpu_transforms.py), so a thread has no dependent table loads;
+//   * a thread produces PX = 2 adjacent output columns of one (clip, frame, row) for ALL channels: up to
+//     24 independent byte loads in flight, the tap arithmetic shared by the channels;
+//   * optional per-clip geometry (random short side, crop window, horizontal flip: the train chain on a batch);
+//   * optional second output = the SlowFast slow pathway (frames slow_pos[j] >= 0 of the kept frames,
+//     pytorchvideo_trainer datamodule/transforms.py:129-136), written from the same registers;
+//   * uint8 destination for pure frame selection / cropping (UniformTemporalSubsample keeps the dtype).
+// grid = (ceil(out_w / (PX * 128)), out_h, n_clips * n_t);  block = 128
+// ---------------------------------------------------------------------------------------------------------------
+struct TapXY {
+  int i0, i1;
+  float l1;
+};
+__device__ __forceinline__ TapXY bilinear_tap(int dst, int in_size, int out_size) {
+  const float scale = __fdiv_rn((float)in_size, (float)out_size);
+  float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
+  src = fmaxf(src, 0.f);
+  TapXY t;
+  t.i0 = min((int)floorf(src), in_size - 1);
+  t.l1 = fminf(fmaxf(src - (float)t.i0, 0.f), 1.f);
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  return t;
+}
+template <typename T> __device__ __forceinline__ void st_out(T* p, float v);
+template <> __device__ __forceinline__ void st_out<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_out<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+template <> __device__ __forceinline__ void st_out<uint8_t>(uint8_t* p, float v) { *p = (uint8_t)v; }   // pass-through only
+// two adjacent outputs: one vector store when the address allows it
+template <typename T> __device__ __forceinline__ void st_out2(T* p, float a, float b, bool two) {
+  if (two && (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0) {
+    if constexpr (sizeof(T) == 2) *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
+    else if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(p) = make_float2(a, b);
+    else *reinterpret_cast<uchar2*>(p) = make_uchar2((unsigned char)a, (unsigned char)b);
+  } else {
+    st_out<T>(p, a);
+    if (two) st_out<T>(p + 1, b);
+  }
+}
+
+template <typename SrcT, typename OutT, int NC>
+__global__ void __launch_bounds__(128)
+clip_transform_batch_kernel(pv_clip_batch_desc d, const SrcT* __restrict__ src, const int32_t* __restrict__ idx_t,
+                            const int32_t* __restrict__ slow_pos, const int32_t* __restrict__ geom,
+                            OutT* __restrict__ dst, OutT* __restrict__ dst_slow) {
+  constexpr int PX = 2;
+  const int y = blockIdx.y;
+  const int clip = blockIdx.z / d.n_t, j = blockIdx.z - clip * d.n_t;
+  const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+  if (xb >= d.out_w) return;
+  int new_h = d.new_h, new_w = d.new_w, top = d.top, left = d.left, flip = d.hflip;
+  if (geom != nullptr) {        // per-clip (new_h, new_w, top, left, hflip)
+    const int32_t* g = geom + 5 * clip;
+    new_h = __ldg(g); new_w = __ldg(g + 1); top = __ldg(g + 2); left = __ldg(g + 3); flip = __ldg(g + 4);
+  }
+  const long long frame = (long long)clip * d.s_clip + (long long)__ldg(idx_t + j) * d.st;
+  const TapXY ty = bilinear_tap(top + y, d.in_h, new_h);
+  const float ly1 = ty.l1, ly0 = 1.f - ly1;
+  const SrcT* r0 = src + frame + (long long)ty.i0 * d.sh;
+  const SrcT* r1 = src + frame + (long long)ty.i1 * d.sh;
+  TapXY tx[PX];
+#pragma unroll
+  for (int i = 0; i < PX; ++i) {
+    const int xo = min(xb + i, d.out_w - 1);
+    tx[i] = bilinear_tap(left + (flip ? d.out_w - 1 - xo : xo), d.in_w, new_w);
+  }
+  // all loads first (independent), then the arithmetic
+  float v[NC][PX][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const long long co = (long long)c * d.sc;
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      const long long xa = (long long)tx[i].i0 * d.sw + co, xc = (long long)tx[i].i1 * d.sw + co;
+      v[c][i][0] = ld_src<SrcT>(r0 + xa); v[c][i][1] = ld_src<SrcT>(r0 + xc);
+      v[c][i][2] = ld_src<SrcT>(r1 + xa); v[c][i][3] = ld_src<SrcT>(r1 + xc);
+    }
+  }
+  const int sp = slow_pos != nullptr ? __ldg(slow_pos + j) : -1;
+  const bool two = (xb + 1 < d.out_w);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float mean = d.mean[c], stdv = d.stdv[c];
+    float out[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      float a = v[c][i][0], b = v[c][i][1], e = v[c][i][2], f = v[c][i][3];
+      if (d.div255) { a = a / 255.0f; b = b / 255.0f; e = e / 255.0f; f = f / 255.0f; }   // reference op order, fp32
+      if (d.normalize) { a = (a - mean) / stdv; b = (b - mean) / stdv; e = (e - mean) / stdv; f = (f - mean) / stdv; }
+      const float lx1 = tx[i].l1, lx0 = 1.f - lx1;
+      out[i] = ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * e + lx1 * f);
+    }
+    const long long pix = (long long)y * d.out_w + xb;
+    OutT* o = dst + (long long)clip * d.d_clip + ((long long)c * d.n_t + j) * d.out_h * d.out_w + pix;
+    st_out2<OutT>(o, out[0], out[1], two);
+    if (sp >= 0) {
+      OutT* os = dst_slow + (long long)clip * d.d_slow_clip + ((long long)c * d.n_slow + sp) * d.out_h * d.out_w + pix;
+      st_out2<OutT>(os, out[0], out[1], two);
+    }
+  }
+}
+
 }  // namespace pv
 
 extern "C" int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void* src,
@@ -88,5 +196,55 @@ extern "C" int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void
   }
 #undef PV_TR
   PV_LAUNCH_OK("clip_transform_kernel");
+  return PV_OK;
+}
+
+
+extern "C" int pv_clip_transform_batch(const pv_clip_batch_desc* d, const void* src, const int32_t* idx_t,
+                                       const int32_t* slow_pos, const int32_t* geom, void* dst, void* dst_slow,
+                                       void* stream) {
+  PV_CHECK_ARG(d && src && idx_t && dst, "null argument");
+  PV_CHECK_ARG(d->C >= 1 && d->C <= 4, "C must be in 1..4 (got %d)", d->C);
+  PV_CHECK_ARG(d->n_clips >= 1 && d->n_t >= 1 && d->out_h >= 1 && d->out_w >= 1, "empty output");
+  PV_CHECK_ARG(d->out_h <= 65535 && (long long)d->n_clips * d->n_t <= 65535, "grid too large");
+  PV_CHECK_ARG(d->in_h >= 1 && d->in_w >= 1 && d->new_h >= 1 && d->new_w >= 1, "bad frame size");
+  PV_CHECK_ARG(geom != nullptr || (d->top >= 0 && d->left >= 0 && d->top + d->out_h <= d->new_h && d->left + d->out_w <= d->new_w),
+               "crop window outside the resized frame");
+  PV_CHECK_ARG((slow_pos == nullptr) == (dst_slow == nullptr) && (slow_pos == nullptr || d->n_slow >= 1), "slow pathway arguments");
+  const bool pass = d->dst_dtype == PV_U8;
+  PV_CHECK_ARG(!pass || (d->src_dtype == PV_U8 && !d->div255 && !d->normalize && geom == nullptr && d->new_h == d->in_h && d->new_w == d->in_w),
+               "uint8 output is a pure frame selection / crop (no resize, no arithmetic)");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)pv::cdiv(d->out_w, 2 * 128), d->out_h, d->n_clips * d->n_t), block(128);
+#define PV_TB(ST, OT, NC)                                                                                      \
+  pv::clip_transform_batch_kernel<ST, OT, NC><<<grid, block, 0, s>>>(*d, (const ST*)src, idx_t, slow_pos, geom, \
+                                                                    (OT*)dst, (OT*)dst_slow)
+#define PV_TBC(ST, OT)                                                          \
+  do {                                                                          \
+    switch (d->C) {                                                             \
+      case 1: PV_TB(ST, OT, 1); break;                                          \
+      case 2: PV_TB(ST, OT, 2); break;                                          \
+      case 3: PV_TB(ST, OT, 3); break;                                          \
+      default: PV_TB(ST, OT, 4); break;                                         \
+    }                                                                           \
+  } while (0)
+  const int od = d->dst_dtype;
+  switch (d->src_dtype) {
+    case PV_U8:
+      if (od == PV_F16) PV_TBC(uint8_t, __half); else if (od == PV_F32) PV_TBC(uint8_t, float); else PV_TBC(uint8_t, uint8_t);
+      break;
+    case PV_F32:
+      if (od == PV_F16) PV_TBC(float, __half); else if (od == PV_F32) PV_TBC(float, float);
+      else { pv::set_error("f32 source needs an f16|f32 destination"); return PV_ERR_INVALID; }
+      break;
+    case PV_F16:
+      if (od == PV_F16) PV_TBC(__half, __half); else if (od == PV_F32) PV_TBC(__half, float);
+      else { pv::set_error("f16 source needs an f16|f32 destination"); return PV_ERR_INVALID; }
+      break;
+    default: pv::set_error("src dtype %d unsupported", d->src_dtype); return PV_ERR_INVALID;
+  }
+#undef PV_TBC
+#undef PV_TB
+  PV_LAUNCH_OK("clip_transform_batch_kernel");
   return PV_OK;
 }

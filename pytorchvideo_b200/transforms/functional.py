@@ -171,19 +171,157 @@ def clip_transform(x, frame_idx=None, resize_hw=None, window=None, mean=None, st
     return out
 
 
+_IDX_CACHE = {}
+
+
+def _dev_i32(values, dev):
+    key = (dev.index, tuple(int(v) for v in values))
+    t = _IDX_CACHE.get(key)
+    if t is None:
+        if len(_IDX_CACHE) > 512:
+            _IDX_CACHE.clear()
+        t = _IDX_CACHE[key] = torch.tensor(list(key[1]), dtype=torch.int32, device=dev)
+    return t
+
+
+def slow_pathway_indices(n_frames, alpha):
+    """SlowFastPackPathway (pytorchvideo_trainer/datamodule/transforms.py:129-136):
+    torch.linspace(0, T - 1, T // alpha).long() - positions inside the (already subsampled) fast clip."""
+    return torch.linspace(0, n_frames - 1, n_frames // alpha).long()
+
+
+def clip_transform_batch(x, frame_idx=None, resize_hw=None, window=None, mean=None, std=None, div255=False,
+                         out_dtype=torch.float16, hflip=False, geom=None, slow_alpha=None, out=None, out_slow=None):
+    """The fused chain on a BATCH of clips in one launch (pv_clip_transform_batch; taps computed in the kernel).
+
+    x         : (B, C, T, H, W) CUDA tensor, C <= 4, any strides (CTHW-contiguous or the decoder's THWC-interleaved
+                frames); a 4-D clip is a batch of one
+    geom      : optional per-clip list of (resize_hw, window, hflip) - the train chain with its own random short
+                side / crop / flip per clip; resize_hw / window / hflip then only give the output size
+    slow_alpha: also emit the SlowFast slow pathway (frames linspace(0, n_t-1, n_t//alpha).long() of the kept
+                frames) from the same pass; returns [slow, fast] like SlowFastPackPathway
+    out_dtype : torch.float16 | torch.float32, or torch.uint8 for a pure frame selection / crop of uint8 clips
+    """
+    squeeze = False
+    if torch.is_tensor(x) and x.dim() == 4:
+        x, squeeze = x.unsqueeze(0), True
+    if not torch.is_tensor(x) or x.dim() != 5:
+        raise RuntimeError("expected a (B, C, T, H, W) or (C, T, H, W) tensor")
+    if x.device.type != "cuda":
+        raise RuntimeError("pytorchvideo_b200 transforms run on the GPU only (no CPU path)")
+    if x.dtype not in _DT:
+        raise RuntimeError("unsupported clip dtype %s" % x.dtype)
+    B, Cc, T, H, W = x.shape
+    if Cc > 4:
+        raise RuntimeError("at most 4 channels per clip (got %d)" % Cc)
+    lib = L.load()
+    dev = x.device
+    idx = torch.arange(T) if frame_idx is None else torch.as_tensor(frame_idx).long().cpu()
+    if idx.numel() == 0 or int(idx.min()) < 0 or int(idx.max()) >= T:
+        raise RuntimeError("frame index out of range")
+    n_t = int(idx.numel())
+    nh, nw = (H, W) if resize_hw is None else (int(resize_hw[0]), int(resize_hw[1]))
+    top, left, oh, ow = (0, 0, nh, nw) if window is None else (int(v) for v in window)
+    geom_d = None
+    if geom is not None:
+        if len(geom) != B:
+            raise RuntimeError("geom needs one entry per clip")
+        flat = []
+        for (ghw, gwin, gflip) in geom:
+            gh, gw = (H, W) if ghw is None else ghw
+            gt, gl, goh, gow = (0, 0, gh, gw) if gwin is None else gwin
+            if (goh, gow) != (oh, ow) or gt < 0 or gl < 0 or gt + goh > gh or gl + gow > gw:
+                raise RuntimeError("per-clip crop windows must have the common output size and lie inside the resized frame")
+            flat += [int(gh), int(gw), int(gt), int(gl), 1 if gflip else 0]
+        geom_d = torch.tensor(flat, dtype=torch.int32, device=dev)
+    elif top < 0 or left < 0 or top + oh > nh or left + ow > nw:
+        raise RuntimeError("crop window outside the frame")
+    d = L.ClipBatchDesc()
+    d.C, d.n_clips, d.n_t = Cc, B, n_t
+    d.in_h, d.in_w, d.new_h, d.new_w = H, W, nh, nw
+    d.top, d.left, d.out_h, d.out_w, d.hflip = top, left, oh, ow, 1 if hflip else 0
+    d.s_clip, d.sc, d.st, d.sh, d.sw = x.stride(0), x.stride(1), x.stride(2), x.stride(3), x.stride(4)
+    normalize = mean is not None or std is not None
+    mean_l = [float(m) for m in (mean if mean is not None else [0.0] * Cc)]
+    std_l = [float(v) for v in (std if std is not None else [1.0] * Cc)]
+    mean_l = mean_l * Cc if len(mean_l) == 1 else mean_l
+    std_l = std_l * Cc if len(std_l) == 1 else std_l
+    for i in range(4):
+        d.mean[i] = mean_l[i] if i < len(mean_l) else 0.0
+        d.stdv[i] = std_l[i] if i < len(std_l) else 1.0
+    d.div255, d.normalize = 1 if div255 else 0, 1 if normalize else 0
+    d.src_dtype = _DT[x.dtype]
+    if out_dtype not in _DT:
+        raise RuntimeError("unsupported output dtype %s" % out_dtype)
+    d.dst_dtype = _DT[out_dtype]
+    if out is None:
+        out = torch.empty((B, Cc, n_t, oh, ow), dtype=out_dtype, device=dev)
+    elif tuple(out.shape) != (B, Cc, n_t, oh, ow) or not out.is_contiguous() or out.dtype != out_dtype:
+        raise RuntimeError("out must be a contiguous %s tensor of shape %s" % (out_dtype, (B, Cc, n_t, oh, ow)))
+    d.d_clip = out.stride(0)
+    idx_d = _dev_i32(idx.tolist(), dev)
+    slow_d, n_slow = None, 0
+    if slow_alpha is not None:
+        sidx = slow_pathway_indices(n_t, int(slow_alpha)).tolist()
+        n_slow = len(sidx)
+        if n_slow < 1:
+            raise RuntimeError("slow pathway would be empty (n_t=%d, alpha=%d)" % (n_t, slow_alpha))
+        pos = [-1] * n_t
+        for k, j in enumerate(sidx):
+            pos[j] = k           # linspace().long() is strictly increasing for alpha >= 1: every slot is unique
+        if len(set(sidx)) != n_slow:
+            raise RuntimeError("slow pathway indices repeat (alpha < 1?)")
+        slow_d = _dev_i32(pos, dev)
+        if out_slow is None:
+            out_slow = torch.empty((B, Cc, n_slow, oh, ow), dtype=out_dtype, device=dev)
+        elif tuple(out_slow.shape) != (B, Cc, n_slow, oh, ow) or not out_slow.is_contiguous() or out_slow.dtype != out_dtype:
+            raise RuntimeError("out_slow has the wrong shape / dtype")
+        d.n_slow, d.d_slow_clip = n_slow, out_slow.stride(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    L.check(lib.pv_clip_transform_batch(C.byref(d), x.data_ptr(), idx_d.data_ptr(),
+                                        slow_d.data_ptr() if slow_d is not None else None,
+                                        geom_d.data_ptr() if geom_d is not None else None, out.data_ptr(),
+                                        out_slow.data_ptr() if out_slow is not None else None, stream),
+            "pv_clip_transform_batch")
+    out._pv_keepalive = (idx_d, slow_d, geom_d)     # device tables must outlive the asynchronous launch
+    if squeeze:
+        out = out[0]
+        out_slow = out_slow[0] if out_slow is not None else None
+    return [out_slow, out] if slow_alpha is not None else out
+
+
 # ---- reference-named functional API -----------------------------------------------------------
+def _as_clip_batch(x, temporal_dim):
+    """View an N-D tensor with its temporal dim at -3 as (clips, channels <= 4, T, H, W) without copying."""
+    nd = x.dim()
+    if nd < 3:
+        raise RuntimeError("uniform_temporal_subsample needs at least (T, H, W)")
+    td = temporal_dim % nd
+    if td != nd - 3:
+        raise NotImplementedError("only temporal_dim == -3 (…, T, H, W) has a B200 kernel; got dim %d of %d" % (temporal_dim, nd))
+    lead = x.shape[:td]
+    v = x.reshape((-1,) + tuple(x.shape[td:])) if nd != 4 else x      # (L, T, H, W); a view for contiguous leading dims
+    Ld = v.shape[0]
+    if Ld <= 4:
+        return v.unsqueeze(0), lead                  # one clip of L channels
+    return v.unsqueeze(1), lead                      # L clips of one channel
+
+
 def uniform_temporal_subsample(x, num_samples, temporal_dim=-3):
-    if x.dim() != 4 or temporal_dim not in (-3, 1):
-        raise RuntimeError("uniform_temporal_subsample: (C, T, H, W) clips with temporal_dim=-3 only")
-    idx = temporal_indices(x.shape[1], num_samples)
-    odt = x.dtype if x.dtype in (torch.float32, torch.float16) else torch.float32
-    if x.dtype == torch.uint8:
-        raise RuntimeError("uint8 clips keep their dtype only inside the fused chain; use "
-                           "FusedClipTransform / create_video_transform for uint8 input")
-    return clip_transform(x, frame_idx=idx, out_dtype=odt)
+    """functional.py:19-41 on any (…, T, H, W) tensor (4-D clips, 5-D batches as used with temporal_dim=2 by
+    tests/test_models_slowfast.py:142-144): frame selection only, dtype preserved (uint8 stays uint8)."""
+    if not torch.is_tensor(x) or x.device.type != "cuda":
+        raise RuntimeError("pytorchvideo_b200 transforms run on the GPU only (no CPU path)")
+    if x.dtype not in _DT:
+        raise RuntimeError("unsupported clip dtype %s" % x.dtype)
+    v, lead = _as_clip_batch(x, temporal_dim)
+    idx = temporal_indices(v.shape[2], num_samples)
+    out = clip_transform_batch(v, frame_idx=idx, out_dtype=x.dtype)
+    return out.reshape(tuple(lead) + (int(idx.numel()),) + tuple(x.shape[-2:]))
 
 
 def uniform_temporal_subsample_repeated(frames, frame_ratios, temporal_dim=-3):
+    """functional.py:134-160: one subsampled tensor per ratio (SlowFast: frame_ratios=(alpha, 1))."""
     t = frames.shape[temporal_dim]
     return [uniform_temporal_subsample(frames, t // r, temporal_dim) for r in frame_ratios]
 

@@ -114,12 +114,14 @@ class FusedClipTransform(nn.Module):
     ("uniform", size, spatial_idx).  Input: uint8 (or float) CUDA clip (C, T, H, W)."""
 
     def __init__(self, num_samples=None, mean=None, std=None, short_side=None, crop=None, div255=True,
-                 out_dtype=torch.float16, random_short_side=None, hflip_prob=0.0):
+                 out_dtype=torch.float16, random_short_side=None, hflip_prob=0.0, slowfast_alpha=None):
         super().__init__()
         self.num_samples, self.mean, self.std = num_samples, mean, std
         self.short_side, self.crop, self.div255, self.out_dtype = short_side, crop, div255, out_dtype
         self.random_short_side = random_short_side
         self.hflip_prob = float(hflip_prob)
+        # emit [slow, fast] (SlowFastPackPathway, pytorchvideo_trainer datamodule/transforms.py:99-138) from the same pass
+        self.slowfast_alpha = slowfast_alpha
 
     def plan(self, shape):
         """Host-side index/window/flip selection for an input of ``shape`` (C, T, H, W).  Random draws
@@ -150,9 +152,37 @@ class FusedClipTransform(nn.Module):
         return idx, hw, win, flip
 
     def forward(self, x, out=None):
-        idx, hw, win, flip = self.plan(x.shape)
-        return Fv.clip_transform(x, frame_idx=idx, resize_hw=hw, window=win, mean=self.mean, std=self.std,
-                                 div255=self.div255, out_dtype=self.out_dtype, out=out, hflip=flip)
+        """x: one clip (C, T, H, W) or a batch (B, C, T, H, W) - ONE launch either way (a batch in train mode
+        draws short side / crop / flip per clip, in clip order).  Returns the clip(s), or [slow, fast] when
+        ``slowfast_alpha`` is set."""
+        if x.dim() == 5 and self._is_random():
+            plans = [self.plan(x.shape[1:]) for _ in range(x.shape[0])]
+            idx, hw, win, _ = plans[0]
+            geom = [(p[1], p[2], p[3]) for p in plans]
+            return Fv.clip_transform_batch(x, frame_idx=idx, resize_hw=hw, window=win, mean=self.mean, std=self.std,
+                                           div255=self.div255, out_dtype=self.out_dtype, geom=geom,
+                                           slow_alpha=self.slowfast_alpha, out=out)
+        idx, hw, win, flip = self.plan(x.shape[-4:])
+        return Fv.clip_transform_batch(x, frame_idx=idx, resize_hw=hw, window=win, mean=self.mean, std=self.std,
+                                       div255=self.div255, out_dtype=self.out_dtype, hflip=flip,
+                                       slow_alpha=self.slowfast_alpha, out=out)
+
+    def _is_random(self):
+        return self.random_short_side is not None or self.hflip_prob > 0.0 or (self.crop is not None and self.crop[0] == "random")
+
+
+class SlowFastPackPathway(nn.Module):
+    """frames (C, T, H, W) or (B, C, T, H, W) -> [slow, fast]; slow = frames at linspace(0, T-1, T//alpha).long()
+    (pytorchvideo_trainer/datamodule/transforms.py:99-138).  One gather launch; inside a FusedClipTransform the
+    same list comes out of the transform kernel itself (``slowfast_alpha``)."""
+
+    def __init__(self, alpha=4):
+        super().__init__()
+        self.alpha = alpha
+
+    def forward(self, frames):
+        out = Fv.clip_transform_batch(frames, out_dtype=frames.dtype, slow_alpha=self.alpha)
+        return [out[0], frames]
 
 
 class RemoveKey:

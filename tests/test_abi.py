@@ -53,8 +53,8 @@ def test_struct_sizes_match_header():
     probe = r'''
     #include <stdio.h>
     #include "pv_b200.h"
-    int main(){ printf("%zu %zu %zu %zu\n", sizeof(pv_clip_transform_desc), sizeof(pv_conv3d_desc),
-                       sizeof(pv_pool3d_desc), sizeof(pv_attention_desc)); return 0; }'''
+    int main(){ printf("%zu %zu %zu %zu %zu\n", sizeof(pv_clip_transform_desc), sizeof(pv_conv3d_desc),
+                       sizeof(pv_pool3d_desc), sizeof(pv_attention_desc), sizeof(pv_clip_batch_desc)); return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "p.c")
@@ -63,7 +63,7 @@ def test_struct_sizes_match_header():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_lib.ClipTransformDesc), ctypes.sizeof(_lib.Conv3dDesc),
-                     ctypes.sizeof(_lib.Pool3dDesc), ctypes.sizeof(_lib.AttentionDesc)]
+                     ctypes.sizeof(_lib.Pool3dDesc), ctypes.sizeof(_lib.AttentionDesc), ctypes.sizeof(_lib.ClipBatchDesc)]
 
 
 def test_product_has_no_cpu_path():
