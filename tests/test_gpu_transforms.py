@@ -116,3 +116,70 @@ def test_random_crop_and_short_side_modules_follow_torchvision_under_seed():
     assert "audio" not in out and out["label"] == 3 and out["video"].shape == (3, 4, 24, 24)
     with pytest.raises(NotImplementedError):
         T.create_video_transform(mode="train", aug_type="randaug")
+
+
+def test_batched_chain_equals_per_clip_chain_and_emits_slowfast_pathways():
+    """pv_clip_transform_batch: one launch over a batch, taps computed in the kernel (no tables) - bit-equal to
+    the table-driven single-clip kernel; the optional second output is the SlowFast slow pathway
+    (pytorchvideo_trainer/datamodule/transforms.py:129-136), bit-equal to index_select on the fast output."""
+    from pytorchvideo_b200.transforms import FusedClipTransform, SlowFastPackPathway
+    from pytorchvideo_b200.transforms import functional as Fv
+    clips = torch.stack([TS.synthetic_u8_clip(40, 90, 160, seed=30 + i) for i in range(3)]).cuda()      # (B, C, T, H, W)
+    mean, std = (0.45, 0.45, 0.45), (0.225, 0.225, 0.225)
+    for dt in (torch.float32, torch.float16):
+        tr = FusedClipTransform(32, mean, std, short_side=48, crop=("center", 40), out_dtype=dt)
+        batch = tr(clips)
+        assert batch.shape == (3, 3, 32, 40, 40)
+        idx, hw, win, _ = tr.plan(clips.shape[1:])
+        for b in range(3):
+            one = Fv.clip_transform(clips[b], frame_idx=idx, resize_hw=hw, window=win, mean=mean, std=std, div255=True,
+                                    out_dtype=dt)                                       # table-driven kernel
+            assert torch.equal(batch[b], one)
+        ref = O.val_chain(clips[1].cpu().numpy(), 32, mean, std, 48, 40)
+        tol = dict(rtol=1e-5, atol=2e-6) if dt == torch.float32 else dict(rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(batch[1].float().cpu().numpy(), ref, **tol)
+        # SlowFast packing from the same pass
+        slow, fast = FusedClipTransform(32, mean, std, short_side=48, crop=("center", 40), out_dtype=dt, slowfast_alpha=4)(clips)
+        assert torch.equal(fast, batch)
+        sidx = torch.linspace(0, 31, 8).long()
+        assert sidx.tolist() == [0, 4, 8, 13, 17, 22, 26, 31]
+        assert torch.equal(slow, torch.index_select(batch, 2, sidx.cuda()))
+    # stand-alone pack module on an already transformed clip / batch
+    s2, f2 = SlowFastPackPathway(4)(batch)
+    assert torch.equal(f2, batch) and torch.equal(s2, torch.index_select(batch, 2, sidx.cuda()))
+    # THWC-interleaved decoder frames, batched
+    thwc = clips.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    assert torch.equal(FusedClipTransform(32, mean, std, short_side=48, crop=("center", 40), out_dtype=torch.float16)(thwc), batch)
+
+
+def test_batched_train_chain_draws_per_clip():
+    """A batch through the train chain draws short side / crop / flip per clip, in clip order, from the global RNG:
+    equal to transforming the clips one after the other under the same seed."""
+    from pytorchvideo_b200.transforms import create_video_transform
+    clips = torch.stack([TS.synthetic_u8_clip(12, 60, 80, seed=50 + i) for i in range(4)]).cuda()
+    tr = create_video_transform(mode="train", num_samples=6, min_size=32, max_size=48, crop_size=24, out_dtype=torch.float32)
+    torch.manual_seed(99)
+    batch = tr(clips)
+    torch.manual_seed(99)
+    singles = torch.stack([tr(clips[b]) for b in range(4)])
+    assert torch.equal(batch, singles)
+
+
+def test_uniform_temporal_subsample_nd_and_uint8():
+    """functional.py:19-41 / 134-160 on 4-D clips, 5-D batches (temporal_dim=2, tests/test_models_slowfast.py:142-144)
+    and uint8 frames: pure index selection, bit-exact, dtype preserved."""
+    from pytorchvideo_b200.transforms import functional as Fv
+    g = torch.Generator().manual_seed(3)
+    x5 = torch.rand(2, 3, 32, 20, 24, generator=g)
+    slow, fast = Fv.uniform_temporal_subsample_repeated(x5.cuda(), (4, 1), temporal_dim=2)
+    idx = torch.clamp(torch.linspace(0, 31, 8), 0, 31).long()
+    assert torch.equal(slow.cpu(), torch.index_select(x5, 2, idx)) and torch.equal(fast.cpu(), x5)
+    u8 = TS.synthetic_u8_clip(20, 18, 22, seed=4)
+    out = Fv.uniform_temporal_subsample(u8.cuda(), 10)
+    assert out.dtype == torch.uint8 and torch.equal(out.cpu(), u8[:, O.linspace_indices(20, 10)])
+    x8 = torch.rand(8, 9, 10, 12, generator=g)            # more than 4 leading entries: treated as 8 one-channel clips
+    assert torch.equal(Fv.uniform_temporal_subsample(x8.cuda(), 4).cpu(), x8[:, O.linspace_indices(9, 4)])
+    h16 = torch.rand(3, 7, 8, 8, generator=g).half()
+    assert torch.equal(Fv.uniform_temporal_subsample(h16.cuda(), 3, temporal_dim=1).cpu(), h16[:, O.linspace_indices(7, 3)])
+    with pytest.raises(NotImplementedError):
+        Fv.uniform_temporal_subsample(x5.cuda(), 4, temporal_dim=1)
