@@ -103,7 +103,8 @@ int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void* src,
  * for pure frame selection (transforms/functional.py:19-41 keeps the dtype; :134-160 _repeated).
  *   src[clip*s_clip + c*sc + idx_t[j]*st + h*sh + w*sw]  ->  dst[clip*d_clip + ((c*n_t + j)*out_h + y)*out_w + x]
  *   slow_pos[j] >= 0: the same pixel is also written to dst_slow[clip*d_slow_clip + ((c*n_slow + slow_pos[j])*out_h + y)*out_w + x]
- *   geom (device, optional): per clip {new_h, new_w, top, left, hflip} overriding the descriptor's values
+ *   geom (device, optional): per clip {new_h, new_w, top, left, hflip, first_frame} overriding the descriptor's
+ *   values; first_frame is added to every idx_t[j] (temporal views of one video: s_clip = 0)
  * idx_t / slow_pos / geom are DEVICE int32 arrays; src/dst device pointers (src may be pinned host memory
  * mapped into the device address space: decoder frames are read exactly once).                            */
 typedef struct pv_clip_batch_desc {
@@ -121,6 +122,11 @@ typedef struct pv_clip_batch_desc {
 int pv_clip_transform_batch(const pv_clip_batch_desc* d, const void* src, const int32_t* idx_t,
                             const int32_t* slow_pos, const int32_t* geom, void* dst, void* dst_slow,
                             void* stream);
+
+/* Test-time multi-view ensembling (pytorchvideo_trainer/module/video_classification.py:290-311, docs model_zoo.md:63
+ * "3 spatial x 10 temporal views"): out[v][k] = reduce over the n_views consecutive rows of video v;
+ * mode 0 = sum, 1 = mean (sum / clip count), 2 = max.  preds: [n_videos * n_views][K] f32.                    */
+int pv_view_reduce(const float* preds, float* out, int n_videos, int n_views, int K, int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout / dtype conversion at the API boundary.

@@ -54,8 +54,10 @@ struct IgemmParams {
   int acc_stride;   // TMEM columns between accumulator stages (block_n rounded up to 32)
   int nacc;         // number of accumulator stages
   int G, cpt;       // k-blocks per pipeline stage (chunk), chunks per tile
-  int split_ab;     // experimental (PVB200_SPLIT_AB=1): warp 0 issues the A loads, warp 1 the B loads
+  int split_ab;     // producer warps that share the loads of a chunk (1, 2 or 4; PVB200_SPLIT_AB)
   int epi_bytes;    // epilogue shared memory (one or - residual prefetch - two staging buffers + scale/bias)
+  int alias_epi;    // 1: every CTA runs exactly ONE tile, so the epilogue staging may reuse the (then idle) tile ring:
+                    //    one more pipeline stage for the layers with fewer tiles than SMs (res4 / res5)
   int pair;         // 1: CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256 per MMA), see pv_sm100.cuh
   int pair_tiles;   // pair mode: n_tiles * ceil(m_tiles / 2) units of work (one per cluster and iteration)
   EpiParams epi;
@@ -83,9 +85,10 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   const uint32_t stage_bytes = (uint32_t)G * (a_bytes + b_bytes);   // [G x A k-block][G x B k-block]
   const int k_elems = P.kbytes >> 1;
   // epilogue staging (1024-aligned) and the barriers live after the tile ring
-  const uint32_t staging_off = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
+  const uint32_t ring_end = (uint32_t)((stages * stage_bytes + 1023u) & ~1023u);
+  const uint32_t staging_off = P.alias_epi ? 0u : ring_end;
   const uint32_t staging = smem_base + staging_off;
-  const uint32_t bar_base = staging + (uint32_t)P.epi_bytes;
+  const uint32_t bar_base = smem_base + max(ring_end, staging_off + (uint32_t)P.epi_bytes);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
@@ -103,7 +106,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     for (int s = 0; s < stages; ++s) {
       // one expect_tx arrive per issuing producer warp; pair mode: the leader's barrier counts the leader's
       // expect_tx arrive plus the peer's plain (remote) arrive, and the bytes of BOTH CTAs' loads
-      mbar_init(full_bar(s), (P.split_ab || pair) ? 2 : 1);
+      mbar_init(full_bar(s), pair ? 2 : 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < nacc; ++s) {
@@ -158,11 +161,15 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     // One producer warp: warp-uniform loop, one elected lane issues the TMA loads of a whole chunk
     // (up to G k-blocks = 2G bulk-tensor loads on ONE mbarrier).  Measured on B200: extra producer warps
     // do not help; what bounds narrow-N layers is the number of barrier rounds, hence the chunking.
-    if (warp == 0 || (warp == 1 && P.split_ab)) {
-      const bool do_a = !P.split_ab || warp == 0, do_b = !P.split_ab || warp == 1;
+    // The loads of a chunk (2 per k-block: A and B) are dealt round-robin to `nsplit` producer warps - one issuing
+    // thread sustains only ~one bulk-tensor load per 330-520 clk (tools/probe/tma_rate.cu), four warps one per ~130.
+    // Warp 0 alone arrives on the full barrier with the expected bytes of the WHOLE chunk; the other warps' loads may
+    // complete before that arrive (the transaction count goes negative, the phase cannot complete without the arrive).
+    const int nsplit = pair ? 1 : P.split_ab;
+    if (warp < nsplit) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (do_a ? (uint32_t)P.rows * P.kbytes : 0u) + (do_b ? b_bytes : 0u);
+      const uint32_t tx_bytes = (uint32_t)P.rows * P.kbytes + b_bytes;
       const int num_kc = P.num_kc, cpt = P.cpt;
       const bool skip_loads = (P.epi.dbg & 4) != 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
@@ -191,17 +198,17 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
                 if (++kk == num_kc) { kk = 0; ++tp; }
               }
             } else if (skip_loads) {               // probe: pipeline skeleton without the loads
-              mbar_arrive(full_bar(stage));
+              if (warp == 0) mbar_arrive(full_bar(stage));
             } else {
-              mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * tx_bytes);
+              if (warp == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)nsub * tx_bytes);
               int tp = tap, kk = kc;
               for (int j = 0; j < nsub; ++j) {
-                if (do_a) {
+                if ((2 * j) % nsplit == warp) {
                   const void* amap = &P.a_maps[P.tap_map[tp]];
                   tma_load_5d(st_base + (uint32_t)j * a_bytes, amap, full_bar(stage), kk * k_elems, o[0] + P.tap_q[tp][0],
                               o[1] + P.tap_q[tp][1], o[2] + P.tap_q[tp][2], o[3] + P.tap_q[tp][3]);
                 }
-                if (do_b)
+                if ((2 * j + 1) % nsplit == warp)
                   tma_load_2d(st_base + (uint32_t)G * a_bytes + (uint32_t)j * b_bytes, &P.b_map, full_bar(stage),
                               (kb0 + j) * k_elems, n0);
                 if (++kk == num_kc) { kk = 0; ++tp; }
@@ -577,18 +584,31 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (G > num_kb) G = num_kb;
     { const char* e = getenv("PVB200_G"); if (e && atoi(e) >= 1 && atoi(e) <= 8) G = atoi(e) < num_kb ? atoi(e) : num_kb; }
     P.epi_bytes = EPI_SMEM_BYTES + (epi_wide_prefetch(P.epi) ? EPI_STAGING_BYTES : 0);
-    const int budget = 227 * 1024 - 2048 - P.epi_bytes - 256;
+    {
+      static const bool no_alias = getenv("PVB200_NO_ALIAS") != nullptr;
+      const long long units = P.pair ? 2ll * P.pair_tiles : (long long)P.m_tiles * P.n_tiles;
+      P.alias_epi = (!no_alias && units <= sm_count && !epi_wide_prefetch(P.epi) && !epi_direct(P.epi)) ? 1 : 0;
+    }
+    const int budget = 227 * 1024 - 2048 - (P.alias_epi ? 0 : P.epi_bytes) - 256;
     while (G > 1 && budget / (G * kb_bytes) < 3) --G;
     int st = budget / (G * kb_bytes);
     if (st > 24 / G) st = 24 / G > 2 ? 24 / G : 2;
     if (st < 2) st = 2;
     P.G = G;
-    { static const bool split = getenv("PVB200_SPLIT_AB") != nullptr; P.split_ab = (split && !P.pair) ? 1 : 0; }
+    {
+      // default: 2 warps (A / B) for one k-block per stage, 4 for chunked stages (window / narrow modes: up to 8 loads)
+      static const int split_env = getenv("PVB200_SPLIT_AB") ? atoi(getenv("PVB200_SPLIT_AB")) : -1;
+      int ns = split_env >= 1 ? split_env : (G >= 2 ? 4 : 2);
+      if (ns > IG_PROD_WARPS) ns = IG_PROD_WARPS;
+      if (ns == 3) ns = 2;
+      P.split_ab = P.pair ? 1 : ns;
+    }
     P.cpt = (num_kb + G - 1) / G;
     P.stages = st;
   }
   const int stage_bytes = P.G * kb_bytes;
-  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + P.epi_bytes +
+  if (P.alias_epi && (long long)P.stages * stage_bytes < P.epi_bytes) P.alias_epi = 0;     // ring smaller than the staging area
+  const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + (P.alias_epi ? 0 : P.epi_bytes) +
                             8 * (2 * P.stages + 2 * 8 + 4) + 16;
 
   // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)

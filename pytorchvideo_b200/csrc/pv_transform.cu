@@ -72,7 +72,9 @@ clip_transform_kernel(pv_clip_transform_desc d, const SrcT* __restrict__ src,
 //     single-clip entry point, tests/test_gpu_transforms.py), so a thread has no dependent table loads;
 //   * a thread produces PX = 2 adjacent output columns of one (clip, frame, row) for ALL channels: up to
 //     24 independent byte loads in flight, the tap arithmetic shared by the channels;
-//   * optional per-clip geometry (random short side, crop window, horizontal flip: the train chain on a batch);
+//   * optional per-clip geometry (random short side, crop window, horizontal flip: the train chain on a batch;
+//     plus a first-frame offset: the 3 spatial x K temporal test-time views of ONE video are a batch whose
+//     clip stride is 0);
 //   * optional second output = the SlowFast slow pathway (frames slow_pos[j] >= 0 of the kept frames,
 //     pytorchvideo_trainer datamodule/transforms.py:129-136), written from the same registers;
 //   * uint8 destination for pure frame selection / cropping (UniformTemporalSubsample keeps the dtype).
@@ -119,11 +121,13 @@ clip_transform_batch_kernel(pv_clip_batch_desc d, const SrcT* __restrict__ src, 
   const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
   if (xb >= d.out_w) return;
   int new_h = d.new_h, new_w = d.new_w, top = d.top, left = d.left, flip = d.hflip;
-  if (geom != nullptr) {        // per-clip (new_h, new_w, top, left, hflip)
-    const int32_t* g = geom + 5 * clip;
+  int t_off = 0;
+  if (geom != nullptr) {        // per-clip (new_h, new_w, top, left, hflip, first frame)
+    const int32_t* g = geom + 6 * clip;
     new_h = __ldg(g); new_w = __ldg(g + 1); top = __ldg(g + 2); left = __ldg(g + 3); flip = __ldg(g + 4);
+    t_off = __ldg(g + 5);
   }
-  const long long frame = (long long)clip * d.s_clip + (long long)__ldg(idx_t + j) * d.st;
+  const long long frame = (long long)clip * d.s_clip + (long long)(__ldg(idx_t + j) + t_off) * d.st;
   const TapXY ty = bilinear_tap(top + y, d.in_h, new_h);
   const float ly1 = ty.l1, ly0 = 1.f - ly1;
   const SrcT* r0 = src + frame + (long long)ty.i0 * d.sh;
@@ -199,6 +203,34 @@ extern "C" int pv_clip_transform_fwd(const pv_clip_transform_desc* d, const void
   return PV_OK;
 }
 
+
+namespace pv {
+// Test-time ensembling over the views of a video (pytorchvideo_trainer module/video_classification.py:290-311:
+// per-video accumulation of the per-clip predictions, "sum" or "max", then division by the clip count):
+// out[v][k] = reduce_{i < n_views} preds[(v*n_views + i)][k];  mode 0 = sum, 1 = mean, 2 = max.
+__global__ void view_reduce_kernel(const float* __restrict__ preds, float* __restrict__ out, int n_videos, int n_views,
+                                   int K, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_videos * K) return;
+  const int v = i / K, k = i - v * K;
+  const float* p = preds + (long long)v * n_views * K + k;
+  float acc = mode == 2 ? -INFINITY : 0.f;
+  for (int j = 0; j < n_views; ++j) {
+    const float x = p[(long long)j * K];
+    acc = mode == 2 ? fmaxf(acc, x) : acc + x;
+  }
+  out[i] = mode == 1 ? acc / (float)n_views : acc;
+}
+}  // namespace pv
+
+extern "C" int pv_view_reduce(const float* preds, float* out, int n_videos, int n_views, int K, int mode, void* stream) {
+  PV_CHECK_ARG(preds && out, "null argument");
+  PV_CHECK_ARG(n_videos >= 1 && n_views >= 1 && K >= 1 && mode >= 0 && mode <= 2, "bad sizes / mode");
+  const int total = n_videos * K;
+  pv::view_reduce_kernel<<<(unsigned)pv::cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(preds, out, n_videos, n_views, K, mode);
+  PV_LAUNCH_OK("view_reduce_kernel");
+  return PV_OK;
+}
 
 extern "C" int pv_clip_transform_batch(const pv_clip_batch_desc* d, const void* src, const int32_t* idx_t,
                                        const int32_t* slow_pos, const int32_t* geom, void* dst, void* dst_slow,

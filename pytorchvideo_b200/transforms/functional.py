@@ -196,8 +196,9 @@ def clip_transform_batch(x, frame_idx=None, resize_hw=None, window=None, mean=No
 
     x         : (B, C, T, H, W) CUDA tensor, C <= 4, any strides (CTHW-contiguous or the decoder's THWC-interleaved
                 frames); a 4-D clip is a batch of one
-    geom      : optional per-clip list of (resize_hw, window, hflip) - the train chain with its own random short
-                side / crop / flip per clip; resize_hw / window / hflip then only give the output size
+    geom      : optional per-clip list of (resize_hw, window, hflip[, first_frame]) - the train chain with its own
+                random short side / crop / flip per clip, or the spatial x temporal test-time views of one video
+                (expand the video to a batch with clip stride 0); resize_hw / window then only give the output size
     slow_alpha: also emit the SlowFast slow pathway (frames linspace(0, n_t-1, n_t//alpha).long() of the kept
                 frames) from the same pass; returns [slow, fast] like SlowFastPackPathway
     out_dtype : torch.float16 | torch.float32, or torch.uint8 for a pure frame selection / crop of uint8 clips
@@ -227,12 +228,16 @@ def clip_transform_batch(x, frame_idx=None, resize_hw=None, window=None, mean=No
         if len(geom) != B:
             raise RuntimeError("geom needs one entry per clip")
         flat = []
-        for (ghw, gwin, gflip) in geom:
+        for entry in geom:
+            ghw, gwin, gflip = entry[:3]
+            goff = int(entry[3]) if len(entry) > 3 else 0
+            if goff + int(idx.min()) < 0 or goff + int(idx.max()) >= T:
+                raise RuntimeError("view frame range outside the clip")
             gh, gw = (H, W) if ghw is None else ghw
             gt, gl, goh, gow = (0, 0, gh, gw) if gwin is None else gwin
             if (goh, gow) != (oh, ow) or gt < 0 or gl < 0 or gt + goh > gh or gl + gow > gw:
                 raise RuntimeError("per-clip crop windows must have the common output size and lie inside the resized frame")
-            flat += [int(gh), int(gw), int(gt), int(gl), 1 if gflip else 0]
+            flat += [int(gh), int(gw), int(gt), int(gl), 1 if gflip else 0, goff]
         geom_d = torch.tensor(flat, dtype=torch.int32, device=dev)
     elif top < 0 or left < 0 or top + oh > nh or left + ow > nw:
         raise RuntimeError("crop window outside the frame")

@@ -51,6 +51,10 @@ CONV_CASES = [
     (2, 32, 6, 10, 10, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, "relu", False),       # Fast-pathway conv_a: narrow TMA mode (64 B rows)
     (1, 16, 4, 9, 9, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "relu", True),         # Fast-pathway conv_b + residual: narrow TMA (32 B rows)
     (2, 32, 2, 9, 9, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, None, False),         # strided shortcut from a 32-wide tensor
+    (1, 216, 3, 39, 39, 216, (3, 3, 3), (1, 2, 2), (1, 1, 1), 216, None, False),    # X3D-L res4 depthwise: odd 39 -> 20, stride 2
+    (1, 96, 2, 39, 39, 192, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, None, False),       # X3D-L strided shortcut on an odd extent
+    (1, 24, 2, 78, 156, 54, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "relu", False),     # X3D-L wide rows (W = 156)
+    (1, 56, 2, 40, 156, 56, (3, 3, 3), (1, 1, 1), (1, 1, 1), 56, "swish", False),   # X3D-L depthwise on W = 156
 ]
 
 
