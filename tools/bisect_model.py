@@ -13,17 +13,30 @@ from pytorchvideo_b200.engine import compile_model
 import pytorchvideo_b200.models.hub as PH
 
 
+def _shallow(m):
+    c = copy.copy(m)
+    c.__dict__ = dict(m.__dict__)
+    c._modules = dict(m._modules)
+    return c
+
+
 def main():
+    """argv: case [f16|f32] [stage index: bisect the res_blocks of blocks[stage] instead of whole blocks]"""
     case = sys.argv[1]
     dtype = sys.argv[2] if len(sys.argv) > 2 else "f16"
+    stage = int(sys.argv[3]) if len(sys.argv) > 3 else None
     model, inp, is_sf = TS.build_case(case, PH)
     nb = len(model.blocks)
     x_cpu = inp
-    for k in range(1, nb):          # the head needs the full net; prefixes end with a feature map
-        sub = copy.copy(model)
-        sub.__dict__ = dict(model.__dict__)
-        sub._modules = dict(model._modules)
-        sub._modules["blocks"] = nn.ModuleList(list(model.blocks)[:k])
+    steps = range(1, nb) if stage is None else range(1, len(model.blocks[stage].res_blocks) + 1)
+    for k in steps:          # the head needs the full net; prefixes end with a feature map
+        sub = _shallow(model)
+        if stage is None:
+            sub._modules["blocks"] = nn.ModuleList(list(model.blocks)[:k])
+        else:
+            st = _shallow(model.blocks[stage])
+            st._modules["res_blocks"] = nn.ModuleList(list(model.blocks[stage].res_blocks)[:k])
+            sub._modules["blocks"] = nn.ModuleList(list(model.blocks)[:stage] + [st])
         ref = oracle_forward(sub, x_cpu)
         dev_in = [t.cuda() for t in inp] if is_sf else inp.cuda()
         try:
@@ -37,7 +50,9 @@ def main():
             print("blocks[:%d]: multi-pathway output, skipped" % k)
             continue
         err = float((out - ref).abs().max()) / max(float(ref.abs().max()), 1e-9)
-        print("blocks[:%d] %-28s out %s  max|d|/max|ref| = %.3e" % (k, type(model.blocks[k - 1]).__name__, tuple(ref.shape), err), flush=True)
+        tag = "blocks[:%d]" % k if stage is None else "blocks[%d].res_blocks[:%d]" % (stage, k)
+        print("%s out %s  max|d|/max|ref| = %.3e  mean|d|/max|ref| = %.3e" % (tag, tuple(ref.shape), err,
+              float((out - ref).abs().mean()) / max(float(ref.abs().max()), 1e-9)), flush=True)
 
 
 main()
