@@ -214,6 +214,30 @@ int pv_dwconv3d_fwd(const pv_conv3d_desc* d, const void* x, const void* w, const
 int pv_conv3d_tcgen05_supported(const pv_conv3d_desc* d);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused bottleneck block for narrow pathways (SlowFast Fast pathway), ONE launch:
+ *   a = relu(bn_a(conv_a(x)))  (kt,1,1) C_in -> C_mid;   b = relu(bn_b(conv_b(a)))  (1,3,3) stride (1,sb,sb), pad 1
+ *   y = act(bn_c(conv_c(b)) + shortcut),  shortcut = x (identity) or bn_1(conv_1(x)), 1x1x1 stride (1,sb,sb)
+ * Replaces BottleneckBlock.forward (models/resnet.py:1345-1365) + ResBlock.forward (resnet.py:1179-1189) for
+ * C_mid in {8, 16, 32}: a and b stay in shared memory, x is read once, the residual comes from the resident x tile.
+ * x, y: NDHWC f16; weights f16 packed [n][k], k = tap * C + ci, K zero-padded to a multiple of 16:
+ *   wa [Cmid][pad16(kt*Cin)], wb [Cmid][pad16(9*Cmid)], wc [Cout][pad16(Cmid)], wsc [Cout][pad16(Cin)] (or NULL);
+ * folded BatchNorm (scale, bias) fp32 per output channel for each of the four convolutions.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pv_bottleneck_desc {
+  int N, T, H, W;            /* input extents; output (T, (H-1)/sb+1, (W-1)/sb+1)                 */
+  int Cin, Cmid, Cout;       /* padded channel counts (multiples of 8; Cin a power of two)        */
+  int kt, sb;                /* temporal taps of conv_a (1|3, padding kt/2); spatial stride of conv_b (1|2) */
+  int has_shortcut;          /* 1: projection shortcut conv_1 + bn_1; 0: identity (Cin == Cout, sb == 1)    */
+  int act;                   /* PV_ACT_RELU | PV_ACT_NONE after the residual add                  */
+  long long x_row_stride, y_row_stride;
+} pv_bottleneck_desc;
+int pv_bottleneck_fused_supported(const pv_bottleneck_desc* d);
+int pv_bottleneck_fused_fwd(const pv_bottleneck_desc* d, const void* x, const void* wa, const void* wb,
+                            const void* wc, const void* wsc, const float* sa, const float* ba,
+                            const float* sb, const float* bb, const float* sc, const float* bc,
+                            const float* ssc, const float* bsc, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Pooling. nn.MaxPool3d stem pool (models/stem.py:94-100), nn.AvgPool3d head pools
  * (models/head.py:116-118, models/slowfast.py:333-341, models/x3d.py:490), MViT skip-path
  * MaxPool3d (layers/attention.py:677-679).  AvgPool divides by the full kernel volume

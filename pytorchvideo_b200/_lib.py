@@ -35,6 +35,12 @@ class ClipBatchDesc(C.Structure):
                 ("div255", C.c_int), ("normalize", C.c_int), ("src_dtype", C.c_int), ("dst_dtype", C.c_int)]
 
 
+class BottleneckDesc(C.Structure):
+    _fields_ = [("N", C.c_int), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("Cin", C.c_int), ("Cmid", C.c_int), ("Cout", C.c_int), ("kt", C.c_int), ("sb", C.c_int),
+                ("has_shortcut", C.c_int), ("act", C.c_int), ("x_row_stride", c_ll), ("y_row_stride", c_ll)]
+
+
 class Conv3dDesc(C.Structure):
     _fields_ = [("dtype", C.c_int),
                 ("N", C.c_int), ("Ti", C.c_int), ("Hi", C.c_int), ("Wi", C.c_int), ("Ci", C.c_int),
@@ -94,6 +100,8 @@ SIGNATURES = {
     "pv_temporal_tap_sum": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_ll, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_ll, c_ll, c_vp]),
     "pv_conv3d_tcgen05_supported": (C.c_int, [C.POINTER(Conv3dDesc)]),
+    "pv_bottleneck_fused_supported": (C.c_int, [C.POINTER(BottleneckDesc)]),
+    "pv_bottleneck_fused_fwd": (C.c_int, [C.POINTER(BottleneckDesc)] + [c_vp] * 15),
     "pv_pool3d_fwd": (C.c_int, [C.POINTER(Pool3dDesc), c_vp, c_vp, c_vp]),
     "pv_channel_sum": (C.c_int, [c_vp, C.c_int, c_ll, C.c_int, c_ll, C.c_int, c_vp, c_vp]),
     "pv_se_gate": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp,
