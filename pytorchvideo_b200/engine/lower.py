@@ -176,8 +176,59 @@ class Lowering:
             x = self.lower(blk, x, "%s.res_blocks.%d" % (name, i))
         return x
 
+    def _fusable_bottleneck(self, m, x):
+        """ResBlock whose whole body runs as ONE launch of the fused narrow-pathway kernel (csrc/pv_fastblock.cu):
+        plain Conv3d / BatchNorm / ReLU bottleneck with a (kt,1,1) conv_a, a dense (1,3,3) conv_b of stride
+        (1,s,s) and an inner width of 8 / 16 / 32 channels (the SlowFast Fast pathway, res2-res4)."""
+        import ctypes as C_
+        import os
+        p = self.p
+        if not p.use_tcgen05 or os.environ.get("PVB200_NO_FUSED"):
+            return False
+        b = m.branch2
+        if type(b).__name__ != "BottleneckBlock" or not isinstance(x, TRef):
+            return False
+        convs = (b.conv_a, b.conv_b, b.conv_c) + ((m.branch1_conv,) if m.branch1_conv is not None else ())
+        for c in convs:
+            if type(c) is not nn.Conv3d or c.groups != 1 or _t3(c.dilation) != (1, 1, 1) or c.padding_mode != "zeros" \
+                    or isinstance(c.padding, str):
+                return False
+        for n_ in (b.norm_a, b.norm_b, b.norm_c):
+            if n_ is None or not _is_bn(n_):
+                return False
+        if type(b.act_a).__name__ != "ReLU" or type(b.act_b).__name__ != "ReLU":
+            return False
+        if m.activation is not None and type(m.activation).__name__ not in ("ReLU", "Identity"):
+            return False
+        ka, kb, kc = _t3(b.conv_a.kernel_size), _t3(b.conv_b.kernel_size), _t3(b.conv_c.kernel_size)
+        if ka[1:] != (1, 1) or ka[0] not in (1, 3) or _t3(b.conv_a.stride) != (1, 1, 1) or _t3(b.conv_a.padding) != (ka[0] // 2, 0, 0):
+            return False
+        sb = _t3(b.conv_b.stride)
+        if kb != (1, 3, 3) or sb[0] != 1 or sb[1] != sb[2] or sb[1] not in (1, 2) or _t3(b.conv_b.padding) != (0, 1, 1):
+            return False
+        if kc != (1, 1, 1) or _t3(b.conv_c.stride) != (1, 1, 1) or _t3(b.conv_c.padding) != (0, 0, 0):
+            return False
+        if b.conv_a.in_channels != x.C or x.lazy_src is not None:
+            return False
+        if m.branch1_conv is not None:
+            c1 = m.branch1_conv
+            if _t3(c1.kernel_size) != (1, 1, 1) or _t3(c1.stride) != (1, sb[1], sb[1]) or _t3(c1.padding) != (0, 0, 0):
+                return False
+            n1 = getattr(m, "branch1_norm", None)
+            if n1 is not None and not _is_bn(n1):
+                return False
+        act = L.ACT_RELU if (m.activation is not None and type(m.activation).__name__ == "ReLU") else L.ACT_NONE
+        d = p.fused_bottleneck_desc(x, x.Cp, b.conv_a.out_channels, b.conv_c.out_channels, ka[0], sb[1],
+                                    m.branch1_conv is not None, act)
+        return bool(p.lib.pv_bottleneck_fused_supported(C_.byref(d)))
+
     def lower_ResBlock(self, m, x, name):
         # models/resnet.py:1179-1189; branch_fusion is x + y for every builder in scope.
+        if self._fusable_bottleneck(m, x):
+            b = m.branch2
+            act = L.ACT_RELU if (m.activation is not None and type(m.activation).__name__ == "ReLU") else L.ACT_NONE
+            return self.p.emit_bottleneck_fused(x, b.conv_a, b.norm_a, b.conv_b, b.norm_b, b.conv_c, b.norm_c,
+                                                m.branch1_conv, getattr(m, "branch1_norm", None), act, name + ".fused")
         if m.branch1_conv is not None:
             shortcut = self.conv(x, m.branch1_conv, getattr(m, "branch1_norm", None), None, None, name + ".branch1")
         else:

@@ -97,3 +97,17 @@ def pack_dense_window(w, ci_pad, co_pad, lead=0):
     tmp[..., :ci] = src
     out[:co, :, lead * ci_pad: (lead + kw) * ci_pad] = tmp.reshape(co, kt * kh, kw * ci_pad)
     return out.reshape(co_pad, kt * kh * win).contiguous()
+
+
+def pack_rows_k16(w, ci_pad, co_pad):
+    """[Co, Ci, kt, kh, kw] -> f16 [co_pad][pad16(taps * ci_pad)], k = tap * ci_pad + ci (zero padded): the
+    [n][k] operand layout of the fused bottleneck kernel (csrc/pv_fastblock.cu)."""
+    co, ci, kt, kh, kw = w.shape
+    taps = kt * kh * kw
+    k = taps * ci_pad
+    kp = (k + 15) // 16 * 16
+    out = torch.zeros(co_pad, kp, dtype=torch.float16)
+    t = torch.zeros(co, taps, ci_pad, dtype=torch.float16)
+    t[:, :, :ci] = w.detach().cpu().permute(0, 2, 3, 4, 1).reshape(co, taps, ci).to(torch.float16)
+    out[:co, :k] = t.reshape(co, k)
+    return out.contiguous()

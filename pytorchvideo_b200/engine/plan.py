@@ -418,6 +418,49 @@ class Plan:
                  reads=(x,) + ((residual,) if residual is not None else ()), writes=(y,) + ((sums,) if sums is not None else ()))
         return y
 
+    def fused_bottleneck_desc(self, x, cin_pad, cmid, cout, kt, sb, has_shortcut, act):
+        d = L.BottleneckDesc()
+        d.N, d.T, d.H, d.W = x.N, x.T, x.H, x.W
+        d.Cin, d.Cmid, d.Cout = cin_pad, PK.pad8(cmid), PK.pad8(cout)
+        d.kt, d.sb, d.has_shortcut, d.act = kt, sb, 1 if has_shortcut else 0, act
+        d.x_row_stride, d.y_row_stride = x.row_stride, PK.pad8(cout)
+        return d
+
+    def emit_bottleneck_fused(self, x, conv_a, bn_a, conv_b, bn_b, conv_c, bn_c, sc_conv, sc_bn, act, name):
+        """ONE launch for conv_a -> conv_b -> conv_c (+ projection / identity shortcut) + activation
+        (csrc/pv_fastblock.cu); the caller has checked eligibility with pv_bottleneck_fused_supported."""
+        self.materialize_input(x)
+        kt, sb = int(conv_a.kernel_size[0]), int(conv_b.stride[1])
+        cmid, cout = conv_a.out_channels, conv_c.out_channels
+        d = self.fused_bottleneck_desc(x, x.Cp, cmid, cout, kt, sb, sc_conv is not None, act)
+        Ho, Wo = (x.H - 1) // sb + 1, (x.W - 1) // sb + 1
+        y = self.new_tensor(x.N, x.T, Ho, Wo, cout, Cp=d.Cout)
+        wa = self.const(PK.pack_rows_k16(conv_a.weight, x.Cp, d.Cmid))
+        wb = self.const(PK.pack_rows_k16(conv_b.weight, d.Cmid, d.Cmid))
+        wc = self.const(PK.pack_rows_k16(conv_c.weight, d.Cmid, d.Cout))
+        ws = self.const(PK.pack_rows_k16(sc_conv.weight, x.Cp, d.Cout)) if sc_conv is not None else None
+        sa, ba = (self.const(t) for t in PK.fold_bn(conv_a.bias, bn_a, cmid, d.Cmid))
+        sbb, bbb = (self.const(t) for t in PK.fold_bn(conv_b.bias, bn_b, cmid, d.Cmid))
+        scc, bcc = (self.const(t) for t in PK.fold_bn(conv_c.bias, bn_c, cout, d.Cout))
+        ss, bs = (self.const(t) for t in PK.fold_bn(sc_conv.bias, sc_bn, cout, d.Cout)) if sc_conv is not None else (None, None)
+        lib = self.lib
+
+        def fn(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+            L.check(lib.pv_bottleneck_fused_fwd(C.byref(d), x.ptr(), wa.data_ptr(), wb.data_ptr(), wc.data_ptr(),
+                                                ws.data_ptr() if ws is not None else None, sa.data_ptr(), ba.data_ptr(),
+                                                sbb.data_ptr(), bbb.data_ptr(), scc.data_ptr(), bcc.data_ptr(),
+                                                ss.data_ptr() if ss is not None else None,
+                                                bs.data_ptr() if bs is not None else None, y.ptr(), stream),
+                    "pv_bottleneck_fused_fwd(%s)" % name)
+        m_in, m_out = x.N * x.T * x.H * x.W, x.N * x.T * Ho * Wo
+        cin = conv_a.in_channels
+        flops = 2.0 * (m_in * cmid * cin * kt + m_out * cmid * cmid * 9 + m_out * cout * cmid +
+                       (m_out * cout * cin if sc_conv is not None else 0))
+        nbytes = (m_in * cin + m_out * cout) * 2 + sum(t.numel() for t in (wa, wb, wc)) * 2
+        self.add(name, fn, "fused_block", flops, nbytes, reads=(x,), writes=(y,))
+        return y
+
     def emit_pool(self, x, mode, kernel, stride, padding, name="pool"):
         self.materialize_input(x)
         kt, kh, kw = kernel

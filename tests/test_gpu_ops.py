@@ -222,3 +222,51 @@ def test_full_size_conv_is_exactly_homogeneous(shape):
         patch = xp[:, t:t + k[0], h:h + k[1], ww:ww + k[2]]
         ref = (w * patch.unsqueeze(0)).sum(dim=(1, 2, 3, 4))
         assert torch.allclose(y1[n, :, t, h, ww], ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) + 1e-4)
+
+
+# ---- fused narrow-pathway bottleneck block (csrc/pv_fastblock.cu) ------------------------------------------------
+FUSED_BLOCK_CASES = [
+    # (N, T, H, W, dim_in, dim_inner, dim_out, kt_a, spatial stride)      SlowFast Fast-pathway geometries, small extents
+    (2, 5, 13, 11, 8, 8, 32, 3, 1),        # res2 block 0: projection shortcut from the 8-channel stem output
+    (2, 6, 17, 15, 32, 8, 32, 3, 1),       # res2 blocks 1-2: identity shortcut, edge tiles in both directions
+    (1, 4, 18, 14, 32, 16, 64, 3, 2),      # res3 block 0: stride 2, projection shortcut
+    (1, 7, 9, 20, 64, 16, 64, 3, 1),       # res3 blocks 1-3
+    (1, 3, 14, 14, 64, 32, 128, 3, 2),     # res4 block 0
+    (2, 9, 14, 14, 128, 32, 128, 3, 1),    # res4 blocks 1-5: several T chunks
+    (1, 4, 12, 12, 32, 8, 32, 1, 1),       # pointwise conv_a (kt = 1)
+    (1, 33, 7, 7, 32, 8, 32, 3, 1),        # long clip: ring wrap-around over many frames
+]
+
+
+@pytest.mark.parametrize("case", FUSED_BLOCK_CASES, ids=[str(i) for i in range(len(FUSED_BLOCK_CASES))])
+def test_fused_bottleneck_block(case):
+    """ONE launch for conv_a -> conv_b -> conv_c (+ shortcut) + ReLU vs the oracle's unfused ResBlock.forward
+    (models/resnet.py:1179-1189, 1345-1365) on f16-grid operands; also equal (to f16 rounding of the two
+    intermediates) to the engine's own unfused lowering."""
+    import os
+    from oracle.interp import oracle_forward
+    from pytorchvideo_b200 import testing as TS
+    from pytorchvideo_b200.engine import compile_model
+    from pytorchvideo_b200.models.resnet import create_bottleneck_block, create_res_block
+    N, T, H, W, cin, cmid, cout, kt, s = case
+    blk = create_res_block(dim_in=cin, dim_inner=cmid, dim_out=cout, bottleneck=create_bottleneck_block,
+                           conv_a_kernel_size=(kt, 1, 1), conv_a_stride=(1, 1, 1), conv_a_padding=(kt // 2, 0, 0),
+                           conv_b_stride=(1, s, s))
+    blk = TS.randomize_model(blk, seed=sum(case), f16_weights=True).eval()
+    x = TS.f16_exact(torch.randn(N, cin, T, H, W, generator=torch.Generator().manual_seed(7)))
+    ref = oracle_forward(blk, x)
+    cm = compile_model(blk, x.cuda(), dtype="f16", use_graph=False)
+    assert cm.plan.stats.get("fused_block", 0) == 1 and cm.plan.num_launches() == 3      # layout in, fused block, layout out
+    out = cm(x.cuda()).float().cpu()
+    assert out.shape == ref.shape
+    scale = float(ref.abs().max())
+    err = (out - ref).abs()
+    assert bool((err <= 2e-3 * ref.abs() + 1e-3 * scale).all()), float(err.max()) / scale
+    os.environ["PVB200_NO_FUSED"] = "1"
+    try:
+        cm2 = compile_model(blk, x.cuda(), dtype="f16", use_graph=False)
+        assert cm2.plan.stats.get("fused_block", 0) == 0
+        out2 = cm2(x.cuda()).float().cpu()
+    finally:
+        del os.environ["PVB200_NO_FUSED"]
+    assert bool(((out - out2).abs() <= 2e-3 * ref.abs() + 1e-3 * scale).all())

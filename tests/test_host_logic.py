@@ -89,10 +89,12 @@ def test_lowering_slowfast_dry_run():
     plan, out_shape = lower_only(m, TS.slowfast_inputs(clip))
     assert out_shape == (2, 400)
     names = [n for n, _ in plan.ops]
-    # 2 stems (conv+pool each), 4 fusion convs, (3+4+6+3)*2 blocks * 3 convs + 8 shortcuts, head
+    # 2 stems (conv+pool each), 4 fusion convs, (3+4+6+3)*2 blocks * 3 convs + 8 shortcuts, head; the 13 blocks of the
+    # Fast pathway's res2-res4 (3 convs each + their 3 projection shortcuts) are ONE fused launch each
     n_conv = plan.stats["tcgen05"] + plan.stats["direct"]
-    assert n_conv == 2 + 4 + 2 * (16 * 3 + 4) + 1
-    assert plan.stats["tcgen05"] >= 100           # every C_in%8==0 dense conv goes to the tensor cores
+    assert plan.stats["fused_block"] == 13
+    assert n_conv == 2 + 4 + 2 * (16 * 3 + 4) + 1 - (13 * 3 + 3)
+    assert plan.stats["tcgen05"] == n_conv        # every C_in%8==0 dense conv goes to the tensor cores
     assert any(n.endswith("multipathway_fusion.conv_fast_to_slow") for n in names)
     assert "blocks.6.output_pool" in names
 
@@ -179,7 +181,7 @@ def test_slowfast_pathways_are_scheduled_on_two_lanes():
     names = [n for n, _ in plan.ops]
     lane = dict(zip(names, plan.op_lane))
     assert lane["blocks.1.multipathway_blocks.0.res_blocks.0.branch2.conv_a"] == 0
-    assert lane["blocks.1.multipathway_blocks.1.res_blocks.0.branch2.conv_a"] == 1
+    assert lane["blocks.1.multipathway_blocks.1.res_blocks.0.fused"] == 1     # Fast-pathway blocks: one fused launch each
     assert lane["blocks.1.multipathway_fusion.conv_fast_to_slow"] == 1
     edges = [(names[j], names[i]) for i, w in enumerate(sc["waits"]) for j in w]
     for k in range(4):
@@ -189,6 +191,7 @@ def test_slowfast_pathways_are_scheduled_on_two_lanes():
     assert len(edges) == 5                       # nothing else crosses lanes
     # every op that is waited for records an event
     assert sc["signals"] == {names.index(a) for a, _ in edges}
+    assert plan.stats["fused_block"] == 13 and len(names) == 90               # res2-res4 of the Fast pathway (3 + 4 + 6 blocks)
     # single-lane models keep one stream
     p2, _ = lower_only(PH.slow_r50().eval(), torch.zeros(1, 3, 8, 224, 224))
     p2._schedule()

@@ -138,13 +138,10 @@ def test_normalize_zero_mean_unit_std_property():
                                   "mvit_base_32x3"])
 def test_oracle_reproduces_reference_model_goldens(case):
     g = _gold("model_%s.pt" % case)
-    hub, kw, B, T, H, W, is_sf = TS.MODEL_CASES[case]
-    model = getattr(PH, hub)(**kw)
-    TS.randomize_model(model, seed=g["weight_seed"])
+    model, inp, is_sf = TS.build_case(case, PH, g["weight_seed"], g["input_seed"])
     assert abs(TS.state_checksum(model) - g["state_checksum"]) <= 1e-6 * abs(g["state_checksum"])
-    clip = TS.synthetic_clip(B, T, H, W, seed=g["input_seed"])
-    np.testing.assert_allclose(TS.tensor_checksum(clip), g["input_checksum"], rtol=1e-12)
-    out = oracle_forward(model, TS.slowfast_inputs(clip) if is_sf else clip)
+    np.testing.assert_allclose(TS.tensor_checksum(inp[1] if is_sf else inp), g["input_checksum"], rtol=1e-12)
+    out = oracle_forward(model, inp)
     ref = g["output"]
     # same ATen ops in the same order; allow for a different CPU's summation order
     assert out.shape == ref.shape
