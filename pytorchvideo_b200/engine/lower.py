@@ -208,7 +208,7 @@ class Lowering:
             return False
         if kc != (1, 1, 1) or _t3(b.conv_c.stride) != (1, 1, 1) or _t3(b.conv_c.padding) != (0, 0, 0):
             return False
-        if b.conv_a.in_channels != x.C or x.lazy_src is not None:
+        if b.conv_a.in_channels != x.C or x.C != x.Cp:      # (a 3-channel network input is padded to 4: not this kernel)
             return False
         if m.branch1_conv is not None:
             c1 = m.branch1_conv
