@@ -33,7 +33,7 @@ struct FbParams {
   int ldwa, ldwb, ldwc, ldws;  // shared-memory row pitches of the weight matrices (elements, K + 8: conflict-free B loads)
   long long xrs, yrs;        // row strides (elements)
   // shared memory carve-up (byte offsets)
-  unsigned off_x, x_slot_bytes, off_a, off_b, off_y, off_wa, off_wb, off_wc, off_ws, off_sb;
+  unsigned off_x, x_slot_bytes, off_a, off_b, off_y, off_wa, off_wb, off_wc, off_ws, off_sb, off_tab;
 };
 
 __device__ __forceinline__ unsigned fb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -63,43 +63,54 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, bool v
 constexpr int FB_WARPS = 8;
 constexpr int FB_THREADS = FB_WARPS * 32;
 constexpr int FB_SLOTS = 4;      // frame ring: t-1, t, t+1 in use, t+2 in flight
+constexpr int FB_MT = 2;         // m-tiles (16 rows) per warp and phase: tiles are chosen with <= 256 rows
+constexpr unsigned FB_SKIP = 0xffffffffu;
 
-// One GEMM phase for one m-tile of 16 rows: acc[nt] += A(16 x K) * W^T, n-tiles nt0 .. nt0+NT-1.
-// Lane l feeds ldmatrix with the address of A row fb_lane_row(l) = (l & 7) + 8 * ((l >> 3) & 1), K-half (l >> 4):
-// chunk_addr(kk) = shared-memory BYTE address (u32) of the 16-byte chunk A[that row][kk .. kk+7], kk a multiple of 8.
-// (The row is fixed per lane, so callers hoist everything row-dependent out of the K loop.)
+template <unsigned ROW_BYTES>
+__device__ __forceinline__ unsigned fb_swz_c(unsigned row, unsigned chunk) {   // fb_swz with a compile-time row size
+  if (ROW_BYTES >= 128u) return chunk ^ (row & 7u);
+  if (ROW_BYTES == 64u) return chunk ^ ((row >> 1) & 3u);
+  if (ROW_BYTES == 32u) return chunk ^ ((row >> 2) & 1u);
+  return chunk;
+}
 __device__ __forceinline__ int fb_lane_row(int lane) { return (lane & 7) + ((lane >> 3) & 1) * 8; }
-
-template <int NT, typename ChunkAddr>
-__device__ __forceinline__ void fb_gemm(float (&acc)[NT][4], int K, const __half* __restrict__ wsm, int ldw, int n0,
-                                        int lane, ChunkAddr chunk_addr) {
-  const int kh = (lane >> 4) * 8;
-  const int g = lane >> 2, q = lane & 3;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    unsigned a[4];
-    ldmatrix_x4(chunk_addr(k0 + kh), a);
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const __half* wrow = wsm + (size_t)(n0 + nt * 8 + g) * ldw + k0 + 2 * q;
-      const unsigned b0 = *reinterpret_cast<const unsigned*>(wrow);
-      const unsigned b1 = *reinterpret_cast<const unsigned*>(wrow + 8);
-      mma_16816(acc[nt], a, b0, b1);
-    }
-  }
+__device__ __forceinline__ unsigned fb_lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void fb_sts32(unsigned addr, unsigned v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned fb_pack(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&h);
 }
 
-template <int CMID>
+// The instruction diet (ncu, first version: 2340 warp-instructions per warp and frame at IPC 2.1, tensor pipe 5 %
+// busy - issue-bound on address arithmetic): every shape is a template parameter, so all K loops unroll and the
+// weight-fragment loads use immediate offsets; everything that depends on the POSITION a lane works on (ldmatrix
+// row addresses, image-border flags, residual and output offsets) is the same for every frame and is computed once
+// per CTA, before the frame loop.
+template <int CIN, int CMID, int KT, int SB, bool HAS_SC>
 __global__ void __launch_bounds__(FB_THREADS)
 bottleneck_fused_kernel(const __grid_constant__ FbParams P, const __half* __restrict__ x, const __half* __restrict__ wa,
                         const __half* __restrict__ wb, const __half* __restrict__ wc, const __half* __restrict__ wsc,
                         const float* __restrict__ sa, const float* __restrict__ ba, const float* __restrict__ sb_,
                         const float* __restrict__ bb, const float* __restrict__ sc, const float* __restrict__ bc,
                         const float* __restrict__ ssc, const float* __restrict__ bsc, __half* __restrict__ y) {
-  constexpr int NTM = CMID / 8;                  // n-tiles of the inner width
+  constexpr int NTM = CMID / 8;                          // n-tiles of the inner width
+  constexpr int COUT = 4 * CMID;
+  constexpr int NG = COUT / 32;                          // 32-channel output groups of phase C
+  constexpr int KA = (KT * CIN + 15) / 16 * 16, KB = (9 * CMID + 15) / 16 * 16, KC = (CMID + 15) / 16 * 16, KS = (CIN + 15) / 16 * 16;
+  constexpr int LDWA = KA + 8, LDWB = KB + 8, LDWC = KC + 8, LDWS = KS + 8;
+  constexpr unsigned XROW = CIN * 2, AROW = CMID * 2, YROW = COUT * 2;
+  constexpr int XCH = XROW / 16;
+  constexpr int PAD_T = KT / 2;
   extern __shared__ __align__(128) unsigned char fb_smem[];
   const unsigned sbase = fb_smem_u32(fb_smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, q = lane & 3;
+  const int g = lane >> 2, q = lane & 3, hi = lane >> 4;
 
   // ---- which tile
   int bid = blockIdx.x;
@@ -108,119 +119,168 @@ bottleneck_fused_kernel(const __grid_constant__ FbParams P, const __half* __rest
   const int tch = bid % P.tchunks;
   const int n = bid / P.tchunks;
   const int oy0 = th * P.TH, ox0 = tw * P.TW;                 // output tile origin
-  const int iy0 = oy0 * P.sb - 1, ix0 = ox0 * P.sb - 1;       // halo tile origin in the input (may be -1)
+  const int iy0 = oy0 * SB - 1, ix0 = ox0 * SB - 1;           // halo tile origin in the input (may be -1)
   const int t_begin = tch * P.TC, t_end = min(P.T, t_begin + P.TC);
   const int npos_in = P.RH * P.RW, npos_out = P.TH * P.TW;
-  const int pad_t = P.kt >> 1;
-  const unsigned xrow_bytes = (unsigned)P.Cin * 2u, arow_bytes = (unsigned)CMID * 2u;
-  const unsigned xchunks = xrow_bytes >> 4;
-  const int cin_log2 = 31 - __clz(P.Cin);
 
-  // ---- weights + folded BN into shared memory (once per CTA)
-  {
-    __half* s_wa = reinterpret_cast<__half*>(fb_smem + P.off_wa);
-    __half* s_wb = reinterpret_cast<__half*>(fb_smem + P.off_wb);
-    __half* s_wc = reinterpret_cast<__half*>(fb_smem + P.off_wc);
-    __half* s_ws = reinterpret_cast<__half*>(fb_smem + P.off_ws);
-    for (int i = tid; i < CMID * (P.KA >> 3); i += FB_THREADS) {
-      const int r = i / (P.KA >> 3), c = (i - r * (P.KA >> 3)) * 8;
-      *reinterpret_cast<uint4*>(s_wa + r * P.ldwa + c) = *reinterpret_cast<const uint4*>(wa + (size_t)r * P.KA + c);
-    }
-    for (int i = tid; i < CMID * (P.KB >> 3); i += FB_THREADS) {
-      const int r = i / (P.KB >> 3), c = (i - r * (P.KB >> 3)) * 8;
-      *reinterpret_cast<uint4*>(s_wb + r * P.ldwb + c) = *reinterpret_cast<const uint4*>(wb + (size_t)r * P.KB + c);
-    }
-    for (int i = tid; i < P.Cout * (P.KC >> 3); i += FB_THREADS) {
-      const int r = i / (P.KC >> 3), c = (i - r * (P.KC >> 3)) * 8;
-      *reinterpret_cast<uint4*>(s_wc + r * P.ldwc + c) = *reinterpret_cast<const uint4*>(wc + (size_t)r * P.KC + c);
-    }
-    if (P.has_sc)
-      for (int i = tid; i < P.Cout * (P.KS >> 3); i += FB_THREADS) {
-        const int r = i / (P.KS >> 3), c = (i - r * (P.KS >> 3)) * 8;
-        *reinterpret_cast<uint4*>(s_ws + r * P.ldws + c) = *reinterpret_cast<const uint4*>(wsc + (size_t)r * P.KS + c);
-      }
-    float* s_sb = reinterpret_cast<float*>(fb_smem + P.off_sb);     // [sa ba sb bb](CMID each) [sc bc ssc bsc](Cout each)
-    for (int i = tid; i < CMID; i += FB_THREADS) {
-      s_sb[i] = sa[i]; s_sb[CMID + i] = ba[i]; s_sb[2 * CMID + i] = sb_[i]; s_sb[3 * CMID + i] = bb[i];
-    }
-    for (int i = tid; i < P.Cout; i += FB_THREADS) {
-      float* o = s_sb + 4 * CMID;
-      o[i] = sc[i]; o[P.Cout + i] = bc[i];
-      o[2 * P.Cout + i] = P.has_sc ? ssc[i] : 0.f; o[3 * P.Cout + i] = P.has_sc ? bsc[i] : 0.f;
-    }
+  // ---- weights, folded BN and the per-position source table into shared memory (once per CTA)
+  __half* s_wa = reinterpret_cast<__half*>(fb_smem + P.off_wa);
+  __half* s_wb = reinterpret_cast<__half*>(fb_smem + P.off_wb);
+  __half* s_wc = reinterpret_cast<__half*>(fb_smem + P.off_wc);
+  __half* s_ws = reinterpret_cast<__half*>(fb_smem + P.off_ws);
+  float* s_sb = reinterpret_cast<float*>(fb_smem + P.off_sb);       // [sa ba sb bb](CMID each) [sc bc ssc bsc](COUT each)
+  int* s_src = reinterpret_cast<int*>(fb_smem + P.off_tab);          // element offset of the position inside a frame, -1 outside
+  for (int i = tid; i < CMID * (KA / 8); i += FB_THREADS) {
+    const int r = i / (KA / 8), c = (i - r * (KA / 8)) * 8;
+    *reinterpret_cast<uint4*>(s_wa + r * LDWA + c) = *reinterpret_cast<const uint4*>(wa + (size_t)r * KA + c);
   }
-  const __half* s_wa = reinterpret_cast<const __half*>(fb_smem + P.off_wa);
-  const __half* s_wb = reinterpret_cast<const __half*>(fb_smem + P.off_wb);
-  const __half* s_wc = reinterpret_cast<const __half*>(fb_smem + P.off_wc);
-  const __half* s_ws = reinterpret_cast<const __half*>(fb_smem + P.off_ws);
-  const float* s_sb = reinterpret_cast<const float*>(fb_smem + P.off_sb);
+  for (int i = tid; i < CMID * (KB / 8); i += FB_THREADS) {
+    const int r = i / (KB / 8), c = (i - r * (KB / 8)) * 8;
+    *reinterpret_cast<uint4*>(s_wb + r * LDWB + c) = *reinterpret_cast<const uint4*>(wb + (size_t)r * KB + c);
+  }
+  for (int i = tid; i < COUT * (KC / 8); i += FB_THREADS) {
+    const int r = i / (KC / 8), c = (i - r * (KC / 8)) * 8;
+    *reinterpret_cast<uint4*>(s_wc + r * LDWC + c) = *reinterpret_cast<const uint4*>(wc + (size_t)r * KC + c);
+  }
+  if (HAS_SC)
+    for (int i = tid; i < COUT * (KS / 8); i += FB_THREADS) {
+      const int r = i / (KS / 8), c = (i - r * (KS / 8)) * 8;
+      *reinterpret_cast<uint4*>(s_ws + r * LDWS + c) = *reinterpret_cast<const uint4*>(wsc + (size_t)r * KS + c);
+    }
+  for (int i = tid; i < CMID; i += FB_THREADS) {
+    s_sb[i] = sa[i]; s_sb[CMID + i] = ba[i]; s_sb[2 * CMID + i] = sb_[i]; s_sb[3 * CMID + i] = bb[i];
+  }
+  for (int i = tid; i < COUT; i += FB_THREADS) {
+    float* o = s_sb + 4 * CMID;
+    o[i] = sc[i]; o[COUT + i] = bc[i];
+    o[2 * COUT + i] = HAS_SC ? ssc[i] : 0.f; o[3 * COUT + i] = HAS_SC ? bsc[i] : 0.f;
+  }
+  for (int pos = tid; pos < npos_in; pos += FB_THREADS) {
+    const int py = pos / P.RW, px = pos - py * P.RW;
+    const int iy = iy0 + py, ix = ix0 + px;
+    const bool ok = (unsigned)iy < (unsigned)P.H && (unsigned)ix < (unsigned)P.W;
+    s_src[pos] = ok ? (int)(((long long)iy * P.W + ix) * P.xrs) : -1;
+  }
+  for (int opos = tid; opos < npos_out; opos += FB_THREADS) {       // output position -> element offset inside a y frame
+    const int qy = opos / P.TW, qx = opos - qy * P.TW;
+    const int oy = oy0 + qy, ox = ox0 + qx;
+    s_src[256 + opos] = (oy < P.Ho && ox < P.Wo) ? (int)(((long long)oy * P.Wo + ox) * P.yrs) : -1;
+  }
+  const float* s_c = s_sb + 4 * CMID;
 
-  // ---- frame loader: halo tile of frame f -> ring slot (f + pad_t + 4) & 3, zero-filled outside the clip
+  // ---- frame loader: halo tile of frame f -> ring slot (f + 8) & 3, zero-filled outside the clip
   const __half* xn = x + (size_t)n * P.T * P.H * P.W * P.xrs;
+  const size_t frame_elems = (size_t)P.H * P.W * P.xrs;
   auto load_frame = [&](int f) {
-    const unsigned slot = (unsigned)(f + 8) & (FB_SLOTS - 1);
-    const unsigned dst0 = sbase + P.off_x + slot * P.x_slot_bytes;
+    const unsigned dst0 = sbase + P.off_x + ((unsigned)(f + 8) & (FB_SLOTS - 1)) * P.x_slot_bytes;
     const bool f_ok = f >= 0 && f < P.T;
-    const int total = npos_in * (int)xchunks;
-    for (int i = tid; i < total; i += FB_THREADS) {
-      const int pos = i / (int)xchunks, ch = i - pos * (int)xchunks;
-      const int py = pos / P.RW, px = pos - py * P.RW;
-      const int iy = iy0 + py, ix = ix0 + px;
-      const bool ok = f_ok && (unsigned)iy < (unsigned)P.H && (unsigned)ix < (unsigned)P.W;
-      const __half* src = ok ? xn + ((size_t)((size_t)f * P.H + iy) * P.W + ix) * P.xrs + ch * 8 : x;
-      cp_async16(dst0 + (unsigned)pos * xrow_bytes + (fb_swz((unsigned)pos, (unsigned)ch, xrow_bytes) << 4), src, ok);
+    const __half* xf = xn + (f_ok ? (size_t)f * frame_elems : 0);
+    for (int i = tid; i < npos_in * XCH; i += FB_THREADS) {
+      const unsigned pos = (unsigned)i / XCH, ch = (unsigned)i % XCH;
+      const int so = s_src[pos];
+      const bool ok = f_ok && so >= 0;
+      cp_async16(dst0 + pos * XROW + (fb_swz_c<XROW>(pos, ch) << 4), ok ? xf + so + ch * 8 : x, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  __syncthreads();                                             // s_src is read by the loader
+  for (int f = t_begin - PAD_T; f <= t_begin + PAD_T; ++f) load_frame(f);
 
-  // prologue: frames t_begin - pad_t .. t_begin + pad_t (pad_t = 0: just t_begin), then one frame ahead
-  for (int f = t_begin - pad_t; f <= t_begin + pad_t; ++f) load_frame(f);
-
+  // ---- per-lane, frame-invariant offsets (FB_MT m-tiles per warp and phase: m-tile = warp + 8 * i)
   const int mt_in = (npos_in + 15) >> 4, mt_out = (npos_out + 15) >> 4;
-  __half* s_a = reinterpret_cast<__half*>(fb_smem + P.off_a);
-  __half* s_b = reinterpret_cast<__half*>(fb_smem + P.off_b);
-  __half* s_y = reinterpret_cast<__half*>(fb_smem + P.off_y);
-  const unsigned a_base = sbase + P.off_a, b_base = sbase + P.off_b;
-  const unsigned yrow_bytes = (unsigned)P.Cout * 2u;
+  const unsigned a_base = sbase + P.off_a, b_base = sbase + P.off_b, y_base = sbase + P.off_y;
+  unsigned A_ld[FB_MT], A_xor[FB_MT], A_st[FB_MT][2];          // phase A: ldmatrix row offset in a slot, swizzle phase, a-tile store
+  unsigned B_pos[FB_MT], B_st[FB_MT][2];                        // phase B: window corner position in the a tile, b-tile store
+  unsigned C_ld[FB_MT], C_x[FB_MT], C_res[FB_MT][2], C_y[FB_MT][2];   // phase C: b row, x centre row (ldmatrix / residual), y-tile store
+#pragma unroll
+  for (int i = 0; i < FB_MT; ++i) {
+    const int mt = warp + FB_WARPS * i;
+    {
+      const unsigned pos = (unsigned)min(mt * 16 + fb_lane_row(lane), npos_in - 1);
+      A_ld[i] = pos * XROW;
+      A_xor[i] = fb_swz_c<XROW>(pos, 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p2 = mt * 16 + g + 8 * h;
+        A_st[i][h] = FB_SKIP;
+        if (mt < mt_in && p2 < npos_in) {
+          // bit 31 marks a position outside the image: a = 0 there (the zero padding of conv_b), not relu(bn(0))
+          A_st[i][h] = ((unsigned)p2 * AROW + (unsigned)(2 * q) * 2u) | (s_src[p2] < 0 ? 0x80000000u : 0u);
+        }
+      }
+    }
+    {
+      const int opos = min(mt * 16 + fb_lane_row(lane), npos_out - 1);
+      const int qy = opos / P.TW, qx = opos - qy * P.TW;
+      B_pos[i] = (unsigned)(qy * SB * P.RW + qx * SB);
+      C_ld[i] = (unsigned)opos;
+      C_x[i] = (unsigned)((qy * SB + 1) * P.RW + qx * SB + 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o2 = mt * 16 + g + 8 * h;
+        B_st[i][h] = FB_SKIP; C_res[i][h] = 0; C_y[i][h] = FB_SKIP;
+        if (mt < mt_out && o2 < npos_out) {
+          const int q2y = o2 / P.TW, q2x = o2 - q2y * P.TW;
+          B_st[i][h] = (unsigned)o2;
+          C_res[i][h] = (unsigned)((q2y * SB + 1) * P.RW + q2x * SB + 1);
+          C_y[i][h] = (unsigned)o2 * YROW + (unsigned)(2 * q) * 2u;
+        }
+      }
+    }
+  }
+  // lane's weight-fragment bases: row g of each n-tile, k = 2q (+8 for the second register)
+  const unsigned wa_l = fb_smem_u32(s_wa) + (unsigned)(g * LDWA + 2 * q) * 2u;
+  const unsigned wb_l = fb_smem_u32(s_wb) + (unsigned)(g * LDWB + 2 * q) * 2u;
+  const unsigned wc_l = fb_smem_u32(s_wc) + (unsigned)(g * LDWC + 2 * q) * 2u;
+  const unsigned ws_l = fb_smem_u32(s_ws) + (unsigned)(g * LDWS + 2 * q) * 2u;
 
   for (int t = t_begin; t < t_end; ++t) {
-    // frame t + pad_t + 1 goes into the slot that frame t - pad_t - 1 ... no longer needs (4 slots >= kt + 1)
-    load_frame(t + pad_t + 1);
+    load_frame(t + PAD_T + 1);                                 // into the slot frame t - PAD_T - 1 no longer needs
     asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the frame just requested has landed
-    __syncthreads();                                           // (also: weights visible on the first step; s_y drained)
+    __syncthreads();                                           // (also: weights / tables visible on the first step; s_y drained)
+    unsigned slot_base[KT];
+#pragma unroll
+    for (int dt = 0; dt < KT; ++dt)
+      slot_base[dt] = sbase + P.off_x + ((unsigned)(t + dt - PAD_T + 8) & (FB_SLOTS - 1)) * P.x_slot_bytes;
 
     // ================= phase A: a = relu(bn_a(conv_a(x))) on the halo tile, 0 outside the image =================
-    for (int mt = warp; mt < mt_in; mt += FB_WARPS) {
+#pragma unroll
+    for (int i = 0; i < FB_MT; ++i) {
+      if (warp + FB_WARPS * i >= mt_in) break;
       float acc[NTM][4];
 #pragma unroll
-      for (int i = 0; i < NTM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-      const int row0 = mt * 16;
-      {
-        const unsigned pos = (unsigned)min(row0 + fb_lane_row(lane), npos_in - 1);
-        const unsigned rowoff = sbase + P.off_x + pos * xrow_bytes;
-        fb_gemm<NTM>(acc, P.KA, s_wa, P.ldwa, 0, lane, [&](int kk) -> unsigned {
-          int dt = kk >> cin_log2;                                 // k = dt * Cin + ci (Cin is a power of two)
-          const int ci = kk & (P.Cin - 1);
-          dt = min(dt, P.kt - 1);                                  // K padding: zero weights, any finite data
-          const unsigned slot = (unsigned)(t + dt - pad_t + 8) & (FB_SLOTS - 1);
-          return rowoff + slot * P.x_slot_bytes + (fb_swz(pos, (unsigned)(ci >> 3), xrow_bytes) << 4);
-        });
+      for (int j = 0; j < NTM; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KA / 16; ++ks) {
+        // this lane's 8-wide K half: k = 16 ks + 8 hi = dt * CIN + ci  (K padding: zero weights, any finite data)
+        int dt, ci;
+        if (CIN == 8) { dt = min(2 * ks + hi, KT - 1); ci = 0; }
+        else { dt = min((16 * ks) / CIN, KT - 1); ci = (16 * ks) % CIN + 8 * hi; }
+        unsigned sb0 = slot_base[0];
+#pragma unroll
+        for (int d2 = 1; d2 < KT; ++d2) sb0 = dt == d2 ? slot_base[d2] : sb0;
+        unsigned a[4];
+        ldmatrix_x4(sb0 + A_ld[i] + ((((unsigned)ci >> 3) ^ A_xor[i]) << 4), a);
+#pragma unroll
+        for (int nt = 0; nt < NTM; ++nt) {
+          const unsigned wofs = (unsigned)((nt * 8) * LDWA + ks * 16) * 2u;
+          mma_16816(acc[nt], a, fb_lds32(wa_l + wofs), fb_lds32(wa_l + wofs + 16u));
+        }
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int pos = row0 + g + 8 * h;
-        if (pos < npos_in) {
-          const int py = pos / P.RW, px = pos - py * P.RW;
-          const bool inside = (unsigned)(iy0 + py) < (unsigned)P.H && (unsigned)(ix0 + px) < (unsigned)P.W;
+        const unsigned st = A_st[i][h];
+        if (st != FB_SKIP) {
+          const bool inside = (st & 0x80000000u) == 0u;
+          const unsigned off = st & 0x7fffffffu;
+          const unsigned pos = off / AROW;
 #pragma unroll
           for (int nt = 0; nt < NTM; ++nt) {
             const int c = nt * 8 + 2 * q;
-            float v0 = fmaf(acc[nt][2 * h], s_sb[c], s_sb[CMID + c]);
-            float v1 = fmaf(acc[nt][2 * h + 1], s_sb[c + 1], s_sb[CMID + c + 1]);
-            v0 = inside ? fmaxf(v0, 0.f) : 0.f;
-            v1 = inside ? fmaxf(v1, 0.f) : 0.f;
-            const unsigned off = (unsigned)pos * arow_bytes + (fb_swz((unsigned)pos, (unsigned)(c >> 3), arow_bytes) << 4) + (unsigned)(c & 7) * 2u;
-            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(s_a) + off) = __floats2half2_rn(v0, v1);
+            float v0 = fmaxf(fmaf(acc[nt][2 * h], s_sb[c], s_sb[CMID + c]), 0.f);
+            float v1 = fmaxf(fmaf(acc[nt][2 * h + 1], s_sb[c + 1], s_sb[CMID + c + 1]), 0.f);
+            if (!inside) { v0 = 0.f; v1 = 0.f; }
+            fb_sts32(a_base + pos * AROW + (fb_swz_c<AROW>(pos, (unsigned)nt) << 4) + (unsigned)(2 * q) * 2u, fb_pack(v0, v1));
           }
         }
       }
@@ -228,35 +288,38 @@ bottleneck_fused_kernel(const __grid_constant__ FbParams P, const __half* __rest
     __syncthreads();
 
     // ================= phase B: b = relu(bn_b(conv_b(a))), 3x3 window of the a tile ============================
-    for (int mt = warp; mt < mt_out; mt += FB_WARPS) {
+#pragma unroll
+    for (int i = 0; i < FB_MT; ++i) {
+      if (warp + FB_WARPS * i >= mt_out) break;
       float acc[NTM][4];
 #pragma unroll
-      for (int i = 0; i < NTM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-      const int row0 = mt * 16;
-      {
-        const int opos = min(row0 + fb_lane_row(lane), npos_out - 1);
-        const int qy = opos / P.TW, qx = opos - qy * P.TW;
-        const unsigned pos0 = (unsigned)(qy * P.sb * P.RW + qx * P.sb);       // window corner in the a tile
-        fb_gemm<NTM>(acc, P.KB, s_wb, P.ldwb, 0, lane, [&](int kk) -> unsigned {
-          int tap = kk / CMID;                                     // k = (dh * 3 + dw) * CMID + ci, CMID a power of two
-          const int ci = kk & (CMID - 1);
-          tap = min(tap, 8);                                       // K padding: zero weights
-          const int dh = (tap * 11) >> 5, dw = tap - dh * 3;       // tap / 3 for tap in 0..8
-          const unsigned pos = pos0 + (unsigned)(dh * P.RW + dw);
-          return a_base + pos * arow_bytes + (fb_swz(pos, (unsigned)(ci >> 3), arow_bytes) << 4);
-        });
+      for (int j = 0; j < NTM; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KB / 16; ++ks) {
+        // k = 16 ks + 8 hi = (dh * 3 + dw) * CMID + ci
+        int tap, ci;
+        if (CMID == 8) { tap = min(2 * ks + hi, 8); ci = 0; }
+        else { tap = min((16 * ks) / CMID, 8); ci = (16 * ks) % CMID + 8 * hi; }
+        const int dh = (tap * 11) >> 5, dw = tap - dh * 3;
+        const unsigned pos = B_pos[i] + (unsigned)(dh * P.RW + dw);
+        unsigned a[4];
+        ldmatrix_x4(a_base + pos * AROW + (fb_swz_c<AROW>(pos, (unsigned)ci >> 3) << 4), a);
+#pragma unroll
+        for (int nt = 0; nt < NTM; ++nt) {
+          const unsigned wofs = (unsigned)((nt * 8) * LDWB + ks * 16) * 2u;
+          mma_16816(acc[nt], a, fb_lds32(wb_l + wofs), fb_lds32(wb_l + wofs + 16u));
+        }
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int opos = row0 + g + 8 * h;
-        if (opos < npos_out) {
+        const unsigned opos = B_st[i][h];
+        if (opos != FB_SKIP) {
 #pragma unroll
           for (int nt = 0; nt < NTM; ++nt) {
             const int c = nt * 8 + 2 * q;
             const float v0 = fmaxf(fmaf(acc[nt][2 * h], s_sb[2 * CMID + c], s_sb[3 * CMID + c]), 0.f);
             const float v1 = fmaxf(fmaf(acc[nt][2 * h + 1], s_sb[2 * CMID + c + 1], s_sb[3 * CMID + c + 1]), 0.f);
-            const unsigned off = (unsigned)opos * arow_bytes + (fb_swz((unsigned)opos, (unsigned)(c >> 3), arow_bytes) << 4) + (unsigned)(c & 7) * 2u;
-            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(s_b) + off) = __floats2half2_rn(v0, v1);
+            fb_sts32(b_base + opos * AROW + (fb_swz_c<AROW>(opos, (unsigned)nt) << 4) + (unsigned)(2 * q) * 2u, fb_pack(v0, v1));
           }
         }
       }
@@ -264,51 +327,62 @@ bottleneck_fused_kernel(const __grid_constant__ FbParams P, const __half* __rest
     __syncthreads();
 
     // ================= phase C: y = act(bn_c(conv_c(b)) + shortcut), 32 output channels per pass ================
-    const unsigned xslot_t = sbase + P.off_x + ((unsigned)(t + 8) & (FB_SLOTS - 1)) * P.x_slot_bytes;
-    const float* s_c = s_sb + 4 * CMID;
-    const int ngroups = P.Cout >> 5;
-    for (int item = warp; item < mt_out * ngroups; item += FB_WARPS) {
-      const int mt = item / ngroups, ng = item - mt * ngroups;
-      const int row0 = mt * 16, n0 = ng * 32;
-      float acc[4][4], acs[4][4];
+    const unsigned xslot_t = slot_base[PAD_T];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; acs[i][0] = acs[i][1] = acs[i][2] = acs[i][3] = 0.f; }
-      const unsigned lpos = (unsigned)min(row0 + fb_lane_row(lane), npos_out - 1);     // this lane's A row
-      fb_gemm<4>(acc, P.KC, s_wc, P.ldwc, n0, lane, [&](int kk) -> unsigned {
-        const int ci = min(kk, CMID - 8);                        // K padding (CMID = 8): zero weights
-        return b_base + lpos * arow_bytes + (fb_swz(lpos, (unsigned)(ci >> 3), arow_bytes) << 4);
-      });
-      if (P.has_sc) {
-        const int lqy = (int)lpos / P.TW, lqx = (int)lpos - lqy * P.TW;
-        const unsigned xpos = (unsigned)((lqy * P.sb + 1) * P.RW + lqx * P.sb + 1);     // centre of the window in the x tile
-        fb_gemm<4>(acs, P.KS, s_ws, P.ldws, n0, lane, [&](int kk) -> unsigned {
-          const int ci = min(kk, P.Cin - 8);
-          return xslot_t + xpos * xrow_bytes + (fb_swz(xpos, (unsigned)(ci >> 3), xrow_bytes) << 4);
-        });
+    for (int i = 0; i < FB_MT; ++i) {
+      if (warp + FB_WARPS * i >= mt_out) break;
+      // A fragments of this m-tile: b rows (conv_c) and x centre rows (projection shortcut), loaded once for all groups
+      unsigned fa[KC / 16][4];
+#pragma unroll
+      for (int ks = 0; ks < KC / 16; ++ks) {
+        const int ci = min(16 * ks + 8 * hi, CMID - 8);          // K padding (CMID = 8): zero weights
+        ldmatrix_x4(b_base + C_ld[i] * AROW + (fb_swz_c<AROW>(C_ld[i], (unsigned)ci >> 3) << 4), fa[ks]);
       }
+#pragma unroll 1
+      for (int ng = 0; ng < NG; ++ng) {
+        float acc[4][4], acs[4][4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int opos = row0 + g + 8 * h;
-        if (opos < npos_out) {
-          const int qy = opos / P.TW, qx = opos - qy * P.TW;
-          const unsigned pos = (unsigned)((qy * P.sb + 1) * P.RW + qx * P.sb + 1);     // centre position in the x tile
+        for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; acs[j][0] = acs[j][1] = acs[j][2] = acs[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < KC / 16; ++ks)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
-            const int c = n0 + nt * 8 + 2 * q;
-            float v0 = fmaf(acc[nt][2 * h], s_c[c], s_c[P.Cout + c]);
-            float v1 = fmaf(acc[nt][2 * h + 1], s_c[c + 1], s_c[P.Cout + c + 1]);
-            if (P.has_sc) {
-              v0 += fmaf(acs[nt][2 * h], s_c[2 * P.Cout + c], s_c[3 * P.Cout + c]);
-              v1 += fmaf(acs[nt][2 * h + 1], s_c[2 * P.Cout + c + 1], s_c[3 * P.Cout + c + 1]);
-            } else {
-              const unsigned xo = pos * xrow_bytes + (fb_swz(pos, (unsigned)(c >> 3), xrow_bytes) << 4) + (unsigned)(c & 7) * 2u;
-              __half2 rv;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(*reinterpret_cast<unsigned*>(&rv)) : "r"(xslot_t + xo));
-              const float2 rf = __half22float2(rv);
-              v0 += rf.x; v1 += rf.y;
+            const unsigned wofs = (unsigned)((ng * 32 + nt * 8) * LDWC + ks * 16) * 2u;
+            mma_16816(acc[nt], fa[ks], fb_lds32(wc_l + wofs), fb_lds32(wc_l + wofs + 16u));
+          }
+        if (HAS_SC) {
+#pragma unroll
+          for (int ks = 0; ks < KS / 16; ++ks) {
+            const int ci = min(16 * ks + 8 * hi, CIN - 8);
+            unsigned a[4];
+            ldmatrix_x4(xslot_t + C_x[i] * XROW + (fb_swz_c<XROW>(C_x[i], (unsigned)ci >> 3) << 4), a);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const unsigned wofs = (unsigned)((ng * 32 + nt * 8) * LDWS + ks * 16) * 2u;
+              mma_16816(acs[nt], a, fb_lds32(ws_l + wofs), fb_lds32(ws_l + wofs + 16u));
             }
-            if (P.act == PV_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(s_y) + (unsigned)opos * yrow_bytes + (unsigned)c * 2u) = __floats2half2_rn(v0, v1);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (C_y[i][h] != FB_SKIP) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const int c = ng * 32 + nt * 8 + 2 * q;
+              float v0 = fmaf(acc[nt][2 * h], s_c[c], s_c[COUT + c]);
+              float v1 = fmaf(acc[nt][2 * h + 1], s_c[c + 1], s_c[COUT + c + 1]);
+              if (HAS_SC) {
+                v0 += fmaf(acs[nt][2 * h], s_c[2 * COUT + c], s_c[3 * COUT + c]);
+                v1 += fmaf(acs[nt][2 * h + 1], s_c[2 * COUT + c + 1], s_c[3 * COUT + c + 1]);
+              } else {                                           // identity shortcut: CIN == COUT, same channel
+                const unsigned rp = C_res[i][h];
+                const unsigned rv = fb_lds32(xslot_t + rp * XROW + (fb_swz_c<XROW>(rp, (unsigned)(c >> 3)) << 4) + (unsigned)(2 * q) * 2u);
+                const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rv));
+                v0 += rf.x; v1 += rf.y;
+              }
+              if (P.act == PV_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              fb_sts32(y_base + C_y[i][h] + (unsigned)(ng * 32 + nt * 8) * 2u, fb_pack(v0, v1));
+            }
           }
         }
       }
@@ -317,15 +391,17 @@ bottleneck_fused_kernel(const __grid_constant__ FbParams P, const __half* __rest
 
     // ================= store the y tile: 16-byte coalesced rows ================================================
     {
-      const int ychunks = (int)(yrow_bytes >> 4);
+      constexpr int YCH = YROW / 16;
       __half* yt = y + ((size_t)n * P.T + t) * P.Ho * P.Wo * P.yrs;
-      for (int i = tid; i < npos_out * ychunks; i += FB_THREADS) {
-        const int opos = i / ychunks, ch = i - opos * ychunks;
-        const int qy = opos / P.TW, qx = opos - qy * P.TW;
-        const int oy = oy0 + qy, ox = ox0 + qx;
-        if (oy < P.Ho && ox < P.Wo)
-          *reinterpret_cast<uint4*>(yt + ((size_t)oy * P.Wo + ox) * P.yrs + ch * 8) =
-              *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(s_y) + (unsigned)opos * yrow_bytes + (unsigned)ch * 16u);
+      const int* s_dst = s_src + 256;
+      for (int i = tid; i < npos_out * YCH; i += FB_THREADS) {
+        const unsigned opos = (unsigned)i / YCH, ch = (unsigned)i % YCH;
+        const int dofs = s_dst[opos];
+        if (dofs >= 0) {
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(y_base + opos * YROW + ch * 16u));
+          *reinterpret_cast<uint4*>(yt + dofs + ch * 8) = v;
+        }
       }
     }
     // (the next iteration's first __syncthreads orders these shared-memory reads before s_y / s_a are rewritten)
@@ -339,16 +415,30 @@ static int fb_pad16(int k) { return (k + 15) / 16 * 16; }
 
 using namespace pv;
 
+namespace {
+struct FbCombo { int cin, cmid, kt, sb, sc; };
+// the instantiated shapes: SlowFast Fast pathway res2 / res3 / res4 (first block with its projection shortcut, the
+// following blocks with the identity), plus a pointwise-conv_a variant
+const FbCombo kCombos[] = {
+    {8, 8, 3, 1, 1},   {32, 8, 3, 1, 0},   {32, 8, 1, 1, 0},
+    {32, 16, 3, 2, 1}, {32, 16, 3, 1, 1},  {64, 16, 3, 1, 0},
+    {64, 32, 3, 2, 1}, {64, 32, 3, 1, 1},  {128, 32, 3, 1, 0},
+};
+bool fb_has_combo(int cin, int cmid, int kt, int sb, int sc) {
+  for (const FbCombo& c : kCombos)
+    if (c.cin == cin && c.cmid == cmid && c.kt == kt && c.sb == sb && c.sc == sc) return true;
+  return false;
+}
+}  // namespace
+
 extern "C" int pv_bottleneck_fused_supported(const pv_bottleneck_desc* d) {
   if (!d) return 0;
-  if (!(d->Cmid == 8 || d->Cmid == 16 || d->Cmid == 32)) return 0;
-  if (d->Cin % 8 || d->Cin < 8 || d->Cin > 256 || (d->Cin & (d->Cin - 1))) return 0;   // power-of-two row bytes (swizzle)
-  if (d->Cout % 32 || d->Cout > 256) return 0;
-  if (!(d->kt == 1 || d->kt == 3)) return 0;
-  if (!(d->sb == 1 || d->sb == 2)) return 0;
+  if (d->Cout != 4 * d->Cmid) return 0;
+  if (!fb_has_combo(d->Cin, d->Cmid, d->kt, d->sb, d->has_shortcut ? 1 : 0)) return 0;
   if (!d->has_shortcut && (d->Cin != d->Cout || d->sb != 1)) return 0;
   if (!(d->act == PV_ACT_RELU || d->act == PV_ACT_NONE)) return 0;
   if (d->x_row_stride % 8 || d->y_row_stride % 8 || d->x_row_stride < d->Cin || d->y_row_stride < d->Cout) return 0;
+  if ((long long)d->H * d->W * d->x_row_stride >= (1ll << 31)) return 0;       // 32-bit in-frame offsets
   return 1;
 }
 
@@ -369,40 +459,43 @@ extern "C" int pv_bottleneck_fused_fwd(const pv_bottleneck_desc* d, const void* 
   P.ldwa = P.KA + 8; P.ldwb = P.KB + 8; P.ldwc = P.KC + 8; P.ldws = P.KS + 8;
   const int sm_count = current_sm_count();
   if (sm_count <= 0) { set_error("cannot query the SM count"); return PV_ERR_CUDA; }
-  // ---- tile search: the largest output tile whose shared memory fits, then enough T chunks to fill the GPU
+  // ---- tile search: efficient tiles (little halo / m-tile padding) that still give every SM a few CTAs
   const size_t w_bytes = ((size_t)d->Cmid * P.ldwa + (size_t)d->Cmid * P.ldwb + (size_t)d->Cout * P.ldwc +
                           (d->has_shortcut ? (size_t)d->Cout * P.ldws : 0)) * 2;
   const size_t sb_bytes = (size_t)(4 * d->Cmid + 4 * d->Cout) * 4;
   const size_t budget = 200 * 1024;
-  int best_th = 0, best_tw = 0;
+  int best_th = 0, best_tw = 0, best_tc = 0;
   double best_score = -1;
-  size_t best_smem = 0;
   for (int th = 2; th <= 16; ++th)
     for (int tw = 2; tw <= 16; ++tw) {
       if (th > P.Ho + 1 || tw > P.Wo + 1) continue;
       const int rh = (th - 1) * d->sb + 3, rw = (tw - 1) * d->sb + 3;
+      if (rh * rw > 16 * FB_MT * FB_WARPS || th * tw > 16 * FB_MT * FB_WARPS) continue;       // FB_MT m-tiles per warp
       const size_t xs = (size_t)rh * rw * d->Cin * 2;
       const size_t need = FB_SLOTS * ((xs + 127) & ~(size_t)127) + (((size_t)rh * rw * d->Cmid * 2 + 127) & ~(size_t)127) +
                           (((size_t)th * tw * d->Cmid * 2 + 127) & ~(size_t)127) + (((size_t)th * tw * d->Cout * 2 + 127) & ~(size_t)127) +
-                          ((w_bytes + 127) & ~(size_t)127) + sb_bytes + 256;
+                          ((w_bytes + 127) & ~(size_t)127) + sb_bytes + 2048 + 512;
       if (need > budget) continue;
+      const long long spatial = (long long)d->N * cdiv(P.Ho, th) * cdiv(P.Wo, tw);
+      const int per_sm = (int)(budget / need) > 4 ? 4 : (int)(budget / need);                  // resident CTAs per SM
+      int tchunks = 1;
+      while (spatial * tchunks < (long long)2 * per_sm * sm_count && d->T / (tchunks + 1) >= 4) ++tchunks;
+      const int tc = (int)cdiv(d->T, tchunks);
+      const double ctas = (double)spatial * (double)cdiv(d->T, tc);
       const double cover = (double)P.Ho * P.Wo / ((double)cdiv(P.Ho, th) * th * cdiv(P.Wo, tw) * tw);   // edge waste
-      const double reuse = (double)(th * tw) * d->sb * d->sb / (double)(rh * rw);                        // halo overhead
+      const double reuse = (double)(th * tw) * d->sb * d->sb / (double)(rh * rw);                        // spatial halo
       const double mtile = (double)(th * tw) / (double)(cdiv(th * tw, 16) * 16) * (double)(rh * rw) / (double)(cdiv(rh * rw, 16) * 16);
-      const double score = cover * reuse * mtile;
-      if (score > best_score) { best_score = score; best_th = th; best_tw = tw; best_smem = need; }
+      const double thalo = (double)tc / (double)(tc + 2 * (d->kt / 2));                                  // temporal halo frames
+      const double fill = ctas >= (double)per_sm * sm_count ? 1.0 : ctas / ((double)per_sm * sm_count);  // machine filled?
+      const double score = cover * reuse * mtile * thalo * fill;
+      if (score > best_score) { best_score = score; best_th = th; best_tw = tw; best_tc = tc; }
     }
   if (best_score < 0) { set_error("fused bottleneck: no tile fits in shared memory"); return PV_ERR_UNSUPPORTED; }
-  P.TH = best_th; P.TW = best_tw;
+  P.TH = best_th; P.TW = best_tw; P.TC = best_tc;
   P.RH = (P.TH - 1) * d->sb + 3; P.RW = (P.TW - 1) * d->sb + 3;
   P.tiles_h = (int)cdiv(P.Ho, P.TH); P.tiles_w = (int)cdiv(P.Wo, P.TW);
-  {
-    const long long spatial = (long long)d->N * P.tiles_h * P.tiles_w;
-    int tchunks = 1;
-    while (spatial * tchunks < 2 * sm_count && d->T / (tchunks + 1) >= 4) ++tchunks;      // >= 4 frames per CTA: halo frames stay cheap
-    P.TC = (int)cdiv(d->T, tchunks);
-    P.tchunks = (int)cdiv(d->T, P.TC);
-  }
+  P.tchunks = (int)cdiv(d->T, P.TC);
+  size_t smem_bytes = 0;
   {
     unsigned off = 0;
     auto take = [&](size_t bytes) { const unsigned o = off; off += (unsigned)((bytes + 127) & ~(size_t)127); return o; };
@@ -416,23 +509,26 @@ extern "C" int pv_bottleneck_fused_fwd(const pv_bottleneck_desc* d, const void* 
     P.off_wc = take((size_t)d->Cout * P.ldwc * 2);
     P.off_ws = take(d->has_shortcut ? (size_t)d->Cout * P.ldws * 2 : 16);
     P.off_sb = take(sb_bytes);
-    best_smem = off;
+    P.off_tab = take(512 * sizeof(int));
+    smem_bytes = off;
   }
   const long long grid = (long long)d->N * P.tchunks * P.tiles_h * P.tiles_w;
   if (grid <= 0) return PV_OK;
   PV_CHECK_ARG(grid < (1ll << 31), "grid too large");
   cudaStream_t s = (cudaStream_t)stream;
-#define PV_FB(CM)                                                                                                   \
-  do {                                                                                                              \
-    PV_OPT_IN_SMEM(bottleneck_fused_kernel<CM>, 208 * 1024);                                                        \
-    bottleneck_fused_kernel<CM><<<(unsigned)grid, FB_THREADS, best_smem, s>>>(                                      \
+#define PV_FB(CI, CM, KT_, SB_, SC_)                                                                                \
+  if (d->Cin == CI && d->Cmid == CM && d->kt == KT_ && d->sb == SB_ && (d->has_shortcut ? 1 : 0) == SC_) {          \
+    PV_OPT_IN_SMEM((bottleneck_fused_kernel<CI, CM, KT_, SB_, (SC_ != 0)>), 208 * 1024);                            \
+    bottleneck_fused_kernel<CI, CM, KT_, SB_, (SC_ != 0)><<<(unsigned)grid, FB_THREADS, smem_bytes, s>>>(           \
         P, (const __half*)x, (const __half*)wa, (const __half*)wb, (const __half*)wc, (const __half*)wsc, sa, ba,   \
         sb_, bb, sc, bc, ssc, bsc, (__half*)y);                                                                     \
-  } while (0)
-  if (d->Cmid == 8) PV_FB(8);
-  else if (d->Cmid == 16) PV_FB(16);
-  else PV_FB(32);
+    PV_LAUNCH_OK("bottleneck_fused_kernel");                                                                        \
+    return PV_OK;                                                                                                   \
+  }
+  PV_FB(8, 8, 3, 1, 1) PV_FB(32, 8, 3, 1, 0) PV_FB(32, 8, 1, 1, 0)
+  PV_FB(32, 16, 3, 2, 1) PV_FB(32, 16, 3, 1, 1) PV_FB(64, 16, 3, 1, 0)
+  PV_FB(64, 32, 3, 2, 1) PV_FB(64, 32, 3, 1, 1) PV_FB(128, 32, 3, 1, 0)
 #undef PV_FB
-  PV_LAUNCH_OK("bottleneck_fused_kernel");
-  return PV_OK;
+  set_error("fused bottleneck: shape not instantiated");
+  return PV_ERR_UNSUPPORTED;
 }
