@@ -352,47 +352,56 @@ __host__ __device__ inline bool epi_direct(const EpiParams& E) {
 // The caller issues the very first residual load (group 0 of its first tile) before the tile loop with
 // epi_prefetch_residual(...).
 // ---------------------------------------------------------------------------------------------
-struct EpiNext { int valid, n0, c1, c2, c3, c4; };
+// One 128-column group of this CTA's epilogue sequence: q-th group = group (q % groups_per_tile) of its (q / gpt)-th tile.
+struct EpiGroup { int valid, n0, ncols, c1, c2, c3, c4; };
+constexpr int EPI_RING = 3;          // staging buffers of the residual ring; residual loads run 2 groups ahead
 
 __device__ __forceinline__ void epi_prefetch_residual(const EpiParams& E, uint32_t epi_smem, uint32_t res_bar, int buf,
-                                                      int ncols, int n0, int c1, int c2, int c3, int c4) {
-  const int nsub = (ncols + 63) >> 6;
+                                                      const EpiGroup& G) {
+  const int nsub = (G.ncols + 63) >> 6;
   const uint32_t bar = res_bar + 8u * (uint32_t)buf;
   mbar_arrive_expect_tx(bar, (uint32_t)(nsub * E.rows * 128));
   for (int s = 0; s < nsub; ++s)
-    tma_load_5d(epi_smem + (uint32_t)buf * EPI_STAGING_BYTES + (uint32_t)s * 16384u, &E.r_map, bar, n0 + s * 64, c1, c2, c3, c4);
+    tma_load_5d(epi_smem + (uint32_t)buf * EPI_STAGING_BYTES + (uint32_t)s * 16384u, &E.r_map, bar, G.n0 + s * 64, G.c1, G.c2, G.c3, G.c4);
 }
 
-__device__ __forceinline__ void epilogue_tile_wide_prefetch(const EpiParams& E, const float* __restrict__ scale,
-                                                            const float* __restrict__ bias, uint32_t t_acc,
-                                                            uint32_t epi_smem, uint8_t* epi_gen, uint32_t res_bar,
-                                                            uint32_t (&res_phase)[2], int& q, int ewarp, int quarter,
-                                                            int lane, int n0, int c1, int c2, int c3, int c4,
-                                                            uint32_t tempty_bar, const EpiNext& nxt) {
+// Wide residual tiles (conv_c + shortcut add + ReLU of every bottleneck): these layers have a short K loop and are
+// bound by their epilogue - residual tile in, output tile out.  profiles/r01_source_counters.md: the MMA warp waits
+// for a free accumulator 68x per tile.  The staging area is a ring of EPI_RING buffers of one 128-column group each:
+//   residual(q + 2) is requested right after store(q) is issued, into the buffer group q - 1 used (free once the
+//   store of q - 1 has been READ, i.e. all bulk groups but the newest: cp.async.bulk.wait_group.read 1),
+// so a residual load has a whole group period (accumulator wait + tcgen05.ld + math of group q + 1) to land and a
+// store drains while the next group is computed.  group_at(q) maps the running group counter to its coordinates.
+template <typename GroupAt>
+__device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const float* __restrict__ scale,
+                                                   const float* __restrict__ bias, uint32_t t_acc, uint32_t epi_smem,
+                                                   uint8_t* epi_gen, uint32_t res_bar, uint32_t (&res_phase)[EPI_RING],
+                                                   int& q, int ewarp, int quarter, int lane, int n_tile0,
+                                                   uint32_t tempty_bar, GroupAt group_at) {
   const int row = quarter * 32 + lane;
   const int chalf = ewarp >> 2;
   const int etid = ewarp * 32 + lane;
   const bool leader = (etid == 0);
   const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
   const uint32_t rsw = (uint32_t)(row & 7);
-  float* sb = reinterpret_cast<float*>(epi_gen + 2 * EPI_STAGING_BYTES);     // scale/bias live after BOTH staging buffers
+  float* sb = reinterpret_cast<float*>(epi_gen + EPI_RING * EPI_STAGING_BYTES);     // scale/bias live after the ring
   for (int i = etid; i < E.block_n; i += EPI_THREADS) {
-    const int c = n0 + i;
+    const int c = n_tile0 + i;
     const bool ok = c < E.Co;
     sb[i] = ok ? __ldg(scale + c) : 0.f;
     sb[256 + i] = ok ? __ldg(bias + c) : 0.f;
   }
   for (int g0 = 0; g0 < E.block_n; g0 += EPI_GROUP_COLS, ++q) {
-    const int buf = q & 1;
-    const int gcols = min(EPI_GROUP_COLS, E.block_n - g0);
-    const int nsub = (gcols + 63) >> 6;
+    const int buf = q % EPI_RING;
+    const EpiGroup G = group_at(q);
+    const int nsub = (G.ncols + 63) >> 6;
     const uint32_t slot = (uint32_t)buf * EPI_STAGING_BYTES;
-    epi_bar_sync(1, EPI_THREADS);                       // scale/bias visible; previous group fully staged + stored
-    mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested one group ago)
+    epi_bar_sync(1, EPI_THREADS);                       // scale/bias visible; previous group fully staged
+    mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested two groups ago)
     res_phase[buf] ^= 1u;
     if (chalf < nsub) {
       const int cbase = g0 + chalf * 64;
-      const int ncols = min(64, gcols - chalf * 64);
+      const int ncols = min(64, G.ncols - chalf * 64);
       uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
       const float* sc = sb + cbase;
       const float* bi = sb + 256 + cbase;
@@ -404,8 +413,7 @@ __device__ __forceinline__ void epilogue_tile_wide_prefetch(const EpiParams& E, 
         default: epi_subtile<PV_ACT_SIGMOID, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
       }
     }
-    const bool last_group = g0 + EPI_GROUP_COLS >= E.block_n;
-    if (last_group) {                                   // accumulator fully read: hand TMEM back to the MMA warp
+    if (g0 + EPI_GROUP_COLS >= E.block_n) {             // accumulator fully read: hand TMEM back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar);   // shared::cluster address: own CTA, or the pair's leader
@@ -414,23 +422,19 @@ __device__ __forceinline__ void epilogue_tile_wide_prefetch(const EpiParams& E, 
     epi_bar_sync(1, EPI_THREADS);
     if (leader) {
       for (int s = 0; s < nsub; ++s)
-        tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, n0 + g0 + s * 64, c1, c2, c3, c4);
+        tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, G.n0 + s * 64, G.c1, G.c2, G.c3, G.c4);
       tma_store_commit();
-      // residual of the next group into the other buffer (free once the store of group q-1 has been read)
-      if (!last_group) {
-        tma_store_wait_read1();
-        epi_prefetch_residual(E, epi_smem, res_bar, buf ^ 1, min(EPI_GROUP_COLS, E.block_n - g0 - EPI_GROUP_COLS),
-                              n0 + g0 + EPI_GROUP_COLS, c1, c2, c3, c4);
-      } else if (nxt.valid) {
-        tma_store_wait_read1();
-        epi_prefetch_residual(E, epi_smem, res_bar, buf ^ 1, min(EPI_GROUP_COLS, E.block_n), nxt.n0, nxt.c1, nxt.c2, nxt.c3, nxt.c4);
+      const EpiGroup N2 = group_at(q + 2);              // its buffer was last used by group q - 1
+      if (N2.valid) {
+        tma_store_wait_read1();                         // every store but the one just issued has read its buffer
+        epi_prefetch_residual(E, epi_smem, res_bar, (q + 2) % EPI_RING, N2);
       }
     }
   }
 }
 
 __host__ __device__ inline bool epi_wide_prefetch(const EpiParams& E) {
-  return !epi_narrow(E.block_n) && E.has_residual && (E.dbg & 256);      // opt-in: PVB200_DEBUG=256
+  return !epi_narrow(E.block_n) && E.has_residual && !(E.dbg & 512);     // PVB200_DEBUG=512: fall back to the single-buffer epilogue
 }
 
 }  // namespace sm100

@@ -1,4 +1,4 @@
-// Fused bottleneck block for NARROW pathways (SlowFast Fast pathway: C_inner = 8 / 16 / 32):
+// Fused bottleneck block for NARROW pathways (SlowFast Fast pathway res2 / res3: C_inner = 8 / 16):
 //
 //   a = relu(bn_a(conv_a(x)))      conv_a: (kt,1,1) temporal, C_in -> C_mid            (resnet.py:1345-1365)
 //   b = relu(bn_b(conv_b(a)))      conv_b: (1,3,3) spatial stride (1,s,s), C_mid -> C_mid
@@ -422,7 +422,8 @@ struct FbCombo { int cin, cmid, kt, sb, sc; };
 const FbCombo kCombos[] = {
     {8, 8, 3, 1, 1},   {32, 8, 3, 1, 0},   {32, 8, 1, 1, 0},
     {32, 16, 3, 2, 1}, {32, 16, 3, 1, 1},  {64, 16, 3, 1, 0},
-    {64, 32, 3, 2, 1}, {64, 32, 3, 1, 1},  {128, 32, 3, 1, 0},
+    // C_mid = 32 (res4: 14 x 14 planes, 170 registers -> one CTA per SM) measured SLOWER than the three tcgen05 launches
+    // (66 vs 50 us per block): not instantiated
 };
 bool fb_has_combo(int cin, int cmid, int kt, int sb, int sc) {
   for (const FbCombo& c : kCombos)
@@ -527,7 +528,6 @@ extern "C" int pv_bottleneck_fused_fwd(const pv_bottleneck_desc* d, const void* 
   }
   PV_FB(8, 8, 3, 1, 1) PV_FB(32, 8, 3, 1, 0) PV_FB(32, 8, 1, 1, 0)
   PV_FB(32, 16, 3, 2, 1) PV_FB(32, 16, 3, 1, 1) PV_FB(64, 16, 3, 1, 0)
-  PV_FB(64, 32, 3, 2, 1) PV_FB(64, 32, 3, 1, 1) PV_FB(128, 32, 3, 1, 0)
 #undef PV_FB
   set_error("fused bottleneck: shape not instantiated");
   return PV_ERR_UNSUPPORTED;

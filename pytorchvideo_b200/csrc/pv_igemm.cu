@@ -95,7 +95,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   const int nacc = P.nacc;                   // accumulator stages in TMEM (2..8)
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + nacc + s); };
   const uint32_t res_bar = bar_base + 8u * (2 * stages + 2 * nacc);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 2 * nacc + 2);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 2 * nacc + EPI_RING);     // res_bar: one barrier per ring buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,8 +114,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       // one arrive per epilogue warp of the tile's group (pair mode: from both CTAs, on the leader's barrier)
       mbar_init(tempty_bar(s), (epi_narrow(P.block_n) ? 4 : EPI_WARPS) * (pair ? 2 : 1));
     }
-    mbar_init(res_bar, 1);
-    mbar_init(res_bar + 8u, 1);
+    for (int s = 0; s < EPI_RING; ++s) mbar_init(res_bar + 8u * s, 1);
     prefetch_tmap(&P.epi.y_map);
     fence_mbar_init();
   }
@@ -282,14 +281,30 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     const bool narrow = epi_narrow(P.block_n);
     // the accumulator is handed back on the MMA issuer's barrier: the leader CTA's (a shared::cluster address)
     auto tempty_addr = [&](int a) { return pair ? mapa_shared(tempty_bar(a), 0) : tempty_bar(a); };
-    // wide residual tiles: double-buffered staging with the residual of the next group prefetched
+    // wide residual tiles: ring of staging buffers, residual loads two groups ahead (epilogue_tile_ring)
     const bool wide_prefetch = epi_wide_prefetch(P.epi);
-    uint32_t res_phase2[2] = {0u, 0u};
+    uint32_t res_phase3[EPI_RING];
+#pragma unroll
+    for (int s = 0; s < EPI_RING; ++s) res_phase3[s] = 0u;
     int q = 0;
-    if (wide_prefetch && ewarp == 0 && lane == 0 && unit0 < total_tiles) {
-      int ntf, of[4];
-      tile_coords(unit0, ntf, of);
-      epi_prefetch_residual(P.epi, staging, res_bar, 0, min(EPI_GROUP_COLS, P.block_n), ntf * P.block_n, of[0], of[1], of[2], of[3]);
+    const int gpt = (P.block_n + EPI_GROUP_COLS - 1) / EPI_GROUP_COLS;      // groups per tile
+    auto group_at = [&](int qq) {
+      EpiGroup G;
+      const int ts = qq / gpt, gi = qq - ts * gpt;
+      const int unit = unit0 + ts * unit_step;
+      G.valid = unit < total_tiles ? 1 : 0;
+      int nt = 0, oc[4] = {0, 0, 0, 0};
+      if (G.valid) tile_coords(unit, nt, oc);
+      G.n0 = nt * P.block_n + gi * EPI_GROUP_COLS;
+      G.ncols = min(EPI_GROUP_COLS, P.block_n - gi * EPI_GROUP_COLS);
+      G.c1 = oc[0]; G.c2 = oc[1]; G.c3 = oc[2]; G.c4 = oc[3];
+      return G;
+    };
+    if (wide_prefetch && ewarp == 0 && lane == 0) {
+      for (int qq = 0; qq < 2; ++qq) {
+        const EpiGroup G0 = group_at(qq);
+        if (G0.valid) epi_prefetch_residual(P.epi, staging, res_bar, qq % EPI_RING, G0);
+      }
     }
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tile_seq) {
       if (narrow && (tile_seq & 1) != (ewarp >> 2)) continue;     // the other group's tile
@@ -305,16 +320,8 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (wide_prefetch) {
-        EpiNext nxt = {0, 0, 0, 0, 0, 0};
-        const int tn = tile + unit_step;
-        if (tn < total_tiles) {
-          int on[4], nn;
-          tile_coords(tn, nn, on);
-          nxt.valid = 1; nxt.n0 = nn * P.block_n; nxt.c1 = on[0]; nxt.c2 = on[1]; nxt.c3 = on[2]; nxt.c4 = on[3];
-        }
-        epilogue_tile_wide_prefetch(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging,
-                                    smem_gen + staging_off, res_bar, res_phase2, q, ewarp, quarter, lane,
-                                    n_tile * P.block_n, o[0], o[1], o[2], o[3], tempty_addr(acc), nxt);
+        epilogue_tile_ring(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
+                           res_bar, res_phase3, q, ewarp, quarter, lane, n_tile * P.block_n, tempty_addr(acc), group_at);
         continue;
       }
       epilogue_tile(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
@@ -583,7 +590,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (G > 4) G = 4;
     if (G > num_kb) G = num_kb;
     { const char* e = getenv("PVB200_G"); if (e && atoi(e) >= 1 && atoi(e) <= 8) G = atoi(e) < num_kb ? atoi(e) : num_kb; }
-    P.epi_bytes = EPI_SMEM_BYTES + (epi_wide_prefetch(P.epi) ? EPI_STAGING_BYTES : 0);
+    P.epi_bytes = EPI_SMEM_BYTES + (epi_wide_prefetch(P.epi) ? (EPI_RING - 1) * EPI_STAGING_BYTES : 0);
     {
       static const bool no_alias = getenv("PVB200_NO_ALIAS") != nullptr;
       const long long units = P.pair ? 2ll * P.pair_tiles : (long long)P.m_tiles * P.n_tiles;

@@ -51,6 +51,8 @@ CONV_CASES = [
     (2, 32, 6, 10, 10, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), 1, "relu", False),       # Fast-pathway conv_a: narrow TMA mode (64 B rows)
     (1, 16, 4, 9, 9, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, "relu", True),         # Fast-pathway conv_b + residual: narrow TMA (32 B rows)
     (2, 32, 2, 9, 9, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, None, False),         # strided shortcut from a 32-wide tensor
+    (2, 64, 8, 56, 56, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "relu", True),      # conv_c + residual, 784 wide tiles: residual ring over several tiles per CTA
+    (1, 256, 4, 14, 14, 1024, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "relu", True),    # res4 conv_c + residual: one tile per CTA, 4 N tiles
     (1, 216, 3, 39, 39, 216, (3, 3, 3), (1, 2, 2), (1, 1, 1), 216, None, False),    # X3D-L res4 depthwise: odd 39 -> 20, stride 2
     (1, 96, 2, 39, 39, 192, (1, 1, 1), (1, 2, 2), (0, 0, 0), 1, None, False),       # X3D-L strided shortcut on an odd extent
     (1, 24, 2, 78, 156, 54, (1, 1, 1), (1, 1, 1), (0, 0, 0), 1, "relu", False),     # X3D-L wide rows (W = 156)
@@ -231,8 +233,7 @@ FUSED_BLOCK_CASES = [
     (2, 6, 17, 15, 32, 8, 32, 3, 1),       # res2 blocks 1-2: identity shortcut, edge tiles in both directions
     (1, 4, 18, 14, 32, 16, 64, 3, 2),      # res3 block 0: stride 2, projection shortcut
     (1, 7, 9, 20, 64, 16, 64, 3, 1),       # res3 blocks 1-3
-    (1, 3, 14, 14, 64, 32, 128, 3, 2),     # res4 block 0
-    (2, 9, 14, 14, 128, 32, 128, 3, 1),    # res4 blocks 1-5: several T chunks
+    (2, 9, 14, 14, 64, 16, 64, 3, 1),      # small planes: several T chunks per clip
     (1, 4, 12, 12, 32, 8, 32, 1, 1),       # pointwise conv_a (kt = 1)
     (1, 33, 7, 7, 32, 8, 32, 3, 1),        # long clip: ring wrap-around over many frames
 ]

@@ -90,10 +90,10 @@ def test_lowering_slowfast_dry_run():
     assert out_shape == (2, 400)
     names = [n for n, _ in plan.ops]
     # 2 stems (conv+pool each), 4 fusion convs, (3+4+6+3)*2 blocks * 3 convs + 8 shortcuts, head; the 13 blocks of the
-    # Fast pathway's res2-res4 (3 convs each + their 3 projection shortcuts) are ONE fused launch each
+    # Fast pathway's res2-res3 (3 convs each + their 2 projection shortcuts) are ONE fused launch each
     n_conv = plan.stats["tcgen05"] + plan.stats["direct"]
-    assert plan.stats["fused_block"] == 13
-    assert n_conv == 2 + 4 + 2 * (16 * 3 + 4) + 1 - (13 * 3 + 3)
+    assert plan.stats["fused_block"] == 7
+    assert n_conv == 2 + 4 + 2 * (16 * 3 + 4) + 1 - (7 * 3 + 2)
     assert plan.stats["tcgen05"] == n_conv        # every C_in%8==0 dense conv goes to the tensor cores
     assert any(n.endswith("multipathway_fusion.conv_fast_to_slow") for n in names)
     assert "blocks.6.output_pool" in names
@@ -191,7 +191,7 @@ def test_slowfast_pathways_are_scheduled_on_two_lanes():
     assert len(edges) == 5                       # nothing else crosses lanes
     # every op that is waited for records an event
     assert sc["signals"] == {names.index(a) for a, _ in edges}
-    assert plan.stats["fused_block"] == 13 and len(names) == 90               # res2-res4 of the Fast pathway (3 + 4 + 6 blocks)
+    assert plan.stats["fused_block"] == 7 and len(names) == 103               # res2 + res3 of the Fast pathway (3 + 4 blocks)
     # single-lane models keep one stream
     p2, _ = lower_only(PH.slow_r50().eval(), torch.zeros(1, 3, 8, 224, 224))
     p2._schedule()

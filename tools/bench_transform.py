@@ -71,6 +71,44 @@ def main():
                      "achieved_GBps_algorithmic": alg / us / 1e3, "frac_of_hbm_peak": alg / us / 1e3 / peaks["hbm_gbs"],
                      "sector_granular_GBps(25.5MB)": 25.5e6 / us / 1e3, "whole_frames_GBps(104.3MB)": 104.3e6 / us / 1e3,
                      "hbm_peak_GBps": peaks["hbm_gbs"], "l2": "4 different 398 MB source clips in rotation (> L2)"}
+    # ---- round 2: batched, table-free kernel (pv_clip_transform_batch): ONE launch over 32 clips of BASELINE config 5
+    del clips[1:]
+    torch.cuda.empty_cache()
+    nb = 32
+    batch = torch.empty((nb, 3, 64, 1080, 1920), dtype=torch.uint8, device=dev)          # 12.7 GB of decoded frames
+    g = torch.Generator(device=dev).manual_seed(5)
+    for b in range(nb):
+        batch[b].random_(0, 256, generator=g)
+    outb = torch.empty((nb, 3, 16, 224, 224), dtype=torch.float16, device=dev)
+    for label, kw in (("batch32", {}), ("batch32_slowfast_pack", {"slowfast_alpha": 4})):
+        trb = FusedClipTransform(16, (0.45,) * 3, (0.225,) * 3, short_side=256, crop=("center", 224), out_dtype=torch.float16, **kw)
+        for _ in range(3):
+            trb(batch, out=outb)
+        torch.cuda.synchronize()
+        n = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            trb(batch, out=outb)
+        e1.record()
+        torch.cuda.synchronize()
+        usb = e0.elapsed_time(e1) / n * 1e3 / nb
+        res[label] = {"us_per_clip": usb, "clips_per_s": 1e6 / usb, "achieved_GBps_algorithmic(14.45MB)": alg / usb / 1e3,
+                      "frac_of_hbm_peak": alg / usb / 1e3 / peaks["hbm_gbs"], "sector_granular_GBps(25.5MB)": 25.5e6 / usb / 1e3,
+                      "frac_of_hbm_peak_sector_granular": 25.5e6 / usb / 1e3 / peaks["hbm_gbs"],
+                      "launch": "one launch per 32 clips, public FusedClipTransform call (host index set-up included)"}
+    one = FusedClipTransform(16, (0.45,) * 3, (0.225,) * 3, short_side=256, crop=("center", 224), out_dtype=torch.float16)
+    for _ in range(3):
+        one(batch[0], out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(64):
+        one(batch[i % nb], out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    res["single_clip_public_call_us"] = e0.elapsed_time(e1) / 64 * 1e3
+    del batch
     # CPU oracle (numpy restatement of the reference chain), one clip
     clip_np = clips[0].cpu().numpy()
     t0 = time.perf_counter()
