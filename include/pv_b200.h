@@ -213,6 +213,15 @@ int pv_dwconv3d_fwd(const pv_conv3d_desc* d, const void* x, const void* w, const
 /* 1 if PV_ALGO_TCGEN05 supports this descriptor (pure host-side check, no GPU needed). */
 int pv_conv3d_tcgen05_supported(const pv_conv3d_desc* d);
 
+/* Stem convolutions (ResNetBasicStem.forward models/stem.py:252-260 conv; X3D stem conv_t models/x3d.py:83-88) on the
+ * 4-channel, W-padded network input, stride 2 along W: zero-copy im2col - the A operand of a filter row is the RAW
+ * input row in shared memory, addressed by a no-swizzle UMMA descriptor with a 16-byte K-chunk stride (csrc/pv_stem.cu).
+ * Descriptor: window-mode conventions of pv_conv3d_desc (x_w_pad, x_w_phys, ci_pad64 = window length 16|32|64).
+ * w: f16 [K / 8][pad16(Co)][8], K = (dt * kh + dh) * window + (lead + dw) * 4 + c;  zero_row: >= 4 KiB of zeros. */
+int pv_conv3d_stem_rows_supported(const pv_conv3d_desc* d);
+int pv_conv3d_stem_rows_fwd(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                            const float* bias, const void* zero_row, void* y, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused bottleneck block for narrow pathways (SlowFast Fast pathway), ONE launch:
  *   a = relu(bn_a(conv_a(x)))  (kt,1,1) C_in -> C_mid;   b = relu(bn_b(conv_b(a)))  (1,3,3) stride (1,sb,sb), pad 1

@@ -100,6 +100,8 @@ SIGNATURES = {
     "pv_temporal_tap_sum": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_ll, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_ll, c_ll, c_vp]),
     "pv_conv3d_tcgen05_supported": (C.c_int, [C.POINTER(Conv3dDesc)]),
+    "pv_conv3d_stem_rows_supported": (C.c_int, [C.POINTER(Conv3dDesc)]),
+    "pv_conv3d_stem_rows_fwd": (C.c_int, [C.POINTER(Conv3dDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pv_bottleneck_fused_supported": (C.c_int, [C.POINTER(BottleneckDesc)]),
     "pv_bottleneck_fused_fwd": (C.c_int, [C.POINTER(BottleneckDesc)] + [c_vp] * 15),
     "pv_pool3d_fwd": (C.c_int, [C.POINTER(Pool3dDesc), c_vp, c_vp, c_vp]),

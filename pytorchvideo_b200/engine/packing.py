@@ -111,3 +111,15 @@ def pack_rows_k16(w, ci_pad, co_pad):
     t[:, :, :ci] = w.detach().cpu().permute(0, 2, 3, 4, 1).reshape(co, taps, ci).to(torch.float16)
     out[:co, :k] = t.reshape(co, k)
     return out.contiguous()
+
+
+def pack_stem_rows(w, ci_pad, co_pad, lead=0):
+    """Stem-rows kernel (csrc/pv_stem.cu): the window packing of ``pack_dense_window`` re-ordered to the canonical
+    no-swizzle K-major UMMA layout with all output channels of a 16-byte K chunk contiguous:
+    [Co, Ci, kt, kh, kw] -> f16 [K / 8][pad16(co_pad)][8]."""
+    rows = pack_dense_window(w, ci_pad, co_pad, lead)            # [co_pad, K]
+    n16 = (co_pad + 15) // 16 * 16
+    k = rows.shape[1]
+    full = torch.zeros(n16, k, dtype=torch.float16)
+    full[:co_pad] = rows
+    return full.reshape(n16, k // 8, 8).permute(1, 0, 2).contiguous()

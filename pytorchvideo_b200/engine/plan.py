@@ -371,6 +371,7 @@ class Plan:
             w_lead = PK.window_lead(x.padw[0], pw, x.Cp)
             d.ci_pad64 = PK.window_elems(kw, x.Cp, w_lead)
 
+        stem_rows, zero_row = False, None
         if depthwise:
             algo, kind = L.ALGO_DIRECT, "depthwise"
             w_d = self.const(PK.pack_depthwise(weight, co_pad, tdt))
@@ -380,7 +381,14 @@ class Plan:
                 want_tc = force_algo == L.ALGO_TCGEN05
             if window and not want_tc:
                 raise RuntimeError("internal: window-mode stem rejected by the library: " + L.last_error())
-            if want_tc:
+            stem_rows = (window and want_tc and residual is None and not os.environ.get("PVB200_NO_STEMROWS")
+                         and bool(self.lib.pv_conv3d_stem_rows_supported(C.byref(d))))
+            if stem_rows:
+                # zero-copy im2col over raw input rows (csrc/pv_stem.cu): its own weight layout and entry point
+                algo, kind = L.ALGO_TCGEN05, "tcgen05"
+                w_d = self.const(PK.pack_stem_rows(weight, x.Cp, co_pad, w_lead))
+                zero_row = self.const(torch.zeros(4096, dtype=torch.float16))
+            elif want_tc:
                 algo, kind = L.ALGO_TCGEN05, "tcgen05"
                 w_d = self.const(PK.pack_dense_window(weight, x.Cp, co_pad, w_lead) if window
                                  else PK.pack_dense_tcgen05(weight, ci_pad64, co_pad))
@@ -404,6 +412,11 @@ class Plan:
                                         y.ptr(), sums.tensor.data_ptr() if sums is not None else None, stream),
                     "pv_dwconv3d_fwd(%s)" % name)
 
+        def fn_stem(stream):
+            d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
+            L.check(lib.pv_conv3d_stem_rows_fwd(C.byref(d), x.ptr(), w_d.data_ptr(), scale_d.data_ptr(), bias_d.data_ptr(),
+                                                zero_row.data_ptr(), y.ptr(), stream), "pv_conv3d_stem_rows_fwd(%s)" % name)
+
         def fn(stream):
             d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride   # may have been retargeted
             d.res_row_stride = residual.row_stride if residual is not None else 0
@@ -414,7 +427,9 @@ class Plan:
         m_out = x.N * To * Ho * Wo
         flops = 2.0 * m_out * co * cig * kt * kh * kw
         nbytes = (x.N * x.npos * ci + m_out * co * (2 if residual is not None else 1)) * esz + weight.numel() * esz
-        self.add(name, fn_dw if (depthwise and residual is None) else fn, kind, flops, nbytes,
+        if stem_rows:
+            self.stats["stem_rows"] = self.stats.get("stem_rows", 0) + 1
+        self.add(name, fn_stem if stem_rows else (fn_dw if (depthwise and residual is None) else fn), kind, flops, nbytes,
                  reads=(x,) + ((residual,) if residual is not None else ()), writes=(y,) + ((sums,) if sums is not None else ()))
         return y
 
