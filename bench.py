@@ -398,6 +398,33 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in pinned)
     d2h = host_out.numel() * host_out.element_size()
 
+    # The fp32 host clips make the e2e number PCIe-bound (SlowFast: 193 MB per step at ~53 GB/s = 3.6 ms > the forward).
+    # Same serving loop with f16 pinned host clips (what a decoder + fused transform hands over): reported beside it.
+    e2e16 = None
+    if args.precision == "f16":
+        pinned16 = [t.half().pin_memory() for t in host_list]
+        cm16 = compile_model(model, [t.to(dev) for t in pinned16] if is_sf else pinned16[0].to(dev), dtype="f16", use_graph=True)
+        pipe16 = cm16.pipeline(depth=2)
+        if world > 1:
+            pipe16.post = _gather
+        t16 = []
+
+        def step16():
+            t16.append(pipe16.submit(pinned16 if is_sf else pinned16[0]))
+            if len(t16) > 1:
+                pipe16.result(t16.pop(0))
+
+        def drain16():
+            while t16:
+                pipe16.result(t16.pop(0))
+        for _ in range(3):
+            step16()
+        drain16()
+        ms16 = timed(step16, args.steps, drain16)
+        e2e16 = {"value": world * B * args.steps / (ms16 / 1e3), "ms_per_step": ms16 / args.steps,
+                 "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in pinned16)}
+        del cm16, pipe16
+
     # ---- roofline of the dominant kernel (per-launch CUDA events, eager replay on torch's stream)
     per_op = cm.plan.profile(iters=3)
     kinds = {}
@@ -456,7 +483,8 @@ def main():
                            "weights": "random (seeded), BN stats randomised"},
                 "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "mode": "double-buffered H2D/compute/D2H (engine/pipeline.py)",
-                        "serial_ms_per_step": ms_e2e_serial / args.steps},
+                        "serial_ms_per_step": ms_e2e_serial / args.steps, "host_dtype": "f32 pinned clips (PCIe-bound)",
+                        "f16_host_clips": e2e16},
                 "gpu_launches": args.steps * cm.plan.num_launches(),
                 "launches_per_step": cm.plan.num_launches(),
                 "roofline": roof, "whole_model": whole, "clocks": clocks}

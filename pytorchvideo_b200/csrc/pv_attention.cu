@@ -123,6 +123,7 @@ static int launch_attention(const pv_attention_desc* d, const void* q, const voi
   return PV_OK;
 }
 
+int attention_tc_dispatch(const pv_attention_desc* d, const void* q, const void* k, const void* v, void* o, cudaStream_t s);
 int attention_mma_dispatch(const pv_attention_desc* d, const void* q, const void* k, const void* v, void* o,
                            cudaStream_t s);   // pv_attention_mma.cu
 
@@ -135,8 +136,10 @@ extern "C" int pv_attention_fwd(const pv_attention_desc* d, const void* q, const
   PV_CHECK_ARG(d->B > 0 && d->H > 0 && d->Nq > 0 && d->Nk > 0, "empty attention problem");
   PV_CHECK_ARG((long long)d->B * d->H <= 65535, "B*H too large");
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->dtype == PV_F16 && !getenv("PVB200_ATTN_SIMT")) {     // tensor-core path (f16 storage)
-    const int rc = pv::attention_mma_dispatch(d, q, k, v, o, s);
+  if (d->dtype == PV_F16 && !getenv("PVB200_ATTN_SIMT")) {     // tensor-core paths (f16 storage)
+    int rc = pv::attention_tc_dispatch(d, q, k, v, o, s);      // tcgen05 / TMEM / TMA (pv_attention_tc.cu)
+    if (rc != PV_ERR_UNSUPPORTED) return rc;
+    rc = pv::attention_mma_dispatch(d, q, k, v, o, s);         // mma.sync fallback (head dims / strides the TMA path rejects)
     if (rc != PV_ERR_UNSUPPORTED) return rc;
   }
 #define PV_ATT(DD)                                                                              \

@@ -206,6 +206,8 @@ def clip_transform_batch(x, frame_idx=None, resize_hw=None, window=None, mean=No
     squeeze = False
     if torch.is_tensor(x) and x.dim() == 4:
         x, squeeze = x.unsqueeze(0), True
+        out = out.unsqueeze(0) if out is not None and out.dim() == 4 else out
+        out_slow = out_slow.unsqueeze(0) if out_slow is not None and out_slow.dim() == 4 else out_slow
     if not torch.is_tensor(x) or x.dim() != 5:
         raise RuntimeError("expected a (B, C, T, H, W) or (C, T, H, W) tensor")
     if x.device.type != "cuda":
