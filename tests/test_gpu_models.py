@@ -66,9 +66,9 @@ F16_BOUNDS = {
     "c2d_r50": (0.82, 8e-4),             # 0.860 / 5.1e-4
     "csn_r101": (0.84, 8e-4),            # 0.885 / 5.2e-4
     "i3d_r50": (0.83, 9e-4),             # 0.868 / 5.4e-4
-    "mvit_base_8x112": (0.54, 1.9e-3),   # 0.615 / 1.24e-3
-    "mvit_base_16x4": (0.62, 1.5e-3),    # 0.660 / 9.6e-4
-    "mvit_base_32x3": (0.62, 1.5e-3),    # 0.660 / 1.02e-3
+    "mvit_base_8x112": (0.54, 1.9e-3),   # 0.615-0.629 / 1.28e-3
+    "mvit_base_16x4": (0.55, 1.6e-3),    # 0.610-0.660 / 1.06e-3 (mma.sync vs tcgen05 attention: +-0.05)
+    "mvit_base_32x3": (0.55, 1.8e-3),    # 0.630-0.660 / 1.21e-3
     # softmax head: the outputs are probabilities, |d p| ~ p * |d logit| - the relative error of the largest
     # probability is the ABSOLUTE logit error (~5e-4 * |logit| scale 15), in-band fraction 0.993
     "r2plus1d_r50": (0.97, 1.2e-2),      # 0.993 / 7.7e-3
