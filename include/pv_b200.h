@@ -291,13 +291,14 @@ int pv_head_reduce(const void* x, int dtype, long long row_stride, int N, long l
  *                holds `groups` consecutive groups of C channels normalised independently with the
  *                same gamma/beta (groups = heads for the per-head norm_q/k/v, attention.py:200-205)
  *                nn.LayerNorm(eps=1e-6) at attention.py:655,703 / vision_transformers.py:333.
- * pv_linear    : y[m][n] = act(sum_k x[m][k] w[n][k] + bias[n]) (+ residual[m][n])
- *                nn.Linear at attention.py:93-95,315-320,541,716  (routes to the conv kernels
- *                as a 1x1x1 convolution; kept as its own entry point for the reference's
- *                Linear call sites).
+ * nn.Linear    : (attention.py:93-95,315-320,541,716) has NO entry point of its own: y = act(x W^T + b) (+ residual) on a
+ *                token tensor [B*N, C] is pv_conv3d_fwd with a 1x1x1 filter (N = B, T = H = 1, W = tokens).
  * pv_attention : o = softmax((q*scale) k^T) v (+ q)    attention.py:531-539, flash-style, the
  *                N_q x N_k matrix is never materialised.  q/k/v/o are [B][N][H][D] with
  *                explicit row strides (elements between consecutive tokens), D = head dim.
+ *                f16: tcgen05 kernel (S and O accumulators in TMEM, Q/K/V tiles by TMA, V consumed MN-major as it
+ *                lies in memory, two-sweep softmax: csrc/pv_attention_tc.cu), mma.sync kernel for head dims /
+ *                strides the TMA path rejects; f32: CUDA-core flash kernel.
  * ------------------------------------------------------------------------------------------- */
 int pv_layernorm(const void* x, void* y, int dtype, long long rows, int groups, int C,
                  long long x_row_stride, long long y_row_stride, const float* gamma,

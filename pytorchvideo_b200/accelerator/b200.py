@@ -18,23 +18,40 @@ class B200Block(EfficientBlockBase):
         super().__init__()
         self.block = block            # parameters stay owned by the original module (same state_dict keys + "block.")
         self.dtype = dtype
-        self._compiled = None
+        self._compiled = None         # the plan built by convert(input_blob_size)
+        self._by_shape = {}           # further shapes seen at run time (a final partial batch): one plan each
+
+    @staticmethod
+    def _shapes(x):
+        return tuple(tuple(t.shape) for t in x) if isinstance(x, (list, tuple)) else (tuple(x.shape),)
+
+    def _compile(self, shapes, device="cuda"):
+        from ..engine import compile_model
+        ex = [torch.empty(tuple(s), dtype=torch.float32, device=device) for s in shapes]
+        self.block.eval()
+        return compile_model(self.block, ex if len(ex) > 1 else ex[0], dtype=self.dtype)
 
     def convert(self, input_blob_size=None, **kwargs):
+        """EfficientBlockBase protocol (efficient_block_base.py:8-35): build the deployable form for the given input
+        size - here the static plan (BN folded, weights re-laid-out, TMA descriptors, CUDA graph).  Like the
+        reference's mobile blocks (convolutions.py:120-122) a block converts once."""
         assert self._compiled is None, "B200Block: already converted, cannot be converted again"
-        from ..engine import compile_model
         if input_blob_size is None:
             raise ValueError("convert() needs the input shape(s)")
-        shapes = input_blob_size if isinstance(input_blob_size[0], (tuple, list, torch.Size)) else [input_blob_size]
-        ex = [torch.empty(tuple(s), dtype=torch.float32, device="cuda") for s in shapes]
-        self.block.eval()
-        self._compiled = compile_model(self.block, ex if len(ex) > 1 else ex[0], dtype=self.dtype)
+        shapes = tuple(tuple(s) for s in input_blob_size) if isinstance(input_blob_size[0], (tuple, list, torch.Size)) \
+            else (tuple(input_blob_size),)
+        self._compiled = self._compile(shapes)
+        self._by_shape[shapes] = self._compiled
 
     def forward(self, x):
-        if self._compiled is None:    # unconverted: compile lazily for this shape
-            shapes = [tuple(t.shape) for t in x] if isinstance(x, (list, tuple)) else tuple(x.shape)
-            self.convert(shapes)
-        return self._compiled(x).clone()
+        shapes = self._shapes(x)
+        cm = self._by_shape.get(shapes)
+        if cm is None:                # unconverted block, or a shape convert() was not given: one more plan
+            dev = (x[0] if isinstance(x, (list, tuple)) else x).device
+            cm = self._by_shape[shapes] = self._compile(shapes, dev)
+            if self._compiled is None:
+                self._compiled = cm
+        return cm(x).clone()
 
 
 def transmute_b200(module: nn.Module):
@@ -57,13 +74,14 @@ def convert_to_deployable_form(model: nn.Module, input_tensor, **kwargs) -> nn.M
         model.convert(shapes)
         return model
     transmute_model(model, "b200")
-    shapes = {}
+    # one hooked forward: every efficient block is converted, explicitly, with the input size it actually receives
+    # (model_conversion.py:104-123 records input_blob_size the same way, then calls convert on each block)
     hooks = []
     for m in model.modules():
         if isinstance(m, B200Block):
             def hook(mod, inp):
-                x = inp[0]
-                shapes[mod] = [tuple(t.shape) for t in x] if isinstance(x, (list, tuple)) else tuple(x.shape)
+                if mod._compiled is None:
+                    mod.convert(B200Block._shapes(inp[0]) if isinstance(inp[0], (list, tuple)) else tuple(inp[0].shape))
             hooks.append(m.register_forward_pre_hook(hook))
     with torch.no_grad():
         model(input_tensor)

@@ -173,3 +173,51 @@ def test_full_size_bench_config_properties():
     perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4])
     permuted = model([t[perm.to(t.device)] for t in inp]).float().cpu()
     assert torch.allclose(permuted, full[perm], rtol=1e-3, atol=1e-3 * scale)
+
+
+def test_accelerator_transmute_route_matches_golden():
+    """The reference's plug-in protocol (accelerator/deployment/common/model_transmuter.py:53-86 +
+    mobile_cpu/utils/model_conversion.py:87-125) with target "b200": every top-level block of a model is replaced
+    by a B200Block, each block is converted with the input size recorded by one hooked forward, and the converted
+    model reproduces the reference golden like the whole-tree plan does (f16 tolerances of F16_BOUNDS)."""
+    from pytorchvideo_b200.accelerator import B200Block, convert_to_deployable_form, transmute_model
+    g, model, inp, _ = _setup_case("c1_x3d_xs")
+    model.cuda()
+    x = inp.cuda()
+    whole = model(x).float().cpu()
+    dep = convert_to_deployable_form(model, x)
+    blocks = [m for m in dep.modules() if isinstance(m, B200Block)]
+    assert len(blocks) == len(model.blocks) and all(b._compiled is not None for b in blocks)
+    with pytest.raises(AssertionError):
+        blocks[0].convert(tuple(x.shape))                    # a block converts once (convolutions.py:120-122)
+    out = dep(x).float().cpu()
+    ref = g["output"]
+    scale = float(ref.abs().max())
+    assert float((out - ref).abs().max()) <= 2e-3 * scale      # block boundaries round-trip through NCDHW fp32
+    assert float((out - whole).abs().max()) <= 2e-3 * scale
+    # a different batch size at run time gets its own plan instead of a silent broadcast
+    x3 = torch.cat([x, x, x], 0)
+    out3 = dep(x3).float().cpu()
+    assert out3.shape == (3, 400) and torch.allclose(out3[2:3], out, rtol=2e-3, atol=2e-3 * scale)
+    # in-place transmute of a fresh tree keeps the parameters (same state_dict values under "block." prefixes)
+    m2 = TS.build_case("c1_x3d_xs", PH, g["weight_seed"], g["input_seed"])[0].cuda()
+    sd = {k: v.clone() for k, v in m2.state_dict().items()}
+    transmute_model(m2, "b200")
+    sd2 = m2.state_dict()
+    assert len(sd2) == len(sd)
+    for k2, v2 in sd2.items():
+        k = k2.replace(".block.", ".", 1)                    # blocks.0.block.conv.conv_t.weight -> blocks.0.conv.conv_t.weight
+        assert k in sd and torch.equal(sd[k], v2), k2
+    model.cpu()
+
+
+def test_compiled_model_rejects_other_shapes():
+    from pytorchvideo_b200.engine import compile_model
+    model = TS.randomize_model(PH.x3d_xs(), seed=3).eval()
+    x = torch.rand(2, 3, 4, 160, 160).cuda()
+    cm = compile_model(model, x)
+    cm(x)
+    with pytest.raises(RuntimeError):
+        cm(x[:1])                                            # would broadcast into the static buffer
+    with pytest.raises(RuntimeError):
+        cm([x])
