@@ -95,9 +95,19 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "DRAM r
 def full_reports():
     out = ["# ncu `--set full --clock-control none` captures, round 2 (B200 sm_100a)", "",
            "Commands: tools/r02_evidence.sh (ncu section).  Times under ncu are cold-cache and serialised.", ""]
-    for rep in sorted(glob.glob(os.path.join(G, "r02_prof*.ncu-rep")) + glob.glob(os.path.join(G, "r02_fused.ncu-rep"))):
+    # the box exports each capture's raw page (r02_prof*.raw.csv) because the .ncu-rep files exceed the copy-back limit
+    reps = sorted(set(glob.glob(os.path.join(G, "r02_prof*.raw.csv")) + glob.glob(os.path.join(G, "r02_prof*.ncu-rep"))))
+    seen = set()
+    for rep in reps:
+        stem = os.path.basename(rep).replace(".raw.csv", "").replace(".ncu-rep", "")
+        if stem in seen:
+            continue
+        seen.add(stem)
         try:
-            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+            if rep.endswith(".csv"):
+                raw = open(rep).read()
+            else:
+                raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
         except Exception as e:
             out.append("%s: unreadable (%s)" % (os.path.basename(rep), e))
             continue
