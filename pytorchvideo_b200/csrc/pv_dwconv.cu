@@ -26,6 +26,8 @@ EncodeTiledFn get_encode_fn();   // pv_igemm.cu
 int conv3d_check(const pv_conv3d_desc* d);
 int conv3d_direct_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
                          const float* bias, const void* residual, void* y, cudaStream_t s);
+int dwconv3d_lane_launch(const pv_conv3d_desc* d, const void* x, const void* w, const float* scale,
+                         const float* bias, void* y, float* se_sums, cudaStream_t stream);   // pv_dwlane.cu
 
 struct DwParams {
   CUtensorMap x_map;          // [Cc(chunk) .. C, W, H, T, N] f16, box [cc, ww, hh, tt, 1], no swizzle
@@ -254,6 +256,10 @@ extern "C" int pv_dwconv3d_fwd(const pv_conv3d_desc* d, const void* x, const voi
   if (rc != PV_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (!getenv("PVB200_DW_SIMT")) {
+    if (!getenv("PVB200_DW_NO_LANE")) {      // 3x3x3: lane-per-channel-pair register stencil (pv_dwlane.cu)
+      rc = pv::dwconv3d_lane_launch(d, x, w, scale, bias, y, se_sums, s);
+      if (rc != PV_ERR_UNSUPPORTED) return rc;
+    }
     rc = pv::dwconv3d_tile_launch(d, x, w, scale, bias, y, se_sums, s);
     if (rc != PV_ERR_UNSUPPORTED) return rc;
   }

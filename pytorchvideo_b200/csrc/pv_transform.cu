@@ -78,14 +78,16 @@ clip_transform_kernel(pv_clip_transform_desc d, const SrcT* __restrict__ src,
 //   * optional second output = the SlowFast slow pathway (frames slow_pos[j] >= 0 of the kept frames,
 //     pytorchvideo_trainer datamodule/transforms.py:129-136), written from the same registers;
 //   * uint8 destination for pure frame selection / cropping (UniformTemporalSubsample keeps the dtype).
-// grid = (ceil(out_w / (PX * 128)), out_h, n_clips * n_t);  block = 128
+// grid = (1, ceil(out_h / TB_ROWS), n_clips * n_t);  block = (min(out_w/2, 256), 256 / that)
 // ---------------------------------------------------------------------------------------------------------------
 struct TapXY {
   int i0, i1;
   float l1;
 };
-__device__ __forceinline__ TapXY bilinear_tap(int dst, int in_size, int out_size) {
-  const float scale = __fdiv_rn((float)in_size, (float)out_size);
+__device__ __forceinline__ float bilinear_scale(int in_size, int out_size) {
+  return __fdiv_rn((float)in_size, (float)out_size);
+}
+__device__ __forceinline__ TapXY bilinear_tap(int dst, int in_size, float scale) {
   float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
   src = fmaxf(src, 0.f);
   TapXY t;
@@ -110,16 +112,32 @@ template <typename T> __device__ __forceinline__ void st_out2(T* p, float a, flo
   }
 }
 
-template <typename SrcT, typename OutT, int NC>
-__global__ void __launch_bounds__(128)
+// Round-2 rework after the ncu capture showed the first version ISSUE-bound, not HBM-bound (48 IEEE fp32 divisions per
+// thread for `x/255` and `(x-mean)/std`): a uint8 source has only 256 possible values per channel, so a block first
+// builds the value table lut[c][u] = ((float)u / 255 - mean[c]) / std[c] in shared memory with the reference's own
+// operations (bit-exact by construction) and a tap becomes one LDS.  A block of 256 threads covers TB_ROWS output
+// rows of one (clip, frame) so the table costs ~0.4 divisions per output instead of 8.
+constexpr int TB_ROWS = 8;
+constexpr int TB_THREADS = 256;
+
+template <typename SrcT, typename OutT, int NC, bool LUT>
+__global__ void __launch_bounds__(TB_THREADS)
 clip_transform_batch_kernel(pv_clip_batch_desc d, const SrcT* __restrict__ src, const int32_t* __restrict__ idx_t,
                             const int32_t* __restrict__ slow_pos, const int32_t* __restrict__ geom,
                             OutT* __restrict__ dst, OutT* __restrict__ dst_slow) {
   constexpr int PX = 2;
-  const int y = blockIdx.y;
+  __shared__ float lut[LUT ? NC * 256 : 1];
+  if constexpr (LUT) {
+    for (int e = threadIdx.y * blockDim.x + threadIdx.x; e < NC * 256; e += blockDim.x * blockDim.y) {
+      const int c = e >> 8;
+      float v = (float)(e & 255);
+      if (d.div255) v = v / 255.0f;                        // reference op order, fp32
+      if (d.normalize) v = (v - d.mean[c]) / d.stdv[c];
+      lut[e] = v;
+    }
+    __syncthreads();
+  }
   const int clip = blockIdx.z / d.n_t, j = blockIdx.z - clip * d.n_t;
-  const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
-  if (xb >= d.out_w) return;
   int new_h = d.new_h, new_w = d.new_w, top = d.top, left = d.left, flip = d.hflip;
   int t_off = 0;
   if (geom != nullptr) {        // per-clip (new_h, new_w, top, left, hflip, first frame)
@@ -127,49 +145,89 @@ clip_transform_batch_kernel(pv_clip_batch_desc d, const SrcT* __restrict__ src, 
     new_h = __ldg(g); new_w = __ldg(g + 1); top = __ldg(g + 2); left = __ldg(g + 3); flip = __ldg(g + 4);
     t_off = __ldg(g + 5);
   }
-  const long long frame = (long long)clip * d.s_clip + (long long)(__ldg(idx_t + j) + t_off) * d.st;
-  const TapXY ty = bilinear_tap(top + y, d.in_h, new_h);
-  const float ly1 = ty.l1, ly0 = 1.f - ly1;
-  const SrcT* r0 = src + frame + (long long)ty.i0 * d.sh;
-  const SrcT* r1 = src + frame + (long long)ty.i1 * d.sh;
-  TapXY tx[PX];
+  // block-uniform channel planes of this (clip, frame); everything per thread below is a 32-bit offset into them
+  // (the host checks in_h*|sh| + in_w*|sw| < 2^31)
+  const SrcT* cbase[NC];
 #pragma unroll
-  for (int i = 0; i < PX; ++i) {
-    const int xo = min(xb + i, d.out_w - 1);
-    tx[i] = bilinear_tap(left + (flip ? d.out_w - 1 - xo : xo), d.in_w, new_w);
-  }
-  // all loads first (independent), then the arithmetic
-  float v[NC][PX][4];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const long long co = (long long)c * d.sc;
-#pragma unroll
-    for (int i = 0; i < PX; ++i) {
-      const long long xa = (long long)tx[i].i0 * d.sw + co, xc = (long long)tx[i].i1 * d.sw + co;
-      v[c][i][0] = ld_src<SrcT>(r0 + xa); v[c][i][1] = ld_src<SrcT>(r0 + xc);
-      v[c][i][2] = ld_src<SrcT>(r1 + xa); v[c][i][3] = ld_src<SrcT>(r1 + xc);
-    }
-  }
+  for (int c = 0; c < NC; ++c)
+    cbase[c] = src + (long long)clip * d.s_clip + (long long)(__ldg(idx_t + j) + t_off) * d.st + (long long)c * d.sc;
   const int sp = slow_pos != nullptr ? __ldg(slow_pos + j) : -1;
-  const bool two = (xb + 1 < d.out_w);
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const float mean = d.mean[c], stdv = d.stdv[c];
-    float out[PX];
+  const int half_w = (d.out_w + PX - 1) / PX;
+  const int y_base = blockIdx.y * TB_ROWS;
+  const int n_rows = min(TB_ROWS, d.out_h - y_base);
+  const int plane = d.out_h * d.out_w;                 // host checks C*n_t*plane < 2^31
+  const unsigned sh = (unsigned)d.sh, sw = (unsigned)d.sw;
+  const float scale_y = bilinear_scale(d.in_h, new_h), scale_x = bilinear_scale(d.in_w, new_w);
+  OutT* const dclip = dst + (long long)clip * d.d_clip + (long long)j * plane;
+  OutT* const sclip = sp >= 0 ? dst_slow + (long long)clip * d.d_slow_clip + (long long)sp * plane : nullptr;
+  const int cstep = d.n_t * plane, cstep_slow = d.n_slow * plane;
+
+  // blockDim = (bx, by): x pairs along threadIdx.x, rows interleaved along threadIdx.y; the column taps are
+  // computed once per thread and reused by its rows
+  for (int xi = threadIdx.x; xi < half_w; xi += blockDim.x) {
+    const int xb = xi * PX;
+    unsigned xo0[PX], xo1[PX];
+    float lx0[PX], lx1[PX];
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
-      float a = v[c][i][0], b = v[c][i][1], e = v[c][i][2], f = v[c][i][3];
-      if (d.div255) { a = a / 255.0f; b = b / 255.0f; e = e / 255.0f; f = f / 255.0f; }   // reference op order, fp32
-      if (d.normalize) { a = (a - mean) / stdv; b = (b - mean) / stdv; e = (e - mean) / stdv; f = (f - mean) / stdv; }
-      const float lx1 = tx[i].l1, lx0 = 1.f - lx1;
-      out[i] = ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * e + lx1 * f);
+      const int xo = min(xb + i, d.out_w - 1);
+      const TapXY t = bilinear_tap(left + (flip ? d.out_w - 1 - xo : xo), d.in_w, scale_x);
+      xo0[i] = t.i0 * sw; xo1[i] = t.i1 * sw;
+      lx1[i] = t.l1; lx0[i] = 1.f - t.l1;
     }
-    const long long pix = (long long)y * d.out_w + xb;
-    OutT* o = dst + (long long)clip * d.d_clip + ((long long)c * d.n_t + j) * d.out_h * d.out_w + pix;
-    st_out2<OutT>(o, out[0], out[1], two);
-    if (sp >= 0) {
-      OutT* os = dst_slow + (long long)clip * d.d_slow_clip + ((long long)c * d.n_slow + sp) * d.out_h * d.out_w + pix;
-      st_out2<OutT>(os, out[0], out[1], two);
+    const bool two = (xb + 1 < d.out_w);
+    for (int r = threadIdx.y; r < n_rows; r += blockDim.y) {
+      const int y = y_base + r;
+      const TapXY ty = bilinear_tap(top + y, d.in_h, scale_y);
+      const float ly1 = ty.l1, ly0 = 1.f - ly1;
+      const unsigned ro0 = ty.i0 * sh, ro1 = ty.i1 * sh;
+      unsigned off[PX][4];
+#pragma unroll
+      for (int i = 0; i < PX; ++i) {
+        off[i][0] = ro0 + xo0[i]; off[i][1] = ro0 + xo1[i];
+        off[i][2] = ro1 + xo0[i]; off[i][3] = ro1 + xo1[i];
+      }
+      // all loads first (independent), then the arithmetic
+      float v[NC][PX][4];
+      if constexpr (LUT) {
+        unsigned u[NC][PX][4];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < PX; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[c][i][k] = __ldg(cbase[c] + off[i][k]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < PX; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[c][i][k] = lut[c * 256 + u[c][i][k]];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float mean = d.mean[c], stdv = d.stdv[c];
+#pragma unroll
+          for (int i = 0; i < PX; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float t = ld_src<SrcT>(cbase[c] + off[i][k]);
+              if (d.div255) t = t / 255.0f;
+              if (d.normalize) t = (t - mean) / stdv;
+              v[c][i][k] = t;
+            }
+        }
+      }
+      const int pix = y * d.out_w + xb;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float out[PX];
+#pragma unroll
+        for (int i = 0; i < PX; ++i)
+          out[i] = ly0 * (lx0[i] * v[c][i][0] + lx1[i] * v[c][i][1]) + ly1 * (lx0[i] * v[c][i][2] + lx1[i] * v[c][i][3]);
+        st_out2<OutT>(dclip + (c * cstep + pix), out[0], out[1], two);
+        if (sp >= 0) st_out2<OutT>(sclip + (c * cstep_slow + pix), out[0], out[1], two);
+      }
     }
   }
 }
@@ -238,7 +296,7 @@ extern "C" int pv_clip_transform_batch(const pv_clip_batch_desc* d, const void* 
   PV_CHECK_ARG(d && src && idx_t && dst, "null argument");
   PV_CHECK_ARG(d->C >= 1 && d->C <= 4, "C must be in 1..4 (got %d)", d->C);
   PV_CHECK_ARG(d->n_clips >= 1 && d->n_t >= 1 && d->out_h >= 1 && d->out_w >= 1, "empty output");
-  PV_CHECK_ARG(d->out_h <= 65535 && (long long)d->n_clips * d->n_t <= 65535, "grid too large");
+  PV_CHECK_ARG((long long)d->n_clips * d->n_t <= 65535, "grid too large");
   PV_CHECK_ARG(d->in_h >= 1 && d->in_w >= 1 && d->new_h >= 1 && d->new_w >= 1, "bad frame size");
   PV_CHECK_ARG(geom != nullptr || (d->top >= 0 && d->left >= 0 && d->top + d->out_h <= d->new_h && d->left + d->out_w <= d->new_w),
                "crop window outside the resized frame");
@@ -247,10 +305,26 @@ extern "C" int pv_clip_transform_batch(const pv_clip_batch_desc* d, const void* 
   PV_CHECK_ARG(!pass || (d->src_dtype == PV_U8 && !d->div255 && !d->normalize && geom == nullptr && d->new_h == d->in_h && d->new_w == d->in_w),
                "uint8 output is a pure frame selection / crop (no resize, no arithmetic)");
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((unsigned)pv::cdiv(d->out_w, 2 * 128), d->out_h, d->n_clips * d->n_t), block(128);
-#define PV_TB(ST, OT, NC)                                                                                      \
-  pv::clip_transform_batch_kernel<ST, OT, NC><<<grid, block, 0, s>>>(*d, (const ST*)src, idx_t, slow_pos, geom, \
-                                                                    (OT*)dst, (OT*)dst_slow)
+  const int half_w = (d->out_w + 1) / 2;
+  const unsigned bx = (unsigned)(half_w >= pv::TB_THREADS ? pv::TB_THREADS : half_w);
+  const unsigned by = (unsigned)(pv::TB_THREADS / bx >= pv::TB_ROWS ? pv::TB_ROWS : (pv::TB_THREADS / bx < 1 ? 1 : pv::TB_THREADS / bx));
+  dim3 grid(1, (unsigned)pv::cdiv(d->out_h, pv::TB_ROWS), d->n_clips * d->n_t), block(bx, by);
+  PV_CHECK_ARG(grid.y <= 65535, "grid too large");
+  auto absll = [](long long v) { return v < 0 ? -v : v; };
+  PV_CHECK_ARG((long long)d->in_h * absll(d->sh) + (long long)d->in_w * absll(d->sw) < (1ll << 31) && d->sh >= 0 && d->sw >= 0,
+               "frame too large for 32-bit in-plane offsets");
+  PV_CHECK_ARG((long long)d->C * (d->n_t > d->n_slow ? d->n_t : d->n_slow) * d->out_h * d->out_w < (1ll << 31),
+               "output clip too large for 32-bit offsets");
+  const bool arith = d->div255 || d->normalize;
+#define PV_TB(ST, OT, NC)                                                                                              \
+  do {                                                                                                                 \
+    if (std::is_same<ST, uint8_t>::value && arith)                                                                     \
+      pv::clip_transform_batch_kernel<ST, OT, NC, std::is_same<ST, uint8_t>::value><<<grid, block, 0, s>>>(            \
+          *d, (const ST*)src, idx_t, slow_pos, geom, (OT*)dst, (OT*)dst_slow);                                         \
+    else                                                                                                               \
+      pv::clip_transform_batch_kernel<ST, OT, NC, false><<<grid, block, 0, s>>>(*d, (const ST*)src, idx_t, slow_pos,   \
+                                                                               geom, (OT*)dst, (OT*)dst_slow);         \
+  } while (0)
 #define PV_TBC(ST, OT)                                                          \
   do {                                                                          \
     switch (d->C) {                                                             \

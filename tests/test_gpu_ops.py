@@ -105,6 +105,12 @@ DW_CASES = [
     (1, 64, 6, 15, 15, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     (1, 128, 2, 7, 7, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     (1, 10, 3, 6, 6, (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # padded channels (10 -> 16)
+    # lane-per-channel-pair kernel (pv_dwlane.cu), X3D-M planes: 2x7 patches on 14x14 / 7x7 (masked row), uneven chunks
+    (1, 216, 4, 14, 14, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 432, 3, 7, 7, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 216, 3, 28, 28, (3, 3, 3), (1, 2, 2), (1, 1, 1)),    # stride 2 -> 14x14
+    (2, 112, 3, 28, 28, (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # 4x4 patches, two chunks of 56
+    (1, 54, 5, 56, 56, (3, 3, 3), (1, 1, 1), (1, 1, 1)),     # X3D-M res2 plane (54 -> 56 padded channels)
 ]
 
 
