@@ -49,6 +49,14 @@ class B200Module(nn.Module):
         cache[key] = cm                            # (re)insert at the most-recently-used end
         return cm
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle (the reference's transmuter deep-copies the model): compiled plans hold device
+        buffers, CUDA graphs and ctypes descriptors and are derived data - a copy recompiles on its first call."""
+        st = dict(self.__dict__)
+        st.pop("_pv_cache", None)
+        st.pop("_pv_tensors", None)
+        return st
+
     def _apply(self, fn, *a, **k):
         self.__dict__.pop("_pv_tensors", None)     # .to()/.cuda() may replace parameter objects
         return super()._apply(fn, *a, **k)

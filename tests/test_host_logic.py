@@ -234,3 +234,17 @@ def test_lowering_accepts_the_reference_modules_themselves():
             sys.path.remove(p)
         for k in [k for k in sys.modules if k == "pytorchvideo" or k.startswith("pytorchvideo.") or k.startswith("fvcore")]:
             del sys.modules[k]
+
+
+def test_modules_deepcopy_without_their_compiled_plans():
+    """The reference's transmuter deep-copies models (accelerator/deployment/common/model_transmuter.py); compiled plans
+    (device buffers, graphs, ctypes descriptors) are derived data and must not travel with a copy or a pickle."""
+    import copy
+    import ctypes
+    m = PH.x3d_xs().eval()
+    m.__dict__["_pv_cache"] = {"k": ctypes.pointer(ctypes.c_int(1))}
+    m.blocks[1].__dict__["_pv_cache"] = {"k": ctypes.pointer(ctypes.c_int(1))}
+    m2 = copy.deepcopy(m)
+    assert "_pv_cache" not in m2.__dict__ and "_pv_cache" not in m2.blocks[1].__dict__
+    assert "_pv_cache" in m.__dict__
+    assert list(m2.state_dict()) == list(m.state_dict())
