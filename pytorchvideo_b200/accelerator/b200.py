@@ -64,16 +64,22 @@ def transmute_b200(module: nn.Module):
 EFFICIENT_BLOCK_TRANSMUTER_REGISTRY.setdefault("b200", []).append(transmute_b200)
 
 
-def convert_to_deployable_form(model: nn.Module, input_tensor, **kwargs) -> nn.Module:
+def convert_to_deployable_form(model: nn.Module, input_tensor, whole_model=True, **kwargs) -> nn.Module:
     """Reference protocol (mobile_cpu/utils/model_conversion.py:87-125): deep-copy, eval, record each
-    efficient block's input shape with one hooked forward, then call ``convert(input_blob_size)``."""
+    efficient block's input shape with one hooked forward, then call ``convert(input_blob_size)``.
+
+    A model that was already transmuted (``transmute_model(model, "b200")``) keeps its blocks.  An untouched model
+    that the engine can lower as a whole becomes ONE block (one plan, no NCDHW round trips between blocks);
+    ``whole_model=False`` forces the per-block route of the reference protocol."""
     model = deepcopy(model).eval()
-    if type(model).__name__ in _WHOLE_BLOCKS:
+    transmuted = any(isinstance(m, B200Block) for m in model.modules())
+    if not transmuted and whole_model and type(model).__name__ in _WHOLE_BLOCKS:
         model = B200Block(model)
         shapes = [tuple(t.shape) for t in input_tensor] if isinstance(input_tensor, (list, tuple)) else tuple(input_tensor.shape)
         model.convert(shapes)
         return model
-    transmute_model(model, "b200")
+    if not transmuted:
+        transmute_model(model, "b200")
     # one hooked forward: every efficient block is converted, explicitly, with the input size it actually receives
     # (model_conversion.py:104-123 records input_blob_size the same way, then calls convert on each block)
     hooks = []

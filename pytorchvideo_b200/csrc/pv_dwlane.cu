@@ -44,7 +44,15 @@ struct DwLaneParams {
 
 constexpr int DWL_WARPS = 8;
 
-template <int S, int PH, int PW>
+// Blackwell's packed fp32 FMA (PTX fma.rn.f32x2, SASS FFMA2): one issue slot for the two channels of a lane
+__device__ __forceinline__ float2 fma_x2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+template <int S, int PH, int PW, bool X2>
 __global__ void __launch_bounds__(DWL_WARPS * 32, 2)
 dwconv3d_lane_kernel(const __grid_constant__ DwLaneParams P, const __half* __restrict__ w,
                      const float* __restrict__ scale, const float* __restrict__ bias,
@@ -116,8 +124,12 @@ dwconv3d_lane_kernel(const __grid_constant__ DwLaneParams P, const __half* __res
               if (j - kw < 0 || (j - kw) % S != 0 || (j - kw) / S >= PW) continue;
               float2& a = acc[(i - kh) / S][(j - kw) / S];
               const float2 wv = wr[(kt * 3 + kh) * 3 + kw];
-              a.x = fmaf(xv.x, wv.x, a.x);
-              a.y = fmaf(xv.y, wv.y, a.y);
+              if constexpr (X2) {
+                a = fma_x2(xv, wv, a);
+              } else {
+                a.x = fmaf(xv.x, wv.x, a.x);
+                a.y = fmaf(xv.y, wv.y, a.y);
+              }
             }
           }
         }
@@ -228,11 +240,18 @@ int dwconv3d_lane_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   }
   const size_t smem = (size_t)P.tt * P.hh * P.ww * P.cc * 2 + 256;
   dim3 grid((unsigned)tiles, (unsigned)chunks), block(DWL_WARPS * 32);
+  static const bool x2 = [] { const char* e = getenv("PVB200_DW_X2"); return !(e && e[0] == '0'); }();
 #define PV_DWL(S_, PH_, PW_)                                                                                  \
   do {                                                                                                        \
-    PV_OPT_IN_SMEM((dwconv3d_lane_kernel<S_, PH_, PW_>), 110 * 1024);                                         \
-    dwconv3d_lane_kernel<S_, PH_, PW_><<<grid, block, smem, stream>>>(P, (const __half*)w, scale, bias,       \
-                                                                     (__half*)y, se_sums);                    \
+    if (x2) {                                                                                                 \
+      PV_OPT_IN_SMEM((dwconv3d_lane_kernel<S_, PH_, PW_, true>), 110 * 1024);                                 \
+      dwconv3d_lane_kernel<S_, PH_, PW_, true><<<grid, block, smem, stream>>>(P, (const __half*)w, scale,     \
+                                                                             bias, (__half*)y, se_sums);      \
+    } else {                                                                                                  \
+      PV_OPT_IN_SMEM((dwconv3d_lane_kernel<S_, PH_, PW_, false>), 110 * 1024);                                \
+      dwconv3d_lane_kernel<S_, PH_, PW_, false><<<grid, block, smem, stream>>>(P, (const __half*)w, scale,    \
+                                                                              bias, (__half*)y, se_sums);     \
+    }                                                                                                         \
   } while (0)
   if (S == 1 && !p27) PV_DWL(1, 4, 4);
   else if (S == 1) PV_DWL(1, 2, 7);

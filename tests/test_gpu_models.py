@@ -185,7 +185,10 @@ def test_accelerator_transmute_route_matches_golden():
     model.cuda()
     x = inp.cuda()
     whole = model(x).float().cpu()
-    dep = convert_to_deployable_form(model, x)
+    one = convert_to_deployable_form(model, x)                 # untouched model the engine lowers whole: ONE block
+    assert isinstance(one, B200Block) and one._compiled is not None
+    assert float((one(x).float().cpu() - whole).abs().max()) <= 1e-3 * float(whole.abs().max())   # same plan; X3D SE sums use fp32 atomics
+    dep = convert_to_deployable_form(model, x, whole_model=False)
     blocks = [m for m in dep.modules() if isinstance(m, B200Block)]
     assert len(blocks) == len(model.blocks) and all(b._compiled is not None for b in blocks)
     with pytest.raises(AssertionError):
