@@ -42,7 +42,6 @@ struct DwLaneParams {
   long long y_row_stride, y_batch_stride;
 };
 
-constexpr int DWL_WARPS = 8;
 
 // Blackwell's packed fp32 FMA (PTX fma.rn.f32x2, SASS FFMA2): one issue slot for the two channels of a lane
 __device__ __forceinline__ float2 fma_x2(float2 a, float2 b, float2 c) {
@@ -52,15 +51,16 @@ __device__ __forceinline__ float2 fma_x2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-template <int S, int PH, int PW, bool X2>
-__global__ void __launch_bounds__(DWL_WARPS * 32, 2)
+// NW warps per CTA: 8 (two 100 KB CTAs per SM) or 4 (four 50 KB CTAs per SM - more CTAs to stagger the TMA waits)
+template <int S, int PH, int PW, bool X2, int NW>
+__global__ void __launch_bounds__(NW * 32, 16 / NW)
 dwconv3d_lane_kernel(const __grid_constant__ DwLaneParams P, const __half* __restrict__ w,
                      const float* __restrict__ scale, const float* __restrict__ bias,
                      __half* __restrict__ y, float* __restrict__ se_sums) {
   constexpr int IH = (PH - 1) * S + 3, IW = (PW - 1) * S + 3;
   extern __shared__ __align__(128) uint8_t dwl_smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ float2 se_part[DWL_WARPS][32];
+  __shared__ float2 se_part[NW][32];
   const __half* xs = reinterpret_cast<const __half*>(dwl_smem);          // [tt][hh][ww][cc]
   const int cc = P.cc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,7 +97,7 @@ dwconv3d_lane_kernel(const __grid_constant__ DwLaneParams P, const __half* __res
   const int total = P.bt * nph * npw;
   const int row_e = P.ww * cc;                       // elements per halo row
   float2 se = make_float2(0.f, 0.f);
-  for (int p = warp; p < total; p += DWL_WARPS) {
+  for (int p = warp; p < total; p += NW) {
     const int pwi = p % npw;
     const int r = p / npw;
     const int phi = r % nph, t = r / nph;
@@ -167,7 +167,7 @@ dwconv3d_lane_kernel(const __grid_constant__ DwLaneParams P, const __half* __res
     if (warp == 0 && live) {
       float2 tot = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < DWL_WARPS; ++k) { tot.x += se_part[k][lane].x; tot.y += se_part[k][lane].y; }
+      for (int k = 0; k < NW; ++k) { tot.x += se_part[k][lane].x; tot.y += se_part[k][lane].y; }
       atomicAdd(se_sums + (long long)n * P.C + ch, tot.x);
       atomicAdd(se_sums + (long long)n * P.C + ch + 1, tot.y);
     }
@@ -197,8 +197,9 @@ int dwconv3d_lane_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
   // patch shape: 4x4 unless the plane is a multiple of 7 wide but not of 4 (14x14, 7x7 planes): 2x7
   const bool p27 = (d->Wo % 4 != 0) && (d->Wo % 7 == 0);
   const int PH = p27 ? 2 : 4, PW = p27 ? 7 : 4;
-  // ---- output box: maximise useful outputs per halo byte under a budget that keeps 2 CTAs per SM
-  const int budget = 100 * 1024;
+  static const int nw = [] { const char* e = getenv("PVB200_DW_WARPS"); return (e && e[0] == '8') ? 8 : 4; }();
+  // ---- output box: maximise useful outputs per halo byte under a budget that keeps 16 / nw CTAs per SM
+  const int budget = (nw == 8 ? 100 : 50) * 1024;
   double best = -1;
   for (int bw = PW; bw <= 56; bw += PW) {
     if (bw - PW >= d->Wo) break;
@@ -211,13 +212,13 @@ int dwconv3d_lane_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
         const long long halo = (long long)tt * hh * ww * P.cc * 2;
         if (halo > budget) continue;
         const int patches = bt * (bh / PH) * (bw / PW);
-        const double warp_eff = (double)patches / (double)(((patches + DWL_WARPS - 1) / DWL_WARPS) * DWL_WARPS);
+        const double warp_eff = (double)patches / (double)(((patches + nw - 1) / nw) * nw);
         const double cov_w = (double)d->Wo / (((d->Wo + bw - 1) / bw) * bw);
         const double cov_h = (double)d->Ho / (((d->Ho + bh - 1) / bh) * bh);
         const double cov_t = (double)d->To / (((d->To + bt - 1) / bt) * bt);
         const double reuse = (double)(bt * bh * bw) / (double)(tt * hh * ww);
         // compute efficiency dominates (FMA-bound); halo reuse breaks ties towards less L2 traffic
-        const double score = warp_eff * cov_w * cov_h * cov_t * (0.75 + 0.25 * reuse) * (patches >= 2 * DWL_WARPS ? 1.0 : 0.9);
+        const double score = warp_eff * cov_w * cov_h * cov_t * (0.75 + 0.25 * reuse) * (patches >= 2 * nw ? 1.0 : 0.9);
         if (score > best) { best = score; P.bt = bt; P.bh = bh; P.bw = bw; P.tt = tt; P.hh = hh; P.ww = ww; }
       }
     }
@@ -239,25 +240,25 @@ int dwconv3d_lane_launch(const pv_conv3d_desc* d, const void* x, const void* w, 
     if (cr != CUDA_SUCCESS) return PV_ERR_UNSUPPORTED;
   }
   const size_t smem = (size_t)P.tt * P.hh * P.ww * P.cc * 2 + 256;
-  dim3 grid((unsigned)tiles, (unsigned)chunks), block(DWL_WARPS * 32);
+  dim3 grid((unsigned)tiles, (unsigned)chunks), block(nw * 32);
   static const bool x2 = [] { const char* e = getenv("PVB200_DW_X2"); return !(e && e[0] == '0'); }();
+#define PV_DWL2(S_, PH_, PW_, X2_, NW_)                                                                       \
+  do {                                                                                                        \
+    PV_OPT_IN_SMEM((dwconv3d_lane_kernel<S_, PH_, PW_, X2_, NW_>), 110 * 1024);                               \
+    dwconv3d_lane_kernel<S_, PH_, PW_, X2_, NW_><<<grid, block, smem, stream>>>(P, (const __half*)w, scale,   \
+                                                                               bias, (__half*)y, se_sums);    \
+  } while (0)
 #define PV_DWL(S_, PH_, PW_)                                                                                  \
   do {                                                                                                        \
-    if (x2) {                                                                                                 \
-      PV_OPT_IN_SMEM((dwconv3d_lane_kernel<S_, PH_, PW_, true>), 110 * 1024);                                 \
-      dwconv3d_lane_kernel<S_, PH_, PW_, true><<<grid, block, smem, stream>>>(P, (const __half*)w, scale,     \
-                                                                             bias, (__half*)y, se_sums);      \
-    } else {                                                                                                  \
-      PV_OPT_IN_SMEM((dwconv3d_lane_kernel<S_, PH_, PW_, false>), 110 * 1024);                                \
-      dwconv3d_lane_kernel<S_, PH_, PW_, false><<<grid, block, smem, stream>>>(P, (const __half*)w, scale,    \
-                                                                              bias, (__half*)y, se_sums);     \
-    }                                                                                                         \
+    if (nw == 8) { if (x2) PV_DWL2(S_, PH_, PW_, true, 8); else PV_DWL2(S_, PH_, PW_, false, 8); }            \
+    else { if (x2) PV_DWL2(S_, PH_, PW_, true, 4); else PV_DWL2(S_, PH_, PW_, false, 4); }                    \
   } while (0)
   if (S == 1 && !p27) PV_DWL(1, 4, 4);
   else if (S == 1) PV_DWL(1, 2, 7);
   else if (!p27) PV_DWL(2, 4, 4);
   else PV_DWL(2, 2, 7);
 #undef PV_DWL
+#undef PV_DWL2
   PV_LAUNCH_OK("dwconv3d_lane_kernel");
   return PV_OK;
 }

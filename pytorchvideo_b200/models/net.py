@@ -15,6 +15,16 @@ class Net(B200Module):
         self.blocks = blocks
         init_net_weights(self)
 
+    def forward(self, x, *extra):
+        # A Net whose blocks were replaced one by one by the accelerator protocol (transmute_model(model, "b200"))
+        # runs them in sequence like the reference's Net.forward (net.py:41-44); each converted block owns its plan and
+        # hands an NCDHW tensor to the next.  An untouched Net compiles into ONE plan (no layout round trips).
+        if any(type(b).__name__ == "B200Block" for b in self.blocks):
+            for b in self.blocks:
+                x = b(x)
+            return x
+        return super().forward(x, *extra)
+
 
 class MultiPathWayWithFuse(B200Module):
     """Per-pathway blocks followed by an optional cross-pathway fusion (net.py:66-122).
