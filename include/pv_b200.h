@@ -277,6 +277,15 @@ int pv_scale_act(const void* x, void* y, int dtype, long long x_row_stride,
                  long long y_row_stride, int N, long long npos, int C, const float* gate,
                  int act, void* stream);
 
+/* RoIAlign for the detection heads (pytorchvideo/models/head.py:441-482 ResNetRoIHead.forward: pool -> squeeze T ->
+ * roi_layer(x, bboxes) -> pool_spatial ...; roi_layer = torchvision.ops.RoIAlign(output_size, spatial_scale,
+ * sampling_ratio), aligned=False, head.py:209-227).  x: NDHWC features with T == 1 ([N][H][W][C], rows of
+ * x_row_stride elements, C % 8 == 0); rois: DEVICE fp32 [K][5] = (batch index, x1, y1, x2, y2) in input pixels;
+ * y: [K][pooled_h][pooled_w][C].  Sampling grid, bilinear weights and boundary rules are torchvision's.          */
+int pv_roi_align_fwd(const void* x, int dtype, long long x_row_stride, int N, int H, int W, int C,
+                     const float* rois, int K, int pooled_h, int pooled_w, float spatial_scale,
+                     int sampling_ratio, void* y, long long y_row_stride, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Head tail (models/head.py:371-391): optional softmax over channels per position
  * (activation applied BEFORE the global average, head.py:383-390), then mean over positions,

@@ -218,12 +218,51 @@ def gen_layers():
     torch.save(out, os.path.join(GOLD, "layers.pt"))
 
 
+def gen_detection():
+    """Detection goldens: the reference's slow_r50_detection / slowfast_r50_detection (trunk +
+    ResNetRoIHead with torchvision.ops.RoIAlign) on small clips, and torchvision.ops.roi_align itself on an op-level
+    case.  Pins oracle/interp.py (roi_align_ref, f_ResNetRoIHead, f_DetectionBBoxNetwork) bit-for-bit."""
+    import torchvision
+    import pytorchvideo.models.hub as RH
+    import pytorchvideo_b200.models.hub as PH
+    from pytorchvideo_b200 import testing as TS
+    from oracle.interp import oracle_forward, roi_align_ref
+    out = {"torchvision": torchvision.__version__}
+    x, boxes, settings = TS.roi_align_case()
+    ra = []
+    for osz, scale, sr in settings:
+        ref = torchvision.ops.roi_align(x, boxes, osz, scale, sr, False)
+        assert torch.equal(ref, roi_align_ref(x, boxes, osz, scale, sr)), "roi_align_ref != torchvision (%s)" % (osz,)
+        ra.append(ref.clone())
+    out["roi_align"] = {"outputs": ra, "input_checksum": TS.tensor_checksum(x), "boxes": boxes.clone()}
+    print("roi_align op case ok (%d settings)" % len(settings), flush=True)
+    for case, (hub, kw, B, T, H, W, is_sf, K) in TS.DETECTION_CASES.items():
+        t0 = time.time()
+        mine, inp, bx, _ = TS.build_detection_case(case, PH)
+        ref = getattr(RH, hub)(pretrained=False, **kw)
+        ref.load_state_dict(mine.state_dict(), strict=True)
+        ref.eval()
+        assert repr(ref.detection_head.roi_layer) == repr(mine.detection_head.roi_layer)
+        with torch.no_grad():
+            y_ref = ref(list(inp) if is_sf else inp, bx)
+            y_orc_ref = oracle_forward(ref, list(inp) if is_sf else inp, bx)
+            y_orc_mine = oracle_forward(mine, list(inp) if is_sf else inp, bx)
+        assert torch.equal(y_ref, y_orc_ref), "oracle != reference on reference modules (%s)" % case
+        assert torch.equal(y_ref, y_orc_mine), "oracle != reference on product tree (%s)" % case
+        out[case] = {"output": y_ref.clone(), "boxes": bx.clone(), "state_checksum": TS.state_checksum(mine),
+                     "weight_seed": 1234, "input_seed": 42}
+        print("%-24s ok  out %s  range [%.4f, %.4f]  (%.1fs)" % (case, tuple(y_ref.shape), float(y_ref.min()),
+                                                                  float(y_ref.max()), time.time() - t0), flush=True)
+    torch.save(out, os.path.join(GOLD, "detection.pt"))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--skip-models", action="store_true")
     ap.add_argument("--skip-transforms", action="store_true")
     ap.add_argument("--skip-layers", action="store_true")
+    ap.add_argument("--skip-detection", action="store_true")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -231,5 +270,7 @@ if __name__ == "__main__":
         gen_transforms()
     if not a.skip_layers and not a.only:
         gen_layers()
+    if not a.skip_detection and not a.only:
+        gen_detection()
     if not a.skip_models:
         gen_models(a.only)

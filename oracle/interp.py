@@ -53,6 +53,62 @@ def _leaf(m, x):
     return None
 
 
+def roi_align_ref(x, rois, output_size, spatial_scale, sampling_ratio):
+    """torchvision.ops.roi_align(aligned=False) restated (torchvision/csrc/ops/cpu/roi_align_kernel.cpp +
+    roi_align_common.h pre_calc_for_bilinear_interpolate); the reference's RoI head calls it through
+    torchvision.ops.RoIAlign (models/head.py:209-227, 470).  fp32 scalar arithmetic in the C++ order (numpy float32),
+    tensor arithmetic over the channel dim in torch.  x: [N, C, H, W]; rois: [K, 5]; returns [K, C, ph, pw]."""
+    import numpy as np
+    f = np.float32
+    N, C, H, W = x.shape
+    ph_n, pw_n = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+    K = rois.shape[0]
+    out = torch.zeros((K, C, ph_n, pw_n), dtype=torch.float32)
+    r = rois.detach().float().cpu().numpy().astype(np.float32)
+    scale = f(spatial_scale)
+    for k in range(K):
+        n = int(r[k, 0])
+        roi_start_w, roi_start_h = r[k, 1] * scale, r[k, 2] * scale
+        roi_end_w, roi_end_h = r[k, 3] * scale, r[k, 4] * scale
+        roi_w = max(roi_end_w - roi_start_w, f(1.0))
+        roi_h = max(roi_end_h - roi_start_h, f(1.0))
+        bin_h, bin_w = roi_h / f(ph_n), roi_w / f(pw_n)
+        grid_h = sampling_ratio if sampling_ratio > 0 else int(np.ceil(roi_h / f(ph_n)))
+        grid_w = sampling_ratio if sampling_ratio > 0 else int(np.ceil(roi_w / f(pw_n)))
+        count = f(max(grid_h * grid_w, 1))
+        feat = x[n]
+        for ph in range(ph_n):
+            for pw in range(pw_n):
+                acc = torch.zeros(C, dtype=torch.float32)
+                for iy in range(grid_h):
+                    yy = roi_start_h + f(ph) * bin_h + f(iy + 0.5) * bin_h / f(grid_h)
+                    for ix in range(grid_w):
+                        xx = roi_start_w + f(pw) * bin_w + f(ix + 0.5) * bin_w / f(grid_w)
+                        y_, x_ = yy, xx
+                        if y_ < -1.0 or y_ > H or x_ < -1.0 or x_ > W:
+                            continue                                   # all four weights are 0
+                        y_ = max(y_, f(0.0))
+                        x_ = max(x_, f(0.0))
+                        y_low, x_low = int(y_), int(x_)
+                        if y_low >= H - 1:
+                            y_high = y_low = H - 1
+                            y_ = f(y_low)
+                        else:
+                            y_high = y_low + 1
+                        if x_low >= W - 1:
+                            x_high = x_low = W - 1
+                            x_ = f(x_low)
+                        else:
+                            x_high = x_low + 1
+                        ly, lx = y_ - f(y_low), x_ - f(x_low)
+                        hy, hx = f(1.0) - ly, f(1.0) - lx
+                        w1, w2, w3, w4 = hy * hx, hy * lx, ly * hx, ly * lx
+                        acc = acc + (float(w1) * feat[:, y_low, x_low] + float(w2) * feat[:, y_low, x_high]
+                                     + float(w3) * feat[:, y_high, x_low] + float(w4) * feat[:, y_high, x_high])
+                out[k, :, ph, pw] = acc / float(count)
+    return out
+
+
 class Oracle:
     def __call__(self, m, x):
         return self.run(m, x)
@@ -175,6 +231,37 @@ class Oracle:
             x = x.view(x.shape[0], -1)
         return x
 
+    def f_ResNetRoIHead(self, m, x, bboxes):     # models/head.py:441-482
+        x = self.run(m.pool, x)
+        if m.roi_layer is not None:
+            if x.shape[-3] != 1:
+                raise Exception("Temporal dimension should be 1. Consider modifying the pool layer.")
+            x = torch.squeeze(x, -3)
+            r = m.roi_layer                      # torchvision.ops.RoIAlign(output_size, spatial_scale, sampling_ratio)
+            assert not getattr(r, "aligned", False)
+            x = roi_align_ref(x, bboxes, r.output_size, r.spatial_scale, r.sampling_ratio)
+            if m.pool_spatial is not None:
+                ps = m.pool_spatial
+                if type(ps).__name__ == "MaxPool2d":
+                    x = F.max_pool2d(x, ps.kernel_size, ps.stride, ps.padding, ps.dilation, ps.ceil_mode)
+                else:
+                    x = F.avg_pool2d(x, ps.kernel_size, ps.stride, ps.padding, ps.ceil_mode, ps.count_include_pad)
+            x = x.unsqueeze(-3)
+        x = self.run(m.dropout, x)
+        x = x.permute((0, 2, 3, 4, 1))
+        x = self.run(m.proj, x)
+        x = x.permute((0, 4, 1, 2, 3))
+        x = self.run(m.activation, x)
+        if m.output_pool is not None:
+            x = self.run(m.output_pool, x)
+            x = x.view(x.shape[0], -1)
+        return x
+
+    def f_DetectionBBoxNetwork(self, m, x, bboxes):   # models/net.py:62-74
+        features = self.run(m.model, x)
+        out = self.f_ResNetRoIHead(m.detection_head, features, bboxes)
+        return out.view(out.shape[0], -1)
+
     # ---- MViT ----------------------------------------------------------------------------
     def f_PatchEmbed(self, m, x):                # models/stem.py:289-292
         x = self.run(m.patch_model, x)
@@ -293,6 +380,8 @@ def oracle_forward(model, x, *extra):
             x = [t.detach().float().cpu() for t in x]
         else:
             x = x.detach().float().cpu()
+        if extra and type(model).__name__ in ("DetectionBBoxNetwork", "ResNetRoIHead"):
+            return getattr(Oracle(), "f_" + type(model).__name__)(model, x, extra[0].detach().float().cpu())
         if extra:
             fn = getattr(Oracle(), "f_" + type(model).__name__)
             y, thw = fn(model, x, list(extra[0]))

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpvb200.so")
-SOURCES = ["pv_api.cu", "pv_transform.cu", "pv_simt.cu", "pv_igemm.cu", "pv_igemm_gather.cu", "pv_dwconv.cu", "pv_dwlane.cu", "pv_fastblock.cu", "pv_stem.cu", "pv_attention.cu", "pv_attention_mma.cu", "pv_attention_tc.cu"]
+SOURCES = ["pv_api.cu", "pv_transform.cu", "pv_roi.cu", "pv_simt.cu", "pv_igemm.cu", "pv_igemm_gather.cu", "pv_dwconv.cu", "pv_dwlane.cu", "pv_fastblock.cu", "pv_stem.cu", "pv_attention.cu", "pv_attention_mma.cu", "pv_attention_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",

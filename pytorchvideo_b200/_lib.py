@@ -112,6 +112,8 @@ SIGNATURES = {
                                C.c_int, c_vp]),
     "pv_head_reduce": (C.c_int, [c_vp, C.c_int, c_ll, C.c_int, c_ll, C.c_int, C.c_int, c_vp,
                                  c_vp]),
+    "pv_roi_align_fwd": (C.c_int, [c_vp, C.c_int, c_ll, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int,
+                                   C.c_int, C.c_float, C.c_int, c_vp, c_ll, c_vp]),
     "pv_layernorm": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_ll, c_ll, c_vp, c_vp,
                                C.c_float, c_vp]),
     "pv_copy_rows": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, c_ll, c_ll, c_vp]),

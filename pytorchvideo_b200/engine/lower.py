@@ -303,6 +303,60 @@ class Lowering:
         x = self.pool(x, m.pool, name + ".pool")
         return self.conv(x, m.post_conv, m.post_norm, m.post_act, None, name + ".post_conv")
 
+    def lower_DetectionBBoxNetwork(self, m, x, name):
+        # models/net.py:62-74: features = model(x); out = detection_head(features, bboxes); out.view(K, -1)
+        feats = self.lower(m.model, x[0] if len(x) == 2 else list(x[:-1]), (name + "." if name else "") + "model")
+        return self.lower_ResNetRoIHead(m.detection_head, [feats, x[-1]], (name + "." if name else "") + "detection_head")
+
+    def lower_ResNetRoIHead(self, m, x, name):
+        # models/head.py:441-482
+        if len(x) != 2:
+            raise RuntimeError("ResNetRoIHead.forward(x, bboxes) takes one feature tensor and the boxes")
+        x, boxes = x
+        if isinstance(x, list):
+            raise RuntimeError("ResNetRoIHead expects ONE feature tensor (PoolConcatPathway(retain_list=False))")
+        name = name or "head"
+        if getattr(m, "pool", None) is not None:
+            x = self.pool(x, m.pool, name + ".pool")
+        roi = getattr(m, "roi_layer", None)
+        if roi is not None:
+            if type(roi).__name__ != "RoIAlign":
+                raise NotImplementedError("roi layer %s unsupported (RoIAlign only)" % type(roi).__name__)
+            if getattr(roi, "aligned", False):
+                raise NotImplementedError("RoIAlign(aligned=True) unsupported")
+            osz = roi.output_size
+            osz = (osz, osz) if isinstance(osz, int) else tuple(osz)
+            x = self.p.emit_roi_align(x, boxes, osz, roi.spatial_scale, roi.sampling_ratio, name + ".roi_layer")
+            ps = getattr(m, "pool_spatial", None)
+            if ps is not None:
+                pn = type(ps).__name__
+                if pn not in ("MaxPool2d", "AvgPool2d"):
+                    raise NotImplementedError("pool_spatial %s unsupported" % pn)
+                k2 = ps.kernel_size if isinstance(ps.kernel_size, (tuple, list)) else (ps.kernel_size,) * 2
+                s2 = ps.stride if isinstance(ps.stride, (tuple, list)) else (ps.stride,) * 2
+                p2 = ps.padding if isinstance(ps.padding, (tuple, list)) else (ps.padding,) * 2
+                if pn == "MaxPool2d" and (ps.dilation not in (1, (1, 1)) or ps.ceil_mode):
+                    raise NotImplementedError("MaxPool2d dilation/ceil_mode unsupported")
+                if pn == "AvgPool2d" and (ps.ceil_mode or not ps.count_include_pad or ps.divisor_override is not None):
+                    raise NotImplementedError("AvgPool2d options unsupported")
+                x = self.p.emit_pool(x, L.POOL_MAX if pn == "MaxPool2d" else L.POOL_AVG, (1,) + tuple(k2), (1,) + tuple(s2),
+                                     (0,) + tuple(p2), name + ".pool_spatial")
+        proj = m.proj
+        if not isinstance(proj, nn.Linear):
+            raise NotImplementedError("head proj %s unsupported" % type(proj).__name__)
+        act = getattr(m, "activation", None)
+        an = None if act is None else type(act).__name__
+        if an not in (None, "Sigmoid", "ReLU", "Identity"):
+            raise NotImplementedError("RoI head activation %s unsupported" % an)
+        w = proj.weight.reshape(proj.out_features, proj.in_features, 1, 1, 1)
+        x = self.p.emit_conv(x, w, proj.bias, None, (1, 1, 1), (0, 0, 0), (1, 1, 1), 1,
+                             L.ACT_RELU if an == "ReLU" else L.ACT_NONE, None, name + ".proj")
+        if an == "Sigmoid":
+            x = self.p.emit_act(x, L.ACT_SIGMOID, name + ".activation")
+        if getattr(m, "output_pool", None) is not None:
+            return self.p.emit_head_reduce(x, False, name + ".output_pool")       # AdaptiveAvgPool3d(1) + view(K, -1)
+        return self.p.emit_to_ncdhw(x, name + ".to_ncdhw")
+
     def lower_ResNetBasicHead(self, m, x, name):
         # models/head.py:371-391
         pool = getattr(m, "pool", None)
@@ -343,8 +397,9 @@ class CompiledModel:
         L.require_device()
         multi = isinstance(example_inputs, (list, tuple))
         ins = list(example_inputs) if multi else [example_inputs]
-        for t in ins:
-            if t.dim() not in (2, 3, 5):
+        raw = _raw_inputs(model, ins)
+        for i, t in enumerate(ins):
+            if i not in raw and t.dim() not in (2, 3, 5):
                 raise RuntimeError("expected a 5-D (B, C, T, H, W) clip or a (B, N, C) token tensor, got %s" % (tuple(t.shape),))
         device = ins[0].device
         if device.type != "cuda":
@@ -352,10 +407,10 @@ class CompiledModel:
         dt = {"f16": L.PV_F16, "f32": L.PV_F32}[dtype]
         self.multi = multi
         self.plan = Plan(device, dt, use_tcgen05)
-        self.static_in = [torch.empty(t.shape, dtype=t.dtype if t.dtype in (torch.float16, torch.float32) else torch.float32,
-                                      device=device) for t in ins]
+        self.static_in = [torch.empty(t.shape, dtype=t.dtype if (t.dtype in (torch.float16, torch.float32) and i not in raw)
+                                      else torch.float32, device=device) for i, t in enumerate(ins)]
         low = Lowering(self.plan, extra)
-        xs = [_emit_input(self.plan, s) for s in self.static_in]
+        xs = [self.plan.raw_input(s) if i in raw else _emit_input(self.plan, s) for i, s in enumerate(self.static_in)]
         out = low.lower(model, xs if multi else xs[0], "")
         out = _emit_output(self.plan, out, tokens=ins[0].dim() != 5)
         self.out_buf, self.out_shape = out
@@ -418,6 +473,18 @@ class CompiledModel:
         return self.output_view()
 
 
+def _raw_inputs(model, ins):
+    """Indices of inputs that are not clips / tokens: the trailing [K, 5] box tensor of the detection modules
+    (DetectionBBoxNetwork.forward(x, bboxes), ResNetRoIHead.forward(x, bboxes))."""
+    if type(model).__name__ in ("DetectionBBoxNetwork", "ResNetRoIHead"):
+        b = ins[-1]
+        if len(ins) < 2 or b.dim() != 2 or b.shape[1] != 5 or b.shape[0] < 1:
+            raise RuntimeError("bboxes must be a [K, 5] tensor (batch index, x1, y1, x2, y2) with K >= 1; "
+                               "RoIAlignRotated ([K, 6]) is unsupported")
+        return {len(ins) - 1}
+    return set()
+
+
 def _emit_input(plan, t):
     if t.dim() == 5:
         return plan.emit_input_ncdhw(t, t.shape[1], 4 if t.shape[1] <= 4 else (t.shape[1] + 7) // 8 * 8)
@@ -445,7 +512,9 @@ def lower_only(model, example_inputs, dtype="f16", use_tcgen05=True, extra=()):
     multi = isinstance(example_inputs, (list, tuple))
     ins = list(example_inputs) if multi else [example_inputs]
     plan = Plan("cpu", {"f16": L.PV_F16, "f32": L.PV_F32}[dtype], use_tcgen05)
-    xs = [_emit_input(plan, torch.empty(t.shape, dtype=torch.float32)) for t in ins]
+    raw = _raw_inputs(model, ins)
+    xs = [plan.raw_input(torch.empty(t.shape, dtype=torch.float32)) if i in raw
+          else _emit_input(plan, torch.empty(t.shape, dtype=torch.float32)) for i, t in enumerate(ins)]
     low = Lowering(plan, extra)
     out = low.lower(model, xs if multi else xs[0], "")
     out = _emit_output(plan, out, tokens=ins[0].dim() != 5)

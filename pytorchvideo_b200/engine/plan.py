@@ -26,6 +26,13 @@ class Buf:
         self.tensor = None
 
 
+class RawIn:
+    """Plan input passed through untouched (see Plan.raw_input)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+
 class TRef:
     def __init__(self, buf, N, T, H, W, C, Cp=None, ch_off=0, row_stride=None):
         self.buf = buf
@@ -536,6 +543,30 @@ class Plan:
         self.add(name + ".gate", fn_gate)
         self.add(name + ".apply", fn_apply)
         return x
+
+    def raw_input(self, static_in):
+        """A plan input that is used as it is (fp32 device tensor, no layout / dtype conversion): the [K, 5] bounding
+        boxes of the detection heads.  The handle carries the static tensor; ops read its data pointer at run time."""
+        return RawIn(static_in)
+
+    def emit_roi_align(self, x, rois, output_size, spatial_scale, sampling_ratio, name="roi_align"):
+        """torchvision RoIAlign (aligned=False) on a T == 1 feature map (models/head.py:462-471): [N,1,H,W,C] x
+        [K,5] -> [K,1,R_h,R_w,C]."""
+        if x.T != 1:
+            raise RuntimeError("Temporal dimension should be 1. Consider modifying the pool layer.")   # head.py:464-467
+        self.materialize_input(x)
+        K = int(rois.tensor.shape[0])
+        rh, rw = int(output_size[0]), int(output_size[1])
+        y = self.new_tensor(K, 1, rh, rw, x.C, Cp=x.Cp)
+        lib = self.lib
+        N, H, W, Cp = x.N, x.H, x.W, x.Cp
+
+        def fn(stream):
+            L.check(lib.pv_roi_align_fwd(x.ptr(), x.dt, x.row_stride, N, H, W, Cp, rois.tensor.data_ptr(), K, rh, rw,
+                                         float(spatial_scale), int(sampling_ratio), y.ptr(), y.row_stride, stream),
+                    "pv_roi_align_fwd(%s)" % name)
+        self.add(name, fn, reads=(x,), writes=(y,))
+        return y
 
     def emit_act(self, x, act, name="act"):
         lib = self.lib

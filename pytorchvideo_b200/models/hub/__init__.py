@@ -5,8 +5,8 @@ import torch.nn as nn
 
 from ..csn import create_csn
 from ..r2plus1d import create_r2plus1d
-from ..resnet import create_resnet
-from ..slowfast import create_slowfast
+from ..resnet import create_resnet, create_resnet_with_roi_head
+from ..slowfast import create_slowfast, create_slowfast_with_roi_head
 from ..x3d import create_x3d
 
 
@@ -19,6 +19,11 @@ def _build(builder, pretrained, **kwargs):
 def slow_r50(pretrained=False, progress=True, **kw):
     return _build(create_resnet, pretrained, stem_conv_kernel_size=(1, 7, 7), head_pool_kernel_size=(8, 7, 7),
                   model_depth=50, **kw)
+
+
+def slow_r50_detection(pretrained=False, progress=True, **kw):
+    """Slow-R50 4x16 detection model (AVA), reference hub/resnet.py:73-90."""
+    return _build(create_resnet_with_roi_head, pretrained, **kw)
 
 
 def c2d_r50(pretrained=False, progress=True, **kw):
@@ -34,6 +39,11 @@ def i3d_r50(pretrained=False, progress=True, **kw):
 
 def slowfast_r50(pretrained=False, progress=True, **kw):
     return _build(create_slowfast, pretrained, model_depth=50, slowfast_fusion_conv_kernel_size=(7, 1, 1), **kw)
+
+
+def slowfast_r50_detection(pretrained=False, progress=True, **kw):
+    """SlowFast-R50 8x8 detection model (AVA), reference hub/slowfast.py:150-181."""
+    return _build(create_slowfast_with_roi_head, pretrained, **kw)
 
 
 def slowfast_r101(pretrained=False, progress=True, **kw):

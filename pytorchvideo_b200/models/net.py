@@ -26,6 +26,22 @@ class Net(B200Module):
         return super().forward(x, *extra)
 
 
+class DetectionBBoxNetwork(B200Module):
+    """A trunk followed by a head that also takes bounding boxes (reference net.py:47-74):
+    ``forward(x, bboxes)`` -> ``[K, num_classes]`` for bboxes [K, 5] = (batch index, x1, y1, x2, y2).
+    Trunk, RoIAlign and head compile into ONE plan per (clip shapes, K)."""
+
+    def __init__(self, model, detection_head):
+        super().__init__()
+        self.model = model
+        self.detection_head = detection_head
+
+    def forward(self, x, bboxes):
+        ins = (list(x) if isinstance(x, (list, tuple)) else [x]) + [bboxes]
+        out = self._pv_compiled(ins)(ins).clone()
+        return out.view(out.shape[0], -1)
+
+
 class MultiPathWayWithFuse(B200Module):
     """Per-pathway blocks followed by an optional cross-pathway fusion (net.py:66-122).
 

@@ -186,3 +186,42 @@ def create_resnet(*, input_channel=3, model_depth=50, model_num_class=400, dropo
                            dropout_rate=dropout_rate, activation=head_activation,
                            output_with_global_average=head_output_with_global_average))
     return Net(blocks=nn.ModuleList(blocks))
+
+
+def create_resnet_with_roi_head(*, input_channel=3, model_depth=50, model_num_class=80, dropout_rate=0.5,
+                                norm=nn.BatchNorm3d, activation=nn.ReLU, stem_dim_out=64,
+                                stem_conv_kernel_size=(1, 7, 7), stem_conv_stride=(1, 2, 2), stem_pool=nn.MaxPool3d,
+                                stem_pool_kernel_size=(1, 3, 3), stem_pool_stride=(1, 2, 2),
+                                stem=create_res_basic_stem, stage1_pool=None, stage1_pool_kernel_size=(2, 1, 1),
+                                stage_conv_a_kernel_size=((1, 1, 1), (1, 1, 1), (3, 1, 1), (3, 1, 1)),
+                                stage_conv_b_kernel_size=((1, 3, 3), (1, 3, 3), (1, 3, 3), (1, 3, 3)),
+                                stage_conv_b_num_groups=(1, 1, 1, 1),
+                                stage_conv_b_dilation=((1, 1, 1), (1, 1, 1), (1, 1, 1), (1, 2, 2)),
+                                stage_spatial_h_stride=(1, 2, 2, 1), stage_spatial_w_stride=(1, 2, 2, 1),
+                                stage_temporal_stride=(1, 1, 1, 1), bottleneck=create_bottleneck_block,
+                                head=None, head_pool=nn.AvgPool3d, head_pool_kernel_size=(4, 1, 1),
+                                head_output_size=(1, 1, 1), head_activation=nn.Sigmoid,
+                                head_output_with_global_average=False, head_spatial_resolution=(7, 7),
+                                head_spatial_scale=1.0 / 16.0, head_sampling_ratio=0):
+    """Slow-only detection network: ResNet trunk without head + RoI head (reference resnet.py:844-1017)."""
+    from .head import create_res_roi_pooling_head
+    from .net import DetectionBBoxNetwork
+    if head is None:
+        head = create_res_roi_pooling_head
+    model = create_resnet(
+        input_channel=input_channel, model_depth=model_depth, model_num_class=model_num_class,
+        dropout_rate=dropout_rate, norm=norm, activation=activation, stem_dim_out=stem_dim_out,
+        stem_conv_kernel_size=stem_conv_kernel_size, stem_conv_stride=stem_conv_stride, stem_pool=stem_pool,
+        stem_pool_kernel_size=stem_pool_kernel_size, stem_pool_stride=stem_pool_stride, stem=stem,
+        stage1_pool=stage1_pool, stage1_pool_kernel_size=stage1_pool_kernel_size,
+        stage_conv_a_kernel_size=stage_conv_a_kernel_size, stage_conv_b_kernel_size=stage_conv_b_kernel_size,
+        stage_conv_b_num_groups=stage_conv_b_num_groups, stage_conv_b_dilation=stage_conv_b_dilation,
+        stage_spatial_h_stride=stage_spatial_h_stride, stage_spatial_w_stride=stage_spatial_w_stride,
+        stage_temporal_stride=stage_temporal_stride, bottleneck=bottleneck, head=None)
+    det_head = head(
+        in_features=stem_dim_out * 2 ** (len(_MODEL_STAGE_DEPTH[model_depth]) + 1), out_features=model_num_class,
+        pool=head_pool, output_size=head_output_size, pool_kernel_size=head_pool_kernel_size,
+        dropout_rate=dropout_rate, activation=head_activation,
+        output_with_global_average=head_output_with_global_average, resolution=head_spatial_resolution,
+        spatial_scale=head_spatial_scale, sampling_ratio=head_sampling_ratio)
+    return DetectionBBoxNetwork(model, det_head)

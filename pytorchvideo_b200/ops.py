@@ -60,6 +60,23 @@ def pool3d(x, mode, kernel, stride, padding, dtype="f16"):
     return out.tensor[: int(torch.tensor(shape).prod())].view(*shape).clone()
 
 
+def roi_align(x, boxes, output_size, spatial_scale, sampling_ratio=0, dtype="f16"):
+    """torchvision-style RoIAlign (aligned=False) of a [N, C, H, W] CUDA feature map for [K, 5] boxes
+    (batch index, x1, y1, x2, y2) -> [K, C, ph, pw] fp32 (pv_roi_align_fwd)."""
+    _require_cuda(x)
+    plan = Plan(x.device, _DT[dtype])
+    x5 = x.contiguous().float().unsqueeze(2)
+    xr = plan.emit_input_ncdhw(x5, x5.shape[1], (x5.shape[1] + 7) // 8 * 8)
+    rois = plan.raw_input(boxes.to(x.device).float().contiguous())
+    osz = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+    y = plan.emit_roi_align(xr, rois, osz, spatial_scale, sampling_ratio)
+    out, shape = plan.emit_to_ncdhw(y)
+    plan.finalize()
+    plan.run(_stream(x.device))
+    torch.cuda.synchronize(x.device)
+    return out.tensor[: int(torch.tensor(shape).prod())].view(*shape).squeeze(2).clone()
+
+
 def layernorm(x, gamma, beta, eps=1e-6, dtype="f16"):
     """LayerNorm over the last dim of a [rows, C] CUDA tensor (C % 8 == 0)."""
     _require_cuda(x)

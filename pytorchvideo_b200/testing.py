@@ -202,3 +202,48 @@ def build_layer_case(name, seed=77):
     g.manual_seed(seed + 1)
     x = f16_exact(torch.randn(shape, generator=g) if len(shape) == 3 else torch.rand(shape, generator=g))
     return m, x, thw
+
+
+# ---- detection cases (tests/golden/detection.pt): trunk + RoIAlign head, weights / clips on the f16 grid ----------
+DETECTION_CASES = {
+    # name: (hub builder, kwargs, batch, T, H, W, is_slowfast, number of boxes)
+    # head_activation=None: compare LOGITS (with random weights the default Sigmoid saturates to 0 / 1 and hides errors)
+    "slow_r50_detection": ("slow_r50_detection", {"head_activation": None}, 2, 4, 128, 128, False, 6),
+    "slowfast_r50_detection": ("slowfast_r50_detection", {"head_activation": None}, 2, 32, 128, 128, True, 5),
+    "slow_r50_detection_sigmoid": ("slow_r50_detection", {}, 1, 4, 96, 96, False, 4),      # the hub default head
+}
+
+
+def synthetic_boxes(n_boxes, batch, H, W, seed=9):
+    """[K, 5] fp32 (batch index, x1, y1, x2, y2) in input pixels: random boxes plus the shapes the RoIAlign boundary
+    rules care about - one reaching outside the frame, one smaller than a feature cell, the whole frame."""
+    g = torch.Generator().manual_seed(seed)
+    b = torch.randint(0, batch, (n_boxes,), generator=g).float()
+    x1 = torch.rand(n_boxes, generator=g) * W * 0.6
+    y1 = torch.rand(n_boxes, generator=g) * H * 0.6
+    x2 = x1 + 8 + torch.rand(n_boxes, generator=g) * W * 0.5
+    y2 = y1 + 8 + torch.rand(n_boxes, generator=g) * H * 0.5
+    boxes = torch.stack([b, x1, y1, x2, y2], 1)
+    if n_boxes >= 3:
+        boxes[0, 1:] = torch.tensor([-20.0, -12.0, W + 30.0, H * 0.5])      # sticks out left / top / right
+        boxes[1, 1:] = torch.tensor([W * 0.5, H * 0.5, W * 0.5 + 3.0, H * 0.5 + 2.0])   # sub-cell box -> size clamp 1
+        boxes[2, 1:] = torch.tensor([0.0, 0.0, float(W), float(H)])
+    return boxes.contiguous()
+
+
+def build_detection_case(case, hub_module, weight_seed=1234, input_seed=42):
+    """(model, clip inputs, boxes, is_slowfast) of a DETECTION_CASES entry."""
+    hub, kw, B, T, H, W, is_sf, K = DETECTION_CASES[case]
+    model = randomize_model(getattr(hub_module, hub)(**kw), seed=weight_seed, f16_weights=True).eval()
+    clip = synthetic_clip(B, T, H, W, seed=input_seed, f16_values=True)
+    return model, (slowfast_inputs(clip) if is_sf else clip), synthetic_boxes(K, B, H, W), is_sf
+
+
+def roi_align_case(seed=5):
+    """Op-level RoIAlign case: feature map on the f16 grid + boxes (see synthetic_boxes), several (output size, scale,
+    sampling ratio) settings.  Golden = torchvision.ops.roi_align (tests/golden/detection.pt["roi_align"])."""
+    g = torch.Generator().manual_seed(seed)
+    x = f16_exact(torch.randn(2, 24, 9, 11, generator=g))
+    boxes = synthetic_boxes(7, 2, 144, 176, seed=seed + 1)
+    settings = [((7, 7), 1.0 / 16.0, 0), ((7, 7), 1.0 / 16.0, 2), ((3, 5), 0.25, 0), ((1, 1), 1.0 / 16.0, 3)]
+    return x, boxes, settings

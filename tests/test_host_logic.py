@@ -248,3 +248,34 @@ def test_modules_deepcopy_without_their_compiled_plans():
     assert "_pv_cache" not in m2.__dict__ and "_pv_cache" not in m2.blocks[1].__dict__
     assert "_pv_cache" in m.__dict__
     assert list(m2.state_dict()) == list(m.state_dict())
+
+
+@pytest.mark.parametrize("case", sorted(TS.DETECTION_CASES))
+def test_detection_models_lower_on_the_host(case):
+    """DetectionBBoxNetwork (trunk + RoIAlign head, models/net.py:47-74, head.py:394-482): one plan whose last ops are
+    roi_align -> spatial max pool -> proj; the [K, 5] boxes are a raw fp32 plan input."""
+    from pytorchvideo_b200.engine.lower import lower_only
+    model, inp, boxes, is_sf = TS.build_detection_case(case, PH)
+    ins = (list(inp) if is_sf else [inp]) + [boxes]
+    plan, shape = lower_only(model, ins)
+    K = boxes.shape[0]
+    assert tuple(shape)[:2] == (K, 80)
+    names = [n for n, _ in plan.ops]
+    assert any(n.endswith("roi_layer") for n in names) and any(n.endswith("pool_spatial") for n in names)
+    # dilated res5 (conv_b dilation (1,2,2), spatial stride 1) keeps the 1/16 feature map the head's spatial_scale assumes
+    assert sum(1 for n in names if n.endswith("roi_layer")) == 1
+    with pytest.raises(RuntimeError):
+        lower_only(model, (list(inp) if is_sf else [inp]) + [torch.zeros(3, 6)])        # RoIAlignRotated boxes
+    with pytest.raises(RuntimeError):
+        lower_only(model, (list(inp) if is_sf else [inp]) + [torch.zeros(0, 5)])
+
+
+def test_detection_state_dict_and_repr_follow_the_reference():
+    m = PH.slowfast_r50_detection()
+    sd = m.state_dict()
+    assert "model.blocks.0.multipathway_blocks.0.conv.weight" in sd and "detection_head.proj.weight" in sd
+    assert sd["detection_head.proj.weight"].shape == (80, 2304)
+    assert repr(m.detection_head.roi_layer) == "RoIAlign(output_size=(7, 7), spatial_scale=0.0625, sampling_ratio=0, aligned=False)"
+    s = PH.slow_r50_detection()
+    assert s.state_dict()["detection_head.proj.weight"].shape == (80, 2048)
+    assert type(s.detection_head.pool).__name__ == "AvgPool3d" and tuple(s.detection_head.pool.kernel_size) == (4, 1, 1)

@@ -239,3 +239,31 @@ def test_state_dict_keys_follow_the_reference_naming():
     x = PH.x3d_xs()
     assert "blocks.1.res_blocks.0.branch2.norm_b.1.block.0.weight" in x.state_dict()
     assert "blocks.0.conv.conv_t.weight" in x.state_dict() and "blocks.5.pool.pre_conv.weight" in x.state_dict()
+
+
+# ---- detection heads: tests/golden/detection.pt was produced by the REAL reference -----------------
+def test_roi_align_restatement_reproduces_torchvision_golden():
+    """oracle.interp.roi_align_ref (torchvision's roi_align, aligned=False, restated) vs the committed outputs of
+    torchvision.ops.roi_align on the op-level case: bit-exact (same fp32 operation order)."""
+    from oracle.interp import roi_align_ref
+    g = _gold("detection.pt")["roi_align"]
+    x, boxes, settings = TS.roi_align_case()
+    np.testing.assert_allclose(TS.tensor_checksum(x), g["input_checksum"], rtol=1e-12)
+    assert torch.equal(boxes, g["boxes"])
+    for (osz, scale, sr), ref in zip(settings, g["outputs"]):
+        out = roi_align_ref(x, boxes, osz, scale, sr)
+        assert torch.equal(out, ref), (osz, scale, sr, float((out - ref).abs().max()))
+
+
+@pytest.mark.parametrize("case", sorted(TS.DETECTION_CASES))
+def test_oracle_reproduces_reference_detection_goldens(case):
+    """Trunk + ResNetRoIHead (models/head.py:441-482, net.py:62-74) through the oracle vs the reference's own
+    slow_r50_detection / slowfast_r50_detection outputs."""
+    g = _gold("detection.pt")[case]
+    model, inp, boxes, is_sf = TS.build_detection_case(case, PH)
+    assert abs(TS.state_checksum(model) - g["state_checksum"]) <= 1e-6 * abs(g["state_checksum"])
+    assert torch.equal(boxes, g["boxes"])
+    out = oracle_forward(model, inp, boxes)
+    ref = g["output"]
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
