@@ -749,9 +749,11 @@ def emit_token_pool(plan, x, thw, pool, norm, heads, has_cls, name="pool"):
         def fn(stream):
             d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
             d.x_batch_stride, d.y_batch_stride = x.npos * x.row_stride, y.npos * y.row_stride
-            L.check(lib.pv_conv3d_fwd(C_.byref(d), L.ALGO_DIRECT, x.ptr() + cls * x.row_stride * esz, w_d.data_ptr(),
-                                      ones.data_ptr(), zeros.data_ptr(), None, y.ptr() + cls * y.row_stride * esz,
-                                      stream), "pv_conv3d_fwd(%s)" % name)
+            # depthwise entry point: lane-per-channel-pair stencil for 3x3x3 in f16, generic stencil otherwise; the
+            # batch strides step over the cls row in front of every sample
+            L.check(lib.pv_dwconv3d_fwd(C_.byref(d), x.ptr() + cls * x.row_stride * esz, w_d.data_ptr(),
+                                        ones.data_ptr(), zeros.data_ptr(), y.ptr() + cls * y.row_stride * esz, None,
+                                        stream), "pv_dwconv3d_fwd(%s)" % name)
         plan.add(name + ".dwconv", fn, "depthwise", 2.0 * x.N * To * Ho * Wo * dim * k[0] * k[1] * k[2],
                  (x.N * T * H * W + x.N * To * Ho * Wo) * dim * esz)
     else:
