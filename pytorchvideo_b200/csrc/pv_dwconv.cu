@@ -179,68 +179,59 @@ dwconv_temporal_kernel(const __half* __restrict__ x, const __half* __restrict__ 
                        long long x_row_stride, long long y_row_stride, long long x_batch_stride,
                        long long y_batch_stride, int act) {
   constexpr int PT = KT / 2;
+  // taps and folded BN as fp32 in shared memory (read per use: keeps them out of the register file, see the ring below)
+  extern __shared__ __align__(16) float tw_smem[];          // [KT][C] taps, [C] scale, [C] bias
+  float* ws = tw_smem;
+  float* scs = tw_smem + KT * C;
+  float* bis = scs + C;
+  for (int i = threadIdx.x; i < KT * C; i += blockDim.x) ws[i] = __half2float(w[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { scs[i] = __ldg(scale + i); bis[i] = __ldg(bias + i); }
+  __syncthreads();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= hw * G) return;
   const long long pos = idx / G;
   const int c = (int)(idx - pos * G) * 8;
   const int n = blockIdx.y;
-  uint4 wraw[KT];                      // taps stay packed (f16 pairs) to keep the register count low; converted at use
-  float sc[8], bi[8];
-#pragma unroll
-  for (int k = 0; k < KT; ++k) wraw[k] = __ldg(reinterpret_cast<const uint4*>(w + (long long)k * C + c));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { sc[i] = __ldg(scale + c + i); bi[i] = __ldg(bias + c + i); }
   const __half* xp = x + (long long)n * x_batch_stride + pos * x_row_stride + c;
   __half* yp = y + (long long)n * y_batch_stride + pos * y_row_stride + c;
   const long long xf = hw * x_row_stride, yf = hw * y_row_stride;      // frame strides
-  float win[KT][8];                                                    // frames t-PT .. t+PT
+  // Ring of 8 raw 16-byte frames: slot f & 7 holds frame f; frames t-PT .. t+PT are the window, the rest is read-ahead
+  // (PF = 8 - KT frames in flight per thread).  Everything stays packed f16 until it is used: ~90 registers, so 5 CTAs
+  // of 128 threads per SM keep ~30 KB of loads outstanding per SM.
+  constexpr int R = 8, PF = R - KT;
+  static_assert(KT <= 5, "ring too small");
+  uint4 ring[R];
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-  for (int k = 0; k < KT; ++k)
+  for (int s = 0; s < R; ++s) ring[s] = z4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) win[k][i] = 0.f;
+  for (int f = 0; f < R - PT; ++f)           // the ring holds frames t-PT .. t-PT+R-1 (frames < 0 stay zero: the padding)
+    ring[f & (R - 1)] = f < T ? __ldg(reinterpret_cast<const uint4*>(xp + (long long)f * xf)) : z4;
+  for (int t0 = 0; t0 < T; t0 += R) {
 #pragma unroll
-  for (int k = 0; k < PT; ++k)                                         // frames 0 .. PT-1 sit in slots PT+1 .. KT-1 after the first shift
-    if (k < T) ld8<__half>(xp + k * xf, win[PT + 1 + k]);
-  // PF frames of raw 16-byte vectors in flight per thread (one load per step would leave ~8 KB per SM outstanding)
-  constexpr int PF = 6;
-  uint4 raw[PF];
-#pragma unroll
-  for (int j = 0; j < PF; ++j)
-    raw[j] = (PT + j < T) ? __ldg(reinterpret_cast<const uint4*>(xp + (long long)(PT + j) * xf)) : make_uint4(0, 0, 0, 0);
-  for (int t0 = 0; t0 < T; t0 += PF) {
-#pragma unroll
-    for (int j = 0; j < PF; ++j) {
-      const int t = t0 + j;
+    for (int j = 0; j < R; ++j) {
+      const int t = t0 + j;                  // t & 7 == j: ring slots are compile-time
       if (t >= T) break;
-#pragma unroll
-      for (int k = 0; k + 1 < KT; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) win[k][i] = win[k + 1][i];
-      {
-        const __half2* h = reinterpret_cast<const __half2*>(&raw[j]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(h[i]);
-          win[KT - 1][2 * i] = f.x; win[KT - 1][2 * i + 1] = f.y;
-        }
-      }
-      const int nf = t + PT + PF;                                      // frame that reuses this slot
-      raw[j] = nf < T ? __ldg(reinterpret_cast<const uint4*>(xp + (long long)nf * xf)) : make_uint4(0, 0, 0, 0);
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
-        const __half2* wh = reinterpret_cast<const __half2*>(&wraw[k]);
+        const __half2* xh = reinterpret_cast<const __half2*>(&ring[(j + k - PT + R) & (R - 1)]);
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + k * C + c), w1 = *reinterpret_cast<const float4*>(ws + k * C + c + 4);
+        const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 wf = __half22float2(wh[i]);
-          v[2 * i] = fmaf(win[k][2 * i], wf.x, v[2 * i]);
-          v[2 * i + 1] = fmaf(win[k][2 * i + 1], wf.y, v[2 * i + 1]);
+          const float2 xf2 = __half22float2(xh[i]);
+          v[2 * i] = fmaf(xf2.x, wf[2 * i], v[2 * i]);
+          v[2 * i + 1] = fmaf(xf2.y, wf[2 * i + 1], v[2 * i + 1]);
         }
       }
+      // frame t-PT leaves the window: its slot takes frame t + PT + PF + 1 - ... = t - PT + R
+      const int nf = t - PT + R;
+      ring[(j - PT + R) & (R - 1)] = nf < T ? __ldg(reinterpret_cast<const uint4*>(xp + (long long)nf * xf)) : z4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i] * sc[i] + bi[i], act);
+      for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i] * scs[c + i] + bis[c + i], act);
       st8<__half>(yp + (long long)t * yf, v);
     }
   }
@@ -260,11 +251,13 @@ int dwconv3d_temporal_launch(const pv_conv3d_desc* d, const void* x, const void*
   const long long blocks = (hw * G + 127) / 128;
   if (blocks > 0x7fffffffll || d->N > 65535) return PV_ERR_UNSUPPORTED;
   dim3 grid((unsigned)blocks, (unsigned)d->N), block(128);
+  const size_t smem = (size_t)(d->kt + 2) * d->Co * sizeof(float);
+  if (smem > 40 * 1024) return PV_ERR_UNSUPPORTED;
   if (d->kt == 5)
-    dwconv_temporal_kernel<5><<<grid, block, 0, stream>>>((const __half*)x, (const __half*)w, scale, bias, (__half*)y, d->To, hw,
+    dwconv_temporal_kernel<5><<<grid, block, smem, stream>>>((const __half*)x, (const __half*)w, scale, bias, (__half*)y, d->To, hw,
                                                         G, d->Co, d->x_row_stride, d->y_row_stride, xbs, ybs, d->act);
   else
-    dwconv_temporal_kernel<3><<<grid, block, 0, stream>>>((const __half*)x, (const __half*)w, scale, bias, (__half*)y, d->To, hw,
+    dwconv_temporal_kernel<3><<<grid, block, smem, stream>>>((const __half*)x, (const __half*)w, scale, bias, (__half*)y, d->To, hw,
                                                         G, d->Co, d->x_row_stride, d->y_row_stride, xbs, ybs, d->act);
   PV_LAUNCH_OK("dwconv_temporal_kernel");
   return PV_OK;
