@@ -32,8 +32,8 @@ def test_roi_align_matches_torchvision_golden(dtype):
 
 # case: (min in-band fraction, max |d|/max|ref|) on the f16 path - measured on B200 (profiles/r02_parity.md)
 F16_BOUNDS = {
-    "slow_r50_detection": (0.80, 4e-3),
-    "slowfast_r50_detection": (0.90, 1.5e-3),
+    "slow_r50_detection": (0.86, 8e-4),                  # 0.900 / 5.4e-4 (logits)
+    "slowfast_r50_detection": (0.95, 6e-4),              # 0.983 / 3.2e-4 (logits)
     "slow_r50_detection_sigmoid": (0.88, 5e-3),          # 0.925 / 3.2e-3 (probabilities: |d p| <= |d logit| / 4)
 }
 
