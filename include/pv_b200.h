@@ -312,6 +312,15 @@ int pv_head_reduce(const void* x, int dtype, long long row_stride, int N, long l
 int pv_layernorm(const void* x, void* y, int dtype, long long rows, int groups, int C,
                  long long x_row_stride, long long y_row_stride, const float* gamma,
                  const float* beta, float eps, void* stream);
+/* pv_layernorm with (a) several (gamma, beta) sets: group g of a row uses set g / groups_per_set (gamma / beta hold
+ * groups / groups_per_set sets of C floats) - the pooled K and V of one block, adjacent channel slices of one buffer, are
+ * normalised by ONE launch with norm_k | norm_v (attention.py:200-205); (b) an optional second source for every
+ * npos-th row (row % npos == 0, read from cls_src + (row / npos) * cls_batch_stride): the cls token by-passes the
+ * pooling conv (attention.py:184-186, 196-197) and is normalised with the pooled rows without a copy launch.     */
+int pv_layernorm_sets(const void* x, void* y, int dtype, long long rows, int groups, int C,
+                      long long x_row_stride, long long y_row_stride, const float* gamma, const float* beta,
+                      int groups_per_set, const void* cls_src, long long cls_batch_stride, long long npos,
+                      float eps, void* stream);
 /* Strided row copy dst[r][0:C] = src[r][0:C] (cls-token rows around the pooling ops). */
 int pv_copy_rows(const void* src, void* dst, int dtype, long long rows, int C,
                  long long src_row_stride, long long dst_row_stride, void* stream);
@@ -321,6 +330,18 @@ int pv_copy_rows(const void* src, void* dst, int dtype, long long rows, int C,
  * x: [B][n_patch][C] (row stride x_row_stride), y: [B][1+n_patch][C] dense.                     */
 int pv_add_pos_cls(const void* x, void* y, int dtype, int B, long long n_patch, int C,
                    long long x_row_stride, const float* pos, int has_cls, void* stream);
+/* Same with separate dtypes: x f16 -> y f32 starts the fp32 residual trunk of the f16 engine (see pv_add_layernorm). */
+int pv_add_pos_cls_to(const void* x, int x_dtype, void* y, int y_dtype, int B, long long n_patch, int C,
+                      long long x_row_stride, const float* pos, int has_cls, void* stream);
+/* Residual add + LayerNorm of MultiScaleBlock.forward (layers/attention.py:746-757: x = x_res + x_block; norm2(x); ...
+ * x = x + x_mlp; the next block's norm1 at :730 / the model's norm_embed, models/vision_transformers.py:177) on an
+ * fp32 trunk:  s = a + b in fp32 (a: a_dtype f16|f32, row stride a_row_stride; b: f16 branch output or NULL),
+ *   sum[r][:] = s (fp32, optional - the residual stream never takes an f16 rounding),
+ *   y[r][:]   = LayerNorm(s) * gamma + beta as f16 (optional - the A operand of the next GEMM), fp32 statistics.
+ * C % 8 == 0, C <= 768; gamma / beta fp32, 16-byte aligned.                                                    */
+int pv_add_layernorm(const void* a, int a_dtype, long long a_row_stride, const void* b, long long b_row_stride,
+                     float* sum, long long sum_row_stride, void* y, long long y_row_stride, long long rows, int C,
+                     const float* gamma, const float* beta, float eps, void* stream);
 typedef struct pv_attention_desc {
   int dtype;
   int B, H, Nq, Nk, D;

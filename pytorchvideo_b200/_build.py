@@ -35,7 +35,8 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into lib/libpvb200.so.  Returns the library path."""
+    """Compile every CUDA source (one object per .cu, in parallel, only the stale ones) and link lib/libpvb200.so.
+    Returns the library path."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
@@ -43,15 +44,38 @@ def build(force=False, verbose=False):
         if os.path.exists(LIB_PATH):   # GPU box without sources changed: keep the shipped binary
             return LIB_PATH
         raise RuntimeError("nvcc not found and no prebuilt libpvb200.so present")
-    os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
-        [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")]
+    headers.append(os.path.join(_HERE, "..", "include", "pv_b200.h"))
+    t_hdr = max(os.path.getmtime(h) for h in headers if os.path.exists(h))
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(t_hdr, os.path.getmtime(path)):
+            return obj, None
+        tmp = obj + ".tmp.%d" % os.getpid()
+        res = subprocess.run([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", tmp, path],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n" % src + res.stdout + res.stderr)
+        os.replace(tmp, obj)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
     if verbose:
-        print(res.stderr)
+        for _, err in results:
+            if err:
+                print(err)
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + [o for o, _ in results],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

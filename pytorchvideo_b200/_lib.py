@@ -116,8 +116,13 @@ SIGNATURES = {
                                    C.c_int, C.c_float, C.c_int, c_vp, c_ll, c_vp]),
     "pv_layernorm": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_ll, c_ll, c_vp, c_vp,
                                C.c_float, c_vp]),
+    "pv_layernorm_sets": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_ll, c_ll, c_vp, c_vp, C.c_int, c_vp,
+                                    c_ll, c_ll, C.c_float, c_vp]),
     "pv_copy_rows": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int, c_ll, c_ll, c_vp]),
     "pv_add_pos_cls": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_ll, C.c_int, c_ll, c_vp, C.c_int, c_vp]),
+    "pv_add_pos_cls_to": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, c_ll, C.c_int, c_ll, c_vp, C.c_int, c_vp]),
+    "pv_add_layernorm": (C.c_int, [c_vp, C.c_int, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, C.c_int, c_vp, c_vp,
+                                   C.c_float, c_vp]),
     "pv_attention_fwd": (C.c_int, [C.POINTER(AttentionDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 

@@ -572,17 +572,29 @@ __global__ void head_reduce_kernel(const T* __restrict__ x, long long row_stride
 // =============================================================================================
 // LayerNorm over the last dim, one warp per row, fp32 statistics (two-pass, like ATen).
 // =============================================================================================
+// Extras of pv_layernorm_sets: several (gamma, beta) sets (group g uses set g / groups_per_set - the pooled K and V
+// of one MViT block are normalised by ONE launch with norm_k | norm_v) and rows whose input comes from another tensor
+// (every npos-th row = the cls token that by-passes the pooling conv, layers/attention.py:184-205: no copy launch).
+struct LnExtra {
+  int groups_per_set;
+  const void* cls_src;
+  long long cls_batch_stride, npos;
+};
 template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int groups, int C,
                  long long x_row_stride, long long y_row_stride, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps) {
+                 const float* __restrict__ beta, float eps, LnExtra X) {
   const long long rg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (row, group)
   if (rg >= rows * groups) return;
   const long long row = rg / groups;
   const int grp = (int)(rg - row * groups);
   const int lane = threadIdx.x & 31;
   const T* xr = x + row * x_row_stride + (long long)grp * C;
+  if (X.cls_src != nullptr && row % X.npos == 0)
+    xr = reinterpret_cast<const T*>(X.cls_src) + (row / X.npos) * X.cls_batch_stride + (long long)grp * C;
+  gamma += (grp / X.groups_per_set) * C;
+  beta += (grp / X.groups_per_set) * C;
   float s = 0.f;
   for (int c = lane * 8; c < C; c += 256) {
     float v[8];
@@ -620,7 +632,7 @@ template <typename T, int NCH>
 __global__ void __launch_bounds__(256)
 layernorm_reg_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int groups, int C,
                      long long x_row_stride, long long y_row_stride, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float eps, int lpr_log2) {
+                     const float* __restrict__ beta, float eps, int lpr_log2, LnExtra X) {
   const int lane = threadIdx.x & 31;
   const int lpr = 1 << lpr_log2;
   const int sub = lane >> lpr_log2, sl = lane & (lpr - 1);
@@ -631,6 +643,10 @@ layernorm_reg_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows,
   const long long row = rg / groups;
   const int grp = (int)(rg - row * groups);
   const T* xr = x + row * x_row_stride + (long long)grp * C;
+  if (X.cls_src != nullptr && row % X.npos == 0)
+    xr = reinterpret_cast<const T*>(X.cls_src) + (row / X.npos) * X.cls_batch_stride + (long long)grp * C;
+  gamma += (grp / X.groups_per_set) * C;
+  beta += (grp / X.groups_per_set) * C;
   float v[NCH][8];
   float s = 0.f;
 #pragma unroll
@@ -671,6 +687,73 @@ layernorm_reg_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows,
       o8[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o8[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
       o8[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o8[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
       st8<T>(yr + c, o8);
+    }
+  }
+}
+
+// Residual add + LayerNorm on an fp32 trunk (MViT token stream, layers/attention.py:746-757: x = x_res + x_block;
+// x_norm = norm2(x); ... x = x + x_mlp; next block's norm1).  s = a + b in fp32 (a: f16 | f32, b: f16 branch or none);
+// s is stored as fp32 (the residual trunk never takes an f16 rounding), y = LN(s) is stored as f16 (the next GEMM's
+// A operand).  Same row-in-registers scheme as layernorm_reg_kernel; sum / y may each be null.
+template <typename TA, bool HAS_B, int NCH>
+__global__ void __launch_bounds__(256)
+add_layernorm_kernel(const TA* __restrict__ a, const __half* __restrict__ b, float* __restrict__ sum,
+                     __half* __restrict__ y, long long rows, int C, long long a_rs, long long b_rs, long long s_rs,
+                     long long y_rs, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     int lpr_log2) {
+  const int lane = threadIdx.x & 31;
+  const int lpr = 1 << lpr_log2;
+  const int sub = lane >> lpr_log2, sl = lane & (lpr - 1);
+  long long row = (((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) << (5 - lpr_log2)) + sub;
+  const bool ok = row < rows;
+  if (!ok) row = 0;
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (sl + i * lpr) * 8;
+    if (ok && c < C) {
+      ld8<TA>(a + row * a_rs + c, v[i]);
+      if (HAS_B) {
+        float w[8];
+        ld8<__half>(b + row * b_rs + c, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] += w[e];
+      }
+      if (sum != nullptr) st8<float>(sum + row * s_rs + c, v[i]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[i][e];
+  }
+  if (y == nullptr) return;
+  for (int o = lpr >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (sl + i * lpr) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = v[i][e] - mean; q = fmaf(dlt, dlt, q); }
+    }
+  }
+  for (int o = lpr >> 1; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (sl + i * lpr) * 8;
+    if (ok && c < C) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      float o8[8];
+      o8[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o8[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+      o8[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o8[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+      o8[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o8[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+      o8[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o8[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+      st8<__half>(y + row * y_rs + c, o8);
     }
   }
 }
@@ -716,8 +799,8 @@ __global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
   st8<T>(dst + r * ds + c, v);
 }
 
-template <typename T>
-__global__ void add_pos_cls_kernel(const T* __restrict__ x, T* __restrict__ y, long long n_patch, int C,
+template <typename T, typename TO>
+__global__ void add_pos_cls_kernel(const T* __restrict__ x, TO* __restrict__ y, long long n_patch, int C,
                                    long long x_row_stride, const float* __restrict__ pos, int has_cls,
                                    long long total) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -736,7 +819,7 @@ __global__ void add_pos_cls_kernel(const T* __restrict__ x, T* __restrict__ y, l
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] += __ldg(pos + i * C + c + q);
   }
-  st8<T>(y + r * C + c, v);
+  st8<TO>(y + r * C + c, v);
 }
 
 }  // namespace pv
@@ -837,20 +920,60 @@ extern "C" int pv_copy_rows(const void* src, void* dst, int dtype, long long row
   return PV_OK;
 }
 
-extern "C" int pv_add_pos_cls(const void* x, void* y, int dtype, int B, long long n_patch, int C,
-                              long long x_row_stride, const float* pos, int has_cls, void* stream) {
+extern "C" int pv_add_pos_cls_to(const void* x, int x_dtype, void* y, int y_dtype, int B, long long n_patch, int C,
+                                 long long x_row_stride, const float* pos, int has_cls, void* stream) {
   PV_CHECK_ARG(x && y && pos, "null pointer");
   PV_CHECK_ARG(C % 8 == 0 && x_row_stride % 8 == 0, "C/strides %% 8");
   const long long total = (long long)B * (n_patch + (has_cls ? 1 : 0)) * (C / 8);
   if (total == 0) return PV_OK;
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((unsigned)cdiv(total, 256)), block(256);
-  if (dtype == PV_F16)
-    add_pos_cls_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, n_patch, C, x_row_stride, pos, has_cls ? 1 : 0, total);
-  else if (dtype == PV_F32)
-    add_pos_cls_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, n_patch, C, x_row_stride, pos, has_cls ? 1 : 0, total);
-  else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
+  const int hc = has_cls ? 1 : 0;
+  if (x_dtype == PV_F16 && y_dtype == PV_F16)
+    add_pos_cls_kernel<__half, __half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, n_patch, C, x_row_stride, pos, hc, total);
+  else if (x_dtype == PV_F16 && y_dtype == PV_F32)
+    add_pos_cls_kernel<__half, float><<<grid, block, 0, s>>>((const __half*)x, (float*)y, n_patch, C, x_row_stride, pos, hc, total);
+  else if (x_dtype == PV_F32 && y_dtype == PV_F32)
+    add_pos_cls_kernel<float, float><<<grid, block, 0, s>>>((const float*)x, (float*)y, n_patch, C, x_row_stride, pos, hc, total);
+  else { set_error("unsupported dtypes %d -> %d", x_dtype, y_dtype); return PV_ERR_INVALID; }
   PV_LAUNCH_OK("add_pos_cls_kernel");
+  return PV_OK;
+}
+
+extern "C" int pv_add_pos_cls(const void* x, void* y, int dtype, int B, long long n_patch, int C,
+                              long long x_row_stride, const float* pos, int has_cls, void* stream) {
+  return pv_add_pos_cls_to(x, dtype, y, dtype, B, n_patch, C, x_row_stride, pos, has_cls, stream);
+}
+
+extern "C" int pv_add_layernorm(const void* a, int a_dtype, long long a_row_stride, const void* b,
+                                long long b_row_stride, float* sum, long long sum_row_stride, void* y,
+                                long long y_row_stride, long long rows, int C, const float* gamma,
+                                const float* beta, float eps, void* stream) {
+  PV_CHECK_ARG(a && (sum || y), "null pointer");
+  PV_CHECK_ARG(!y || (gamma && beta), "LayerNorm output without gamma / beta");
+  PV_CHECK_ARG(a_dtype == PV_F16 || a_dtype == PV_F32, "a must be f16 or f32");
+  PV_CHECK_ARG(C % 8 == 0 && a_row_stride % 8 == 0 && b_row_stride % 8 == 0 && sum_row_stride % 8 == 0 &&
+               y_row_stride % 8 == 0, "C/strides %% 8");
+  PV_CHECK_ARG(a_row_stride >= C && (!b || b_row_stride >= C) && (!sum || sum_row_stride >= C) &&
+               (!y || y_row_stride >= C), "row stride < C");
+  PV_CHECK_ARG(!y || ((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0), "gamma / beta must be 16-byte aligned");
+  if (rows == 0) return PV_OK;
+  const int chunks = C / 8;
+  int lpr_log2 = 2;
+  while ((1 << lpr_log2) < chunks && lpr_log2 < 5) ++lpr_log2;
+  const int nch = (chunks + (1 << lpr_log2) - 1) >> lpr_log2;
+  if (nch > 3) { set_error("pv_add_layernorm: C = %d > 768 unsupported", C); return PV_ERR_UNSUPPORTED; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long per_block = 8ll << (5 - lpr_log2);
+  dim3 grid((unsigned)cdiv(rows, per_block)), block(256);
+#define PV_ALN(TA, HB, N_) add_layernorm_kernel<TA, HB, N_><<<grid, block, 0, s>>>((const TA*)a, (const __half*)b, sum, (__half*)y, \
+    rows, C, a_row_stride, b_row_stride, sum_row_stride, y_row_stride, gamma, beta, eps, lpr_log2)
+#define PV_ALN_N(TA, HB) do { if (nch == 1) PV_ALN(TA, HB, 1); else if (nch == 2) PV_ALN(TA, HB, 2); else PV_ALN(TA, HB, 3); } while (0)
+  if (a_dtype == PV_F16) { if (b) PV_ALN_N(__half, true); else PV_ALN_N(__half, false); }
+  else { if (b) PV_ALN_N(float, true); else PV_ALN_N(float, false); }
+#undef PV_ALN_N
+#undef PV_ALN
+  PV_LAUNCH_OK("add_layernorm_kernel");
   return PV_OK;
 }
 
@@ -1061,10 +1184,15 @@ extern "C" int pv_head_reduce(const void* x, int dtype, long long row_stride, in
   return PV_OK;
 }
 
-extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, int groups, int C,
-                            long long x_row_stride, long long y_row_stride, const float* gamma,
-                            const float* beta, float eps, void* stream) {
+extern "C" int pv_layernorm_sets(const void* x, void* y, int dtype, long long rows, int groups, int C,
+                                 long long x_row_stride, long long y_row_stride, const float* gamma,
+                                 const float* beta, int groups_per_set, const void* cls_src,
+                                 long long cls_batch_stride, long long npos, float eps, void* stream) {
   PV_CHECK_ARG(x && y && gamma && beta, "null pointer");
+  PV_CHECK_ARG(groups_per_set >= 1 && groups % groups_per_set == 0, "groups %% groups_per_set");
+  PV_CHECK_ARG(!cls_src || (npos >= 1 && rows % npos == 0 && cls_batch_stride % 8 == 0), "cls rows: rows %% npos, stride %% 8");
+  pv::LnExtra X;
+  X.groups_per_set = groups_per_set; X.cls_src = cls_src; X.cls_batch_stride = cls_batch_stride; X.npos = npos > 0 ? npos : 1;
   PV_CHECK_ARG(groups >= 1 && C % 8 == 0 && x_row_stride % 8 == 0 && y_row_stride % 8 == 0, "C/strides %% 8");
   PV_CHECK_ARG(x_row_stride >= (long long)groups * C && y_row_stride >= (long long)groups * C, "row stride < groups*C");
   if (rows == 0) return PV_OK;
@@ -1077,7 +1205,7 @@ extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, i
   if (nch <= 3 && aligned16 && (dtype == PV_F16 || dtype == PV_F32)) {
     const long long per_block = 8ll << (5 - lpr_log2);     // rows per 256-thread block
     dim3 grid((unsigned)cdiv(rows * groups, per_block)), block(256);
-#define PV_LN(TT, N_) layernorm_reg_kernel<TT, N_><<<grid, block, 0, s>>>((const TT*)x, (TT*)y, rows, groups, C, x_row_stride, y_row_stride, gamma, beta, eps, lpr_log2)
+#define PV_LN(TT, N_) layernorm_reg_kernel<TT, N_><<<grid, block, 0, s>>>((const TT*)x, (TT*)y, rows, groups, C, x_row_stride, y_row_stride, gamma, beta, eps, lpr_log2, X)
     if (dtype == PV_F16) { if (nch == 1) PV_LN(__half, 1); else if (nch == 2) PV_LN(__half, 2); else PV_LN(__half, 3); }
     else { if (nch == 1) PV_LN(float, 1); else if (nch == 2) PV_LN(float, 2); else PV_LN(float, 3); }
 #undef PV_LN
@@ -1087,11 +1215,18 @@ extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, i
   dim3 grid((unsigned)cdiv(rows * groups, 8)), block(256);
   if (dtype == PV_F16)
     layernorm_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, (__half*)y, rows, groups, C, x_row_stride,
-                                                 y_row_stride, gamma, beta, eps);
+                                                 y_row_stride, gamma, beta, eps, X);
   else if (dtype == PV_F32)
     layernorm_kernel<float><<<grid, block, 0, s>>>((const float*)x, (float*)y, rows, groups, C, x_row_stride,
-                                                y_row_stride, gamma, beta, eps);
+                                                y_row_stride, gamma, beta, eps, X);
   else { set_error("unsupported dtype %d", dtype); return PV_ERR_INVALID; }
   PV_LAUNCH_OK("layernorm_kernel");
   return PV_OK;
+}
+
+extern "C" int pv_layernorm(const void* x, void* y, int dtype, long long rows, int groups, int C,
+                            long long x_row_stride, long long y_row_stride, const float* gamma,
+                            const float* beta, float eps, void* stream) {
+  return pv_layernorm_sets(x, y, dtype, rows, groups, C, x_row_stride, y_row_stride, gamma, beta, groups > 0 ? groups : 1,
+                           nullptr, 0, 1, eps, stream);
 }

@@ -555,10 +555,18 @@ def _lower_mvit_attention(low, attn, xn, thw, name, residual=None):
     thw_q = thw
     if getattr(attn, "pool_q", None) is not None:
         q, thw_q = PL.emit_token_pool(p, q, thw, attn.pool_q, getattr(attn, "norm_q", None), heads, has_cls, name + ".pool_q")
-    if getattr(attn, "pool_k", None) is not None:
-        k, _ = PL.emit_token_pool(p, k, thw, attn.pool_k, getattr(attn, "norm_k", None), heads, has_cls, name + ".pool_k")
-    if getattr(attn, "pool_v", None) is not None:
-        v, _ = PL.emit_token_pool(p, v, thw, attn.pool_v, getattr(attn, "norm_v", None), heads, has_cls, name + ".pool_v")
+    pool_k, pool_v = getattr(attn, "pool_k", None), getattr(attn, "pool_v", None)
+    norm_k, norm_v = getattr(attn, "norm_k", None), getattr(attn, "norm_v", None)
+    if pool_k is not None and pool_v is not None and PL.pools_fusable(pool_k, pool_v, norm_k, norm_v):
+        # k | v are adjacent channel slices of the QKV GEMM output: ONE depthwise launch + ONE LayerNorm launch for both
+        kv, _ = PL.emit_token_pool(p, PL.channel_slice(qkv, dim_att, 2 * dim_att), thw, (pool_k, pool_v), (norm_k, norm_v),
+                                   heads, has_cls, name + ".pool_kv")
+        k, v = PL.channel_slice(kv, 0, dim_att), PL.channel_slice(kv, dim_att, dim_att)
+    else:
+        if pool_k is not None:
+            k, _ = PL.emit_token_pool(p, k, thw, pool_k, norm_k, heads, has_cls, name + ".pool_k")
+        if pool_v is not None:
+            v, _ = PL.emit_token_pool(p, v, thw, pool_v, norm_v, heads, has_cls, name + ".pool_v")
     o = PL.emit_attention(p, q, k, v, heads, attn.scale, attn.residual_pool, name + ".core")
     x = PL.emit_linear(p, o, attn.proj.weight, attn.proj.bias, L.ACT_NONE, residual, name + ".proj")
     return x, thw_q
@@ -573,27 +581,41 @@ def _lower_mlp(low, mlp, xn, name, residual=None):
     return PL.emit_linear(low.p, h, mlp.fc2.weight, mlp.fc2.bias, L.ACT_NONE, residual, name + ".fc2")
 
 
-def _lower_mvit_block(low, blk, x, thw, name):
-    """MultiScaleBlock.forward (layers/attention.py:729-757); DropPath is the identity in eval."""
+def _lower_mvit_block(low, blk, x, thw, name, xn=None, next_ln=None, want_sum=True):
+    """MultiScaleBlock.forward (layers/attention.py:729-757); DropPath is the identity in eval.
+    Returns (x, thw', xn_next).  f16 engine with ``plan.trunk32``: the residual stream x is fp32 - the branch outputs
+    (attention proj, fc2) stay f16 and each residual add is fused with the LayerNorm that follows it (norm2; ``next_ln`` =
+    the next block's norm1 / the model's norm_embed, whose f16 output comes back as xn_next; ``xn`` = this block's
+    already normalised input handed over by the previous block)."""
     p = low.p
     attn = blk.attn
     if getattr(blk, "norm1_is_batchnorm_1d", False) or getattr(blk, "norm2_is_batchnorm_1d", False):
         raise NotImplementedError("batchnorm MViT variant unsupported")
     has_cls = attn.has_cls_embed
     thw = _check_thw(x, thw, has_cls, name)
-    xn = PL.emit_layernorm(p, x, blk.norm1, name + ".norm1")
+    trunk32 = p.trunk32
+    if xn is None:
+        xn = PL.emit_layernorm(p, x, blk.norm1, name + ".norm1")
     widen = blk.dim != blk.dim_out
     if blk.dim_mul_in_att and widen:
         x = PL.emit_linear(p, xn, blk.proj.weight, blk.proj.bias, L.ACT_NONE, None, name + ".proj")
     x_res = x
     if getattr(blk, "pool_skip", None) is not None:
         x_res, _ = PL.emit_token_pool(p, x, thw, blk.pool_skip, None, 1, has_cls, name + ".pool_skip")
-    x, thw_q = _lower_mvit_attention(low, attn, xn, thw, name + ".attn", residual=x_res)
-    xn2 = PL.emit_layernorm(p, x, blk.norm2, name + ".norm2")
+    if trunk32:
+        br, thw_q = _lower_mvit_attention(low, attn, xn, thw, name + ".attn", residual=None)
+        x, xn2 = PL.emit_add_layernorm(p, x_res, br, blk.norm2, name + ".norm2")
+    else:
+        x, thw_q = _lower_mvit_attention(low, attn, xn, thw, name + ".attn", residual=x_res)
+        xn2 = PL.emit_layernorm(p, x, blk.norm2, name + ".norm2")
     if (not blk.dim_mul_in_att) and widen:
         x = PL.emit_linear(p, xn2, blk.proj.weight, blk.proj.bias, L.ACT_NONE, None, name + ".proj")
+    if trunk32:
+        br2 = _lower_mlp(low, blk.mlp, xn2, name + ".mlp", residual=None)
+        x, xn_next = PL.emit_add_layernorm(p, x, br2, next_ln, name + ".add", want_sum=want_sum or next_ln is None)
+        return x, thw_q, xn_next
     x = _lower_mlp(low, blk.mlp, xn2, name + ".mlp", residual=x)
-    return x, thw_q
+    return x, thw_q, None
 
 
 def _pos_table(enc):
@@ -649,18 +671,27 @@ def _lower_mvit(self, m, x, name):
     if (x.T, x.H, x.W) != (T, H, W):
         raise RuntimeError("input clip gives a %s patch grid but the model was built for %s" % ((x.T, x.H, x.W), (T, H, W)))
     pos, has_cls = _pos_table(enc)
-    x = PL.emit_pos_cls(p, x, pos, has_cls, "cls_positional_encoding")
+    ne = m.norm_embed
+    ne_is_ln = type(ne).__name__ == "LayerNorm"
+    if p.trunk32 and not ne_is_ln:
+        p.trunk32 = False            # the head's GEMM needs f16 tokens: without a final LayerNorm keep the f16 stream
+    x = PL.emit_pos_cls(p, x, pos, has_cls, "cls_positional_encoding", out_dt=L.PV_F32 if p.trunk32 else None)
     thw = (T, H, W)
+    xn = None
+    nb = len(m.blocks)
     for i, blk in enumerate(m.blocks):
-        x, thw = _lower_mvit_block(self, blk, x, thw, "blocks.%d" % i)
+        last = i + 1 == nb
+        nxt = (ne if last else m.blocks[i + 1].norm1) if p.trunk32 else None
+        x, thw, xn = _lower_mvit_block(self, blk, x, thw, "blocks.%d" % i, xn=xn, next_ln=nxt, want_sum=not last)
     head = m.head
     if type(head).__name__ == "Identity":
         raise NotImplementedError("headless MViT output is unsupported")
     if type(head).__name__ != "VisionTransformerBasicHead":
         raise NotImplementedError("MViT head %s unsupported" % type(head).__name__)
     mode = head.sequence_pool.mode if head.sequence_pool is not None else None
-    ne = m.norm_embed
-    if type(ne).__name__ == "LayerNorm":
+    if p.trunk32:
+        x = xn                 # norm_embed was fused into the last block's residual add
+    elif ne_is_ln:
         if mode == "cls":      # only the cls row reaches the head: normalise just those B rows
             x = PL.emit_layernorm(p, x, ne, "norm_embed", rows_stride=x.npos * x.row_stride, rows=x.N)
         else:
@@ -678,7 +709,7 @@ def _tok_out(x, squeeze=False):
 def _lower_block_module(self, m, x, name):
     if len(self.extra) != 1:
         raise RuntimeError("MultiScaleBlock.forward(x, thw_shape): thw_shape is required")
-    y, thw = _lower_mvit_block(self, m, x, self.extra[0], name or "block")
+    y, thw, _ = _lower_mvit_block(self, m, x, self.extra[0], name or "block")
     self.aux_out = list(thw)
     return _tok_out(y)
 

@@ -94,6 +94,9 @@ class Plan:
         self.op_io = []        # (reads, writes) as lists of TRef / Buf, or None = unknown (acts as a full barrier)
         self.sched = None
         self.multi_lane = os.environ.get("PVB200_LANES", "1") != "0"
+        # f16 engine, MViT: the residual token stream (16 blocks x 2 adds) is kept in fp32 - branch outputs stay f16, the
+        # add + LayerNorm is one kernel (pv_add_layernorm).  PVB200_TRUNK32=0 restores the all-f16 stream (A/B only).
+        self.trunk32 = dt == L.PV_F16 and os.environ.get("PVB200_TRUNK32", "1") != "0"
         self._streams = {}
         self._events = {}
 
@@ -622,7 +625,7 @@ class Plan:
         self.materialize_input(x)
         lib = self.lib
         if x.row_stride != x.C or x.Cp != x.C:
-            dense = self.new_tensor(x.N, 1, 1, x.npos, x.C, Cp=x.C)
+            dense = self.new_tensor(x.N, 1, 1, x.npos, x.C, Cp=x.C, dt=x.dt)
             src = x
 
             def fn_c(stream):
@@ -679,6 +682,14 @@ def emit_layernorm(plan, x, ln, name="ln", rows_stride=None, rows=None):
     xs = x.row_stride if rows_stride is None else rows_stride
     y = plan.new_tensor(x.N, 1, 1, x.npos if rows is None else 1, C, Cp=C)
     lib = plan.lib
+    if x.dt != plan.dt:          # fp32 trunk of the f16 engine: f32 in, f16 out
+        assert x.dt == L.PV_F32 and plan.dt == L.PV_F16
+
+        def fn32(stream):
+            L.check(lib.pv_add_layernorm(x.ptr(), x.dt, xs, None, 0, None, 0, y.ptr(), y.row_stride, n_rows, C,
+                                         g.data_ptr(), b.data_ptr(), eps, stream), "pv_add_layernorm(%s)" % name)
+        plan.add(name, fn32, "other", 0.0, n_rows * C * 6)
+        return y
 
     def fn(stream):
         L.check(lib.pv_layernorm(x.ptr(), y.ptr(), x.dt, n_rows, 1, C, xs, y.row_stride, g.data_ptr(), b.data_ptr(),
@@ -687,64 +698,123 @@ def emit_layernorm(plan, x, ln, name="ln", rows_stride=None, rows=None):
     return y
 
 
-def emit_pos_cls(plan, x, pos_table, has_cls, name="posenc"):
-    """x: patch tokens as produced by the patch-embed conv [B, T', H', W', C] -> [B, cls+THW, C]."""
-    n_patch = x.npos
-    C = x.C
-    pos = plan.const(pos_table.float().contiguous())
-    y = _tok(plan, x.N, n_patch + (1 if has_cls else 0), C)
+def emit_add_layernorm(plan, a, br, ln, name="add_ln", want_sum=True):
+    """fp32 residual trunk of the f16 engine (layers/attention.py:746-757): s = a + br with a f16|f32 and br the f16
+    branch output; returns (s as an fp32 token tensor or None, LayerNorm(s) as f16 or None when ln is None)."""
+    C = a.C
+    assert br.C == C and br.N == a.N and br.npos == a.npos, "residual / branch shape mismatch"
+    assert br.dt == L.PV_F16 and plan.dt == L.PV_F16
+    assert want_sum or ln is not None
+    n_rows = a.N * a.npos
+    s = _tok(plan, a.N, a.npos, C, dt=L.PV_F32) if want_sum else None
+    y = g = b = None
+    eps = 0.0
+    if ln is not None:
+        assert tuple(ln.normalized_shape) == (C,), "LayerNorm width mismatch"
+        g = plan.const(ln.weight.detach().float().cpu())
+        b = plan.const(ln.bias.detach().float().cpu())
+        eps = float(ln.eps)
+        y = _tok(plan, a.N, a.npos, C)
     lib = plan.lib
 
     def fn(stream):
-        L.check(lib.pv_add_pos_cls(x.ptr(), y.ptr(), x.dt, x.N, n_patch, C, x.row_stride, pos.data_ptr(),
-                                   1 if has_cls else 0, stream), "pv_add_pos_cls")
-    plan.add(name, fn, "other", 0.0, 2 * x.N * n_patch * C * 2)
+        L.check(lib.pv_add_layernorm(a.ptr(), a.dt, a.row_stride, br.ptr(), br.row_stride,
+                                     s.ptr() if s is not None else None, s.row_stride if s is not None else 0,
+                                     y.ptr() if y is not None else None, y.row_stride if y is not None else 0,
+                                     n_rows, C, g.data_ptr() if g is not None else None,
+                                     b.data_ptr() if b is not None else None, eps, stream), "pv_add_layernorm(%s)" % name)
+    plan.add(name, fn, "other", 0.0, n_rows * C * (_ESIZE[a.dt] + 2 + (4 if want_sum else 0) + (2 if ln is not None else 0)))
+    return s, y
+
+
+def emit_pos_cls(plan, x, pos_table, has_cls, name="posenc", out_dt=None):
+    """x: patch tokens as produced by the patch-embed conv [B, T', H', W', C] -> [B, cls+THW, C] (out_dt = PV_F32
+    starts the fp32 residual trunk of the f16 engine)."""
+    n_patch = x.npos
+    C = x.C
+    pos = plan.const(pos_table.float().contiguous())
+    y = _tok(plan, x.N, n_patch + (1 if has_cls else 0), C, dt=out_dt)
+    lib = plan.lib
+
+    def fn(stream):
+        L.check(lib.pv_add_pos_cls_to(x.ptr(), x.dt, y.ptr(), y.dt, x.N, n_patch, C, x.row_stride, pos.data_ptr(),
+                                      1 if has_cls else 0, stream), "pv_add_pos_cls_to")
+    plan.add(name, fn, "other", 0.0, x.N * n_patch * C * (_ESIZE[x.dt] + _ESIZE[y.dt]))
     return y
+
+
+def _pool_geometry(pool):
+    kind = type(pool).__name__
+    if kind == "Conv3d":
+        k, s, p, dl = [tuple(int(v) for v in t) for t in (pool.kernel_size, pool.stride, pool.padding, pool.dilation)]
+        return kind, k, s, p, dl, int(pool.in_channels)
+    if kind == "MaxPool3d":
+        k, s, p = [tuple(int(v) for v in (t if isinstance(t, (tuple, list)) else (t,) * 3))
+                   for t in (pool.kernel_size, pool.stride, pool.padding)]
+        return kind, k, s, p, (1, 1, 1), 0
+    raise NotImplementedError("pool module %s unsupported" % kind)
+
+
+def pools_fusable(pool_a, pool_b, norm_a, norm_b):
+    """True when two _AttentionPool branches (pool_k / pool_v) can run as ONE depthwise launch + ONE LayerNorm launch over
+    adjacent channel slices: same conv geometry, LayerNorms of the same width / eps."""
+    if type(pool_a).__name__ != "Conv3d" or type(pool_b).__name__ != "Conv3d":
+        return False
+    if _pool_geometry(pool_a) != _pool_geometry(pool_b):
+        return False
+    na, nb = type(norm_a).__name__, type(norm_b).__name__
+    if na != "LayerNorm" or nb != "LayerNorm":
+        return False
+    return tuple(norm_a.normalized_shape) == tuple(norm_b.normalized_shape) and float(norm_a.eps) == float(norm_b.eps)
 
 
 def emit_token_pool(plan, x, thw, pool, norm, heads, has_cls, name="pool"):
     """_AttentionPool (layers/attention.py:162-212) on a token tensor/slice x [B, cls+THW, dim]:
     depthwise Conv3d / MaxPool3d over the (T,H,W) grid of the patch tokens (cls row passes through),
-    then the per-head LayerNorm over head_dim (cls row included).  Returns (tokens, thw')."""
+    then the per-head LayerNorm over head_dim (cls row included; it is read straight from x by the LayerNorm
+    launch).  ``pool`` / ``norm`` may be tuples (pool_k, pool_v) / (norm_k, norm_v): x then holds the branches as
+    adjacent channel slices and both run in one depthwise + one LayerNorm launch (see pools_fusable).
+    Returns (tokens, thw')."""
     import ctypes as C_
+    pools = list(pool) if isinstance(pool, (tuple, list)) else [pool]
+    norms = list(norm) if isinstance(norm, (tuple, list)) else [norm] * len(pools)
+    nset = len(pools)
     T, H, W = thw
-    dim = x.C
+    dim_all = x.C
+    assert dim_all % nset == 0
+    dim = dim_all // nset
     cls = 1 if has_cls else 0
     assert x.npos == cls + T * H * W, "token count does not match thw"
-    kind = type(pool).__name__
+    kind, k, s, p, dl, pool_ch = _pool_geometry(pools[0])
+    for q in pools[1:]:
+        assert _pool_geometry(q) == (kind, k, s, p, dl, pool_ch)
     if kind == "Conv3d":
-        k, s, p, dl = [tuple(int(v) for v in t) for t in (pool.kernel_size, pool.stride, pool.padding, pool.dilation)]
-        if pool.groups != pool.in_channels or pool.in_channels != pool.out_channels or pool.bias is not None:
-            raise NotImplementedError("%s: only depthwise, bias-free pooling convs are supported" % name)
-        if dim % pool.in_channels:
+        for q in pools:
+            if q.groups != q.in_channels or q.in_channels != q.out_channels or q.bias is not None:
+                raise NotImplementedError("%s: only depthwise, bias-free pooling convs are supported" % name)
+        if dim % pool_ch:
             raise RuntimeError("%s: pool channels do not divide the token width" % name)
-    elif kind == "MaxPool3d":
-        k, s, p = [tuple(int(v) for v in (t if isinstance(t, (tuple, list)) else (t,) * 3))
-                   for t in (pool.kernel_size, pool.stride, pool.padding)]
-        dl = (1, 1, 1)
-    else:
-        raise NotImplementedError("%s: pool module %s unsupported" % (name, kind))
     To = (T + 2 * p[0] - dl[0] * (k[0] - 1) - 1) // s[0] + 1
     Ho = (H + 2 * p[1] - dl[1] * (k[1] - 1) - 1) // s[1] + 1
     Wo = (W + 2 * p[2] - dl[2] * (k[2] - 1) - 1) // s[2] + 1
-    y = _tok(plan, x.N, cls + To * Ho * Wo, dim)
+    y = _tok(plan, x.N, cls + To * Ho * Wo, dim_all, dt=x.dt)
     lib = plan.lib
-    esz = _ESIZE[plan.dt]
+    esz = _ESIZE[x.dt]
     if kind == "Conv3d":
-        reps = dim // pool.in_channels
-        w_full = pool.weight.detach().cpu().repeat(reps, 1, 1, 1, 1)      # same filter for every head
-        w_d = plan.const(PK.pack_depthwise(w_full, dim, _TORCH_DT[plan.dt]))
-        ones = plan.const(torch.ones(dim, dtype=torch.float32))
-        zeros = plan.const(torch.zeros(dim, dtype=torch.float32))
+        reps = dim // pool_ch
+        w_full = torch.cat([q.weight.detach().cpu().repeat(reps, 1, 1, 1, 1) for q in pools], 0)   # same filter for every head
+        w_d = plan.const(PK.pack_depthwise(w_full, dim_all, _TORCH_DT[x.dt]))
+        ones = plan.const(torch.ones(dim_all, dtype=torch.float32))
+        zeros = plan.const(torch.zeros(dim_all, dtype=torch.float32))
         d = L.Conv3dDesc()
-        d.dtype = plan.dt
-        d.N, d.Ti, d.Hi, d.Wi, d.Ci = x.N, T, H, W, dim
-        d.To, d.Ho, d.Wo, d.Co = To, Ho, Wo, dim
+        d.dtype = x.dt
+        d.N, d.Ti, d.Hi, d.Wi, d.Ci = x.N, T, H, W, dim_all
+        d.To, d.Ho, d.Wo, d.Co = To, Ho, Wo, dim_all
         d.kt, d.kh, d.kw = k
         d.st, d.sh, d.sw = s
         d.pt, d.ph, d.pw = p
         d.dt, d.dh, d.dw = dl
-        d.groups, d.act, d.has_residual = dim, L.ACT_NONE, 0
+        d.groups, d.act, d.has_residual = dim_all, L.ACT_NONE, 0
 
         def fn(stream):
             d.x_row_stride, d.y_row_stride = x.row_stride, y.row_stride
@@ -754,12 +824,12 @@ def emit_token_pool(plan, x, thw, pool, norm, heads, has_cls, name="pool"):
             L.check(lib.pv_dwconv3d_fwd(C_.byref(d), x.ptr() + cls * x.row_stride * esz, w_d.data_ptr(),
                                         ones.data_ptr(), zeros.data_ptr(), y.ptr() + cls * y.row_stride * esz, None,
                                         stream), "pv_dwconv3d_fwd(%s)" % name)
-        plan.add(name + ".dwconv", fn, "depthwise", 2.0 * x.N * To * Ho * Wo * dim * k[0] * k[1] * k[2],
-                 (x.N * T * H * W + x.N * To * Ho * Wo) * dim * esz)
+        plan.add(name + ".dwconv", fn, "depthwise", 2.0 * x.N * To * Ho * Wo * dim_all * k[0] * k[1] * k[2],
+                 (x.N * T * H * W + x.N * To * Ho * Wo) * dim_all * esz)
     else:
         d = L.Pool3dDesc()
-        d.dtype, d.mode = plan.dt, L.POOL_MAX
-        d.N, d.Ti, d.Hi, d.Wi, d.C = x.N, T, H, W, dim
+        d.dtype, d.mode = x.dt, L.POOL_MAX
+        d.N, d.Ti, d.Hi, d.Wi, d.C = x.N, T, H, W, dim_all
         d.To, d.Ho, d.Wo = To, Ho, Wo
         d.kt, d.kh, d.kw = k
         d.st, d.sh, d.sw = s
@@ -770,25 +840,34 @@ def emit_token_pool(plan, x, thw, pool, norm, heads, has_cls, name="pool"):
             d.x_batch_stride, d.y_batch_stride = x.npos * x.row_stride, y.npos * y.row_stride
             L.check(lib.pv_pool3d_fwd(C_.byref(d), x.ptr() + cls * x.row_stride * esz,
                                       y.ptr() + cls * y.row_stride * esz, stream), "pv_pool3d_fwd(%s)" % name)
-        plan.add(name + ".maxpool", fn, "other", 0.0, (x.N * T * H * W + x.N * To * Ho * Wo) * dim * esz)
-    if cls:
-        def fn_cls(stream):
-            L.check(lib.pv_copy_rows(x.ptr(), y.ptr(), x.dt, x.N, dim, x.npos * x.row_stride, y.npos * y.row_stride,
-                                     stream), "pv_copy_rows(%s)" % name)
-        plan.add(name + ".cls", fn_cls)
-    if norm is not None and type(norm).__name__ != "Identity":
-        if type(norm).__name__ != "LayerNorm":
-            raise NotImplementedError("%s: pool norm %s unsupported" % (name, type(norm).__name__))
-        hd = int(norm.normalized_shape[0])
-        assert dim % hd == 0
-        g = plan.const(norm.weight.detach().float().cpu())
-        b = plan.const(norm.bias.detach().float().cpu())
-        eps = float(norm.eps)
+        plan.add(name + ".maxpool", fn, "other", 0.0, (x.N * T * H * W + x.N * To * Ho * Wo) * dim_all * esz)
+    have_norm = [n is not None and type(n).__name__ != "Identity" for n in norms]
+    if any(have_norm) and not all(have_norm):
+        raise NotImplementedError("%s: fused pooling branches need a norm on every branch" % name)
+    if not all(have_norm):
+        if cls:
+            def fn_cls(stream):
+                L.check(lib.pv_copy_rows(x.ptr(), y.ptr(), x.dt, x.N, dim_all, x.npos * x.row_stride, y.npos * y.row_stride,
+                                         stream), "pv_copy_rows(%s)" % name)
+            plan.add(name + ".cls", fn_cls)
+        return y, (To, Ho, Wo)
+    for n in norms:
+        if type(n).__name__ != "LayerNorm":
+            raise NotImplementedError("%s: pool norm %s unsupported" % (name, type(n).__name__))
+    hd = int(norms[0].normalized_shape[0])
+    eps = float(norms[0].eps)
+    for n in norms[1:]:
+        assert int(n.normalized_shape[0]) == hd and float(n.eps) == eps
+    assert dim % hd == 0
+    g = plan.const(torch.cat([n.weight.detach().float().cpu() for n in norms]))
+    b = plan.const(torch.cat([n.bias.detach().float().cpu() for n in norms]))
 
-        def fn_ln(stream):
-            L.check(lib.pv_layernorm(y.ptr(), y.ptr(), y.dt, y.N * y.npos, dim // hd, hd, y.row_stride, y.row_stride,
-                                     g.data_ptr(), b.data_ptr(), eps, stream), "pv_layernorm(%s)" % name)
-        plan.add(name + ".norm", fn_ln)
+    def fn_ln(stream):
+        # in place on the pooled rows; the cls row of every sample (row % npos == 0) is read from x: no copy launch
+        L.check(lib.pv_layernorm_sets(y.ptr(), y.ptr(), y.dt, y.N * y.npos, dim_all // hd, hd, y.row_stride, y.row_stride,
+                                      g.data_ptr(), b.data_ptr(), dim // hd, x.ptr() if cls else None,
+                                      x.npos * x.row_stride, y.npos, eps, stream), "pv_layernorm_sets(%s)" % name)
+    plan.add(name + ".norm", fn_ln, "other", 0.0, 2 * y.N * y.npos * dim_all * esz)
     return y, (To, Ho, Wo)
 
 

@@ -92,6 +92,25 @@ def layernorm(x, gamma, beta, eps=1e-6, dtype="f16"):
     return y.float()
 
 
+def add_layernorm(a, b, gamma, beta, eps=1e-6):
+    """fp32-trunk residual add + LayerNorm: a [rows, C] (f16 or f32 CUDA tensor, used as is), b [rows, C] f16 or None.
+    Returns (a + b as f32, LayerNorm(a + b) as f16)."""
+    _require_cuda(a)
+    lib = L.load()
+    a = a.contiguous()
+    assert a.dtype in (torch.float16, torch.float32)
+    bb = None if b is None else b.half().contiguous()
+    rows, Cc = a.shape
+    s = torch.empty((rows, Cc), dtype=torch.float32, device=a.device)
+    y = torch.empty((rows, Cc), dtype=torch.float16, device=a.device)
+    g, be = gamma.float().contiguous().to(a.device), beta.float().contiguous().to(a.device)
+    L.check(lib.pv_add_layernorm(a.data_ptr(), _DT["f16" if a.dtype == torch.float16 else "f32"], Cc,
+                                 None if bb is None else bb.data_ptr(), Cc, s.data_ptr(), Cc, y.data_ptr(), Cc, rows, Cc,
+                                 g.data_ptr(), be.data_ptr(), float(eps), _stream(a.device)), "pv_add_layernorm")
+    torch.cuda.synchronize(a.device)
+    return s, y
+
+
 def attention(q, k, v, scale, add_q_residual=False, dtype="f16"):
     """q: [B,H,Nq,D], k/v: [B,H,Nk,D] CUDA tensors -> [B,H,Nq,D] (f32)."""
     _require_cuda(q, k, v)
