@@ -287,6 +287,7 @@ def main():
     ap.add_argument("--workload", default="slowfast_r50", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f16", choices=["f16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident-only", action="store_true", help="A/B runs: time the resident step only and print a short line")
     ap.add_argument("--dump-kernels", default=None, help="write per-launch times (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -306,7 +307,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.require_device()
+    numa = None
     if world > 1:
+        numa = PAR.bind_to_gpu_numa(local_rank)      # before any pinned allocation (first touch on the GPU's socket)
         PAR.init_process_group("nccl")
 
     model, B, T, H, W, is_sf = build_model_and_inputs(args.workload)
@@ -387,6 +390,14 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
+    if args.resident_only:
+        if rank == 0:
+            print(json.dumps({"workload": args.workload, "ms_per_step": ms_per_step, "value": value, "n_gpus": world,
+                              "launches_per_step": cm.plan.num_launches(), "resident_only": True,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("PVB200_")}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(2):
         step_e2e_serial()
     ms_e2e_serial = timed(step_e2e_serial, args.steps)
@@ -479,7 +490,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16" if args.precision == "f16" else "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "clip": [3, T, H, W], "batch_per_gpu": B, "global_batch": B * world,
-                           "parallelism": "dp%d" % world, "l2": "inputs (%.0f MB/step) larger than L2; CUDA-graph replay" % (h2d / 1e6),
+                           "parallelism": "dp%d" % world, "numa_bound": numa is not None, "l2": "inputs (%.0f MB/step) larger than L2; CUDA-graph replay" % (h2d / 1e6),
                            "weights": "random (seeded), BN stats randomised"},
                 "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "mode": "double-buffered H2D/compute/D2H (engine/pipeline.py)",

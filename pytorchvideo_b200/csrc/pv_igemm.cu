@@ -543,6 +543,8 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
       const double cost = waves * tile_cycles(c) + 1e-3 * cdiv(d->Co, c);
       if (cost < best) { best = cost; bn = c; }
     }
+    // PVB200_BN=64|128|256: A/B override of the tile width (tools/epi_sweep.py); read per launch on purpose
+    { const char* e = getenv("PVB200_BN"); const int v = e ? atoi(e) : 0; if ((v == 64 || v == 128 || v == 256) && v < co16) bn = v; }
     P.block_n = bn;
     P.n_tiles = (int)cdiv(d->Co, bn);
   }
