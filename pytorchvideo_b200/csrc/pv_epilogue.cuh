@@ -28,6 +28,7 @@ struct EpiParams {
   CUtensorMap y_map;    // output  [Co, d1, d2, d3, d4], box [64, b1, b2, b3, b4], SWIZZLE_128B
   CUtensorMap r_map;    // residual, same geometry
   int block_n, Co, rows, act, has_residual;
+  int ring2;   // wide tiles without a residual: two staging buffers, the store of a group drains while the next is computed
   int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip stores, 2 = skip epilogue math, 4 = producers skip loads,
              // 32 = MMA warp skips the MMAs, 64 = flip the direct / TMA-staged epilogue choice (see epi_direct)
   // direct (register -> global) epilogue for BLOCK_N <= 64: row r of a tile decodes into box coordinates
@@ -372,19 +373,27 @@ __device__ __forceinline__ void epi_prefetch_residual(const EpiParams& E, uint32
 //   store of q - 1 has been READ, i.e. all bulk groups but the newest: cp.async.bulk.wait_group.read 1),
 // so a residual load has a whole group period (accumulator wait + tcgen05.ld + math of group q + 1) to land and a
 // store drains while the next group is computed.  group_at(q) maps the running group counter to its coordinates.
-template <typename GroupAt>
+//
+// RES = false (wide tiles WITHOUT a residual: projection shortcuts, every MViT linear): the same loop over a ring of
+// EPI_RING_NORES = 2 buffers - the bulk store of group q drains while group q + 1 is computed (the single-buffer
+// epilogue_tile waits for the store's shared-memory read before it may stage the next group: tools/epi_sweep.py measures
+// store-only 35 us + math-only 35-39 us = 50 us for a 64 -> 256 pointwise layer).  Buffer (q + 1) % 2 is free once the
+// store of group q - 1 has been read: the same wait_group.read 1 after the store of group q is issued.
+constexpr int EPI_RING_NORES = 2;
+template <bool RES, typename GroupAt>
 __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const float* __restrict__ scale,
                                                    const float* __restrict__ bias, uint32_t t_acc, uint32_t epi_smem,
                                                    uint8_t* epi_gen, uint32_t res_bar, uint32_t (&res_phase)[EPI_RING],
                                                    int& q, int ewarp, int quarter, int lane, int n_tile0,
                                                    uint32_t tempty_bar, GroupAt group_at) {
+  constexpr int R = RES ? EPI_RING : EPI_RING_NORES;
   const int row = quarter * 32 + lane;
   const int chalf = ewarp >> 2;
   const int etid = ewarp * 32 + lane;
   const bool leader = (etid == 0);
   const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
   const uint32_t rsw = (uint32_t)(row & 7);
-  float* sb = reinterpret_cast<float*>(epi_gen + EPI_RING * EPI_STAGING_BYTES);     // scale/bias live after the ring
+  float* sb = reinterpret_cast<float*>(epi_gen + R * EPI_STAGING_BYTES);     // scale/bias live after the ring
   for (int i = etid; i < E.block_n; i += EPI_THREADS) {
     const int c = n_tile0 + i;
     const bool ok = c < E.Co;
@@ -392,25 +401,27 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
     sb[256 + i] = ok ? __ldg(bias + c) : 0.f;
   }
   for (int g0 = 0; g0 < E.block_n; g0 += EPI_GROUP_COLS, ++q) {
-    const int buf = q % EPI_RING;
+    const int buf = q % R;
     const EpiGroup G = group_at(q);
     const int nsub = (G.ncols + 63) >> 6;
     const uint32_t slot = (uint32_t)buf * EPI_STAGING_BYTES;
-    epi_bar_sync(1, EPI_THREADS);                       // scale/bias visible; previous group fully staged
-    mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested two groups ago)
-    res_phase[buf] ^= 1u;
-    if (chalf < nsub) {
+    epi_bar_sync(1, EPI_THREADS);                       // scale/bias visible; previous group fully staged; buffer free (leader waited)
+    if (RES) {
+      mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested two groups ago)
+      res_phase[buf] ^= 1u;
+    }
+    if (chalf < nsub && !(E.dbg & 2)) {
       const int cbase = g0 + chalf * 64;
       const int ncols = min(64, G.ncols - chalf * 64);
       uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
       const float* sc = sb + cbase;
       const float* bi = sb + 256 + cbase;
       switch (E.act) {
-        case PV_ACT_RELU: epi_subtile<PV_ACT_RELU, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
-        case PV_ACT_NONE: epi_subtile<PV_ACT_NONE, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
-        case PV_ACT_SWISH: epi_subtile<PV_ACT_SWISH, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
-        case PV_ACT_GELU: epi_subtile<PV_ACT_GELU, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
-        default: epi_subtile<PV_ACT_SIGMOID, true>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_RELU: epi_subtile<PV_ACT_RELU, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_NONE: epi_subtile<PV_ACT_NONE, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_SWISH: epi_subtile<PV_ACT_SWISH, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        case PV_ACT_GELU: epi_subtile<PV_ACT_GELU, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
+        default: epi_subtile<PV_ACT_SIGMOID, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
       }
     }
     if (g0 + EPI_GROUP_COLS >= E.block_n) {             // accumulator fully read: hand TMEM back to the MMA warp
@@ -421,13 +432,19 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
     fence_proxy_async_smem();
     epi_bar_sync(1, EPI_THREADS);
     if (leader) {
-      for (int s = 0; s < nsub; ++s)
-        tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, G.n0 + s * 64, G.c1, G.c2, G.c3, G.c4);
+      if (!(E.dbg & 1)) {
+        for (int s = 0; s < nsub; ++s)
+          tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, G.n0 + s * 64, G.c1, G.c2, G.c3, G.c4);
+      }
       tma_store_commit();
-      const EpiGroup N2 = group_at(q + 2);              // its buffer was last used by group q - 1
-      if (N2.valid) {
-        tma_store_wait_read1();                         // every store but the one just issued has read its buffer
-        epi_prefetch_residual(E, epi_smem, res_bar, (q + 2) % EPI_RING, N2);
+      if (RES) {
+        const EpiGroup N2 = group_at(q + 2);            // its buffer was last used by group q - 1
+        if (N2.valid) {
+          tma_store_wait_read1();                       // every store but the one just issued has read its buffer
+          epi_prefetch_residual(E, epi_smem, res_bar, (q + 2) % EPI_RING, N2);
+        }
+      } else {
+        tma_store_wait_read1();                         // the store of group q - 1 has read buffer (q + 1) % 2
       }
     }
   }
@@ -435,6 +452,10 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
 
 __host__ __device__ inline bool epi_wide_prefetch(const EpiParams& E) {
   return !epi_narrow(E.block_n) && E.has_residual && !(E.dbg & 512);     // PVB200_DEBUG=512: fall back to the single-buffer epilogue
+}
+// wide tiles without a residual: two staging buffers (E.ring2, decided per launch on the host)
+__host__ __device__ inline bool epi_wide_ring2(const EpiParams& E) {
+  return !epi_narrow(E.block_n) && !E.has_residual && E.ring2 != 0;
 }
 
 }  // namespace sm100

@@ -279,3 +279,35 @@ def test_detection_state_dict_and_repr_follow_the_reference():
     s = PH.slow_r50_detection()
     assert s.state_dict()["detection_head.proj.weight"].shape == (80, 2048)
     assert type(s.detection_head.pool).__name__ == "AvgPool3d" and tuple(s.detection_head.pool.kernel_size) == (4, 1, 1)
+
+
+def test_mvit_fp32_trunk_and_fused_pooling_plan():
+    """f16 engine, MViT-B: the residual stream is fp32 (every residual add is a pv_add_layernorm launch fused with the
+    LayerNorm that follows - norm2 / next block's norm1 / norm_embed), pooled K and V share one depthwise + one
+    LayerNorm launch, no cls copy launches except on the norm-less skip path; f32 parity mode keeps the plain lowering."""
+    from pytorchvideo_b200 import _lib as L
+    m = PH.mvit_base_16x4(spatial_size=112, temporal_size=8).eval()
+    x = torch.zeros(2, 3, 8, 112, 112)
+    plan = lower_only(m, x)[0]
+    names = [mm["name"] for mm in plan.meta]
+    assert plan.trunk32 and len(names) == 165
+    assert names.count("blocks.0.norm1") == 1 and not any(n.endswith(".norm1") for n in names if not n.startswith("blocks.0."))
+    assert sum(n.endswith(".norm2") for n in names) == 16 and sum(n.endswith(".add") for n in names) == 16
+    assert sum(n.endswith(".pool_kv.dwconv") for n in names) == 16 and not any(".pool_k." in n or ".pool_v." in n for n in names)
+    assert [n for n in names if n.endswith(".cls")] == ["blocks.%d.pool_skip.cls" % i for i in (1, 3, 14)]
+    assert "norm_embed" not in names                       # fused into blocks.15.add
+    # the trunk tensors are f32 buffers, everything a GEMM reads is f16
+    dts = {b.dt for b in plan.bufs}
+    assert dts == {L.PV_F16, L.PV_F32}
+    plan32 = lower_only(m, x, dtype="f32")[0]
+    n32 = [mm["name"] for mm in plan32.meta]
+    assert not plan32.trunk32 and "norm_embed" in n32 and not any(n.endswith(".add") for n in n32)
+
+
+def test_numa_helpers_are_safe_without_sysfs(tmp_path):
+    from pytorchvideo_b200 import parallel as PAR
+    assert PAR._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert PAR._parse_cpulist("") == set()
+    # no GPU / no sysfs entry: a silent no-op, never an exception (bench.py calls it on every multi-rank run)
+    assert PAR.gpu_numa_cpus(0, sysfs=str(tmp_path)) == (None, None)
+    assert PAR.bind_to_gpu_numa(0) is None
