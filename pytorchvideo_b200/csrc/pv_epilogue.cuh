@@ -123,6 +123,46 @@ __device__ __forceinline__ void epi_subtile(uint32_t t_addr, uint8_t* srow, uint
   }
 }
 
+// Same for a full 64-column sub-tile with both x32 TMEM loads in flight before the first use (one wait instead of two).
+template <int ACT, bool RES>
+__device__ __forceinline__ void epi_subtile64(uint32_t t_addr, uint8_t* srow, uint32_t rsw, const float* sc, const float* bi) {
+  uint32_t v[64];
+  tmem_ld32(t_addr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  tmem_ld32(t_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  tmem_ld_wait();
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    const int cc = h * 8;
+    uint4* cell = reinterpret_cast<uint4*>(srow + ((((uint32_t)cc >> 3) ^ rsw) << 4));
+    const float4 s0 = *reinterpret_cast<const float4*>(sc + cc), s1 = *reinterpret_cast<const float4*>(sc + cc + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bi + cc), b1 = *reinterpret_cast<const float4*>(bi + cc + 4);
+    float f[8];
+    f[0] = fmaf(__uint_as_float(v[h * 8 + 0]), s0.x, b0.x);
+    f[1] = fmaf(__uint_as_float(v[h * 8 + 1]), s0.y, b0.y);
+    f[2] = fmaf(__uint_as_float(v[h * 8 + 2]), s0.z, b0.z);
+    f[3] = fmaf(__uint_as_float(v[h * 8 + 3]), s0.w, b0.w);
+    f[4] = fmaf(__uint_as_float(v[h * 8 + 4]), s1.x, b1.x);
+    f[5] = fmaf(__uint_as_float(v[h * 8 + 5]), s1.y, b1.y);
+    f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), s1.z, b1.z);
+    f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), s1.w, b1.w);
+    if (RES) {
+      const uint4 rv = *cell;
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 r2 = __half22float2(rh[q]);
+        f[2 * q] += r2.x;
+        f[2 * q + 1] += r2.y;
+      }
+    }
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(act_t<ACT>(f[2 * q]), act_t<ACT>(f[2 * q + 1]));
+    *cell = ov;
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_subtile_res(bool res, uint32_t t_addr, uint8_t* srow, uint32_t rsw,
                                                 const float* sc, const float* bi, int ncols) {
@@ -416,6 +456,10 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
       uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
       const float* sc = sb + cbase;
       const float* bi = sb + 256 + cbase;
+      const bool ld64 = (E.dbg & 4096) && ncols == 64;      // A/B switch: both TMEM loads of the sub-tile in flight
+      if (ld64 && E.act == PV_ACT_RELU) epi_subtile64<PV_ACT_RELU, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi);
+      else if (ld64 && E.act == PV_ACT_NONE) epi_subtile64<PV_ACT_NONE, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi);
+      else
       switch (E.act) {
         case PV_ACT_RELU: epi_subtile<PV_ACT_RELU, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
         case PV_ACT_NONE: epi_subtile<PV_ACT_NONE, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;

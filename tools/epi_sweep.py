@@ -39,7 +39,8 @@ VARIANTS = [("base", {}), ("bn128", {"PVB200_BN": "128"}), ("bn64", {"PVB200_BN"
             ("epi_only", {"PVB200_DEBUG": "36"}), ("epi_only_no_store", {"PVB200_DEBUG": "37"}),
             ("no_mma", {"PVB200_DEBUG": "32"}), ("single_buf", {"PVB200_DEBUG": "512"}),
             ("ring2", {"PVB200_EPI_RING2": "1"}), ("ring2_no_store", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "1"}),
-            ("ring2_no_math", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "2"})]
+            ("ring2_no_math", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "2"}),
+            ("ring2_ld64", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "4096"})]
 if os.environ.get("SWEEP_VARIANTS"):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ["SWEEP_VARIANTS"].split(",")]
 REP = 10
