@@ -28,7 +28,6 @@ struct EpiParams {
   CUtensorMap y_map;    // output  [Co, d1, d2, d3, d4], box [64, b1, b2, b3, b4], SWIZZLE_128B
   CUtensorMap r_map;    // residual, same geometry
   int block_n, Co, rows, act, has_residual;
-  int ring2;   // wide tiles without a residual: two staging buffers, the store of a group drains while the next is computed
   int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip stores, 2 = skip epilogue math, 4 = producers skip loads,
              // 32 = MMA warp skips the MMAs, 64 = flip the direct / TMA-staged epilogue choice (see epi_direct)
   // direct (register -> global) epilogue for BLOCK_N <= 64: row r of a tile decodes into box coordinates
@@ -120,46 +119,6 @@ __device__ __forceinline__ void epi_subtile(uint32_t t_addr, uint8_t* srow, uint
       for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(act_t<ACT>(f[2 * q]), act_t<ACT>(f[2 * q + 1]));
       *cell = ov;
     }
-  }
-}
-
-// Same for a full 64-column sub-tile with both x32 TMEM loads in flight before the first use (one wait instead of two).
-template <int ACT, bool RES>
-__device__ __forceinline__ void epi_subtile64(uint32_t t_addr, uint8_t* srow, uint32_t rsw, const float* sc, const float* bi) {
-  uint32_t v[64];
-  tmem_ld32(t_addr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-  tmem_ld32(t_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-  tmem_ld_wait();
-#pragma unroll
-  for (int h = 0; h < 8; ++h) {
-    const int cc = h * 8;
-    uint4* cell = reinterpret_cast<uint4*>(srow + ((((uint32_t)cc >> 3) ^ rsw) << 4));
-    const float4 s0 = *reinterpret_cast<const float4*>(sc + cc), s1 = *reinterpret_cast<const float4*>(sc + cc + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(bi + cc), b1 = *reinterpret_cast<const float4*>(bi + cc + 4);
-    float f[8];
-    f[0] = fmaf(__uint_as_float(v[h * 8 + 0]), s0.x, b0.x);
-    f[1] = fmaf(__uint_as_float(v[h * 8 + 1]), s0.y, b0.y);
-    f[2] = fmaf(__uint_as_float(v[h * 8 + 2]), s0.z, b0.z);
-    f[3] = fmaf(__uint_as_float(v[h * 8 + 3]), s0.w, b0.w);
-    f[4] = fmaf(__uint_as_float(v[h * 8 + 4]), s1.x, b1.x);
-    f[5] = fmaf(__uint_as_float(v[h * 8 + 5]), s1.y, b1.y);
-    f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), s1.z, b1.z);
-    f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), s1.w, b1.w);
-    if (RES) {
-      const uint4 rv = *cell;
-      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 r2 = __half22float2(rh[q]);
-        f[2 * q] += r2.x;
-        f[2 * q + 1] += r2.y;
-      }
-    }
-    uint4 ov;
-    __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(act_t<ACT>(f[2 * q]), act_t<ACT>(f[2 * q + 1]));
-    *cell = ov;
   }
 }
 
@@ -413,20 +372,14 @@ __device__ __forceinline__ void epi_prefetch_residual(const EpiParams& E, uint32
 //   store of q - 1 has been READ, i.e. all bulk groups but the newest: cp.async.bulk.wait_group.read 1),
 // so a residual load has a whole group period (accumulator wait + tcgen05.ld + math of group q + 1) to land and a
 // store drains while the next group is computed.  group_at(q) maps the running group counter to its coordinates.
-//
-// RES = false (wide tiles WITHOUT a residual: projection shortcuts, every MViT linear): the same loop over a ring of
-// EPI_RING_NORES = 2 buffers - the bulk store of group q drains while group q + 1 is computed (the single-buffer
-// epilogue_tile waits for the store's shared-memory read before it may stage the next group: tools/epi_sweep.py measures
-// store-only 35 us + math-only 35-39 us = 50 us for a 64 -> 256 pointwise layer).  Buffer (q + 1) % 2 is free once the
-// store of group q - 1 has been read: the same wait_group.read 1 after the store of group q is issued.
-constexpr int EPI_RING_NORES = 2;
-template <bool RES, typename GroupAt>
+template <typename GroupAt>
 __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const float* __restrict__ scale,
                                                    const float* __restrict__ bias, uint32_t t_acc, uint32_t epi_smem,
                                                    uint8_t* epi_gen, uint32_t res_bar, uint32_t (&res_phase)[EPI_RING],
                                                    int& q, int ewarp, int quarter, int lane, int n_tile0,
                                                    uint32_t tempty_bar, GroupAt group_at) {
-  constexpr int R = RES ? EPI_RING : EPI_RING_NORES;
+  constexpr int R = EPI_RING;
+  constexpr bool RES = true;
   const int row = quarter * 32 + lane;
   const int chalf = ewarp >> 2;
   const int etid = ewarp * 32 + lane;
@@ -446,20 +399,14 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
     const int nsub = (G.ncols + 63) >> 6;
     const uint32_t slot = (uint32_t)buf * EPI_STAGING_BYTES;
     epi_bar_sync(1, EPI_THREADS);                       // scale/bias visible; previous group fully staged; buffer free (leader waited)
-    if (RES) {
-      mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested two groups ago)
-      res_phase[buf] ^= 1u;
-    }
+    mbar_wait(res_bar + 8u * (uint32_t)buf, res_phase[buf]);   // residual of THIS group (requested two groups ago)
+    res_phase[buf] ^= 1u;
     if (chalf < nsub && !(E.dbg & 2)) {
       const int cbase = g0 + chalf * 64;
       const int ncols = min(64, G.ncols - chalf * 64);
       uint8_t* srow = epi_gen + slot + chalf * 16384 + row * 128;
       const float* sc = sb + cbase;
       const float* bi = sb + 256 + cbase;
-      const bool ld64 = (E.dbg & 4096) && ncols == 64;      // A/B switch: both TMEM loads of the sub-tile in flight
-      if (ld64 && E.act == PV_ACT_RELU) epi_subtile64<PV_ACT_RELU, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi);
-      else if (ld64 && E.act == PV_ACT_NONE) epi_subtile64<PV_ACT_NONE, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi);
-      else
       switch (E.act) {
         case PV_ACT_RELU: epi_subtile<PV_ACT_RELU, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
         case PV_ACT_NONE: epi_subtile<PV_ACT_NONE, RES>(t_row + (uint32_t)cbase, srow, rsw, sc, bi, ncols); break;
@@ -481,14 +428,10 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
           tma_store_5d(&E.y_map, epi_smem + slot + (uint32_t)s * 16384u, G.n0 + s * 64, G.c1, G.c2, G.c3, G.c4);
       }
       tma_store_commit();
-      if (RES) {
-        const EpiGroup N2 = group_at(q + 2);            // its buffer was last used by group q - 1
-        if (N2.valid) {
-          tma_store_wait_read1();                       // every store but the one just issued has read its buffer
-          epi_prefetch_residual(E, epi_smem, res_bar, (q + 2) % EPI_RING, N2);
-        }
-      } else {
-        tma_store_wait_read1();                         // the store of group q - 1 has read buffer (q + 1) % 2
+      const EpiGroup N2 = group_at(q + 2);              // its buffer was last used by group q - 1
+      if (N2.valid) {
+        tma_store_wait_read1();                         // every store but the one just issued has read its buffer
+        epi_prefetch_residual(E, epi_smem, res_bar, (q + 2) % EPI_RING, N2);
       }
     }
   }
@@ -496,10 +439,6 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
 
 __host__ __device__ inline bool epi_wide_prefetch(const EpiParams& E) {
   return !epi_narrow(E.block_n) && E.has_residual && !(E.dbg & 512);     // PVB200_DEBUG=512: fall back to the single-buffer epilogue
-}
-// wide tiles without a residual: two staging buffers (E.ring2, decided per launch on the host)
-__host__ __device__ inline bool epi_wide_ring2(const EpiParams& E) {
-  return !epi_narrow(E.block_n) && !E.has_residual && E.ring2 != 0;
 }
 
 }  // namespace sm100

@@ -283,7 +283,6 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     auto tempty_addr = [&](int a) { return pair ? mapa_shared(tempty_bar(a), 0) : tempty_bar(a); };
     // wide residual tiles: ring of staging buffers, residual loads two groups ahead (epilogue_tile_ring)
     const bool wide_prefetch = epi_wide_prefetch(P.epi);
-    const bool wide_ring2 = epi_wide_ring2(P.epi);
     uint32_t res_phase3[EPI_RING];
 #pragma unroll
     for (int s = 0; s < EPI_RING; ++s) res_phase3[s] = 0u;
@@ -320,13 +319,8 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (wide_ring2) {
-        epilogue_tile_ring<false>(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
-                                  res_bar, res_phase3, q, ewarp, quarter, lane, n_tile * P.block_n, tempty_addr(acc), group_at);
-        continue;
-      }
       if (wide_prefetch) {
-        epilogue_tile_ring<true>(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
+        epilogue_tile_ring(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                            res_bar, res_phase3, q, ewarp, quarter, lane, n_tile * P.block_n, tempty_addr(acc), group_at);
         continue;
       }
@@ -579,11 +573,6 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
   { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
-  // wide tiles without a residual: double-buffered staging (epilogue_tile_ring<false>); PVB200_EPI_RING2=0|1, read per launch
-  {
-    const char* e = getenv("PVB200_EPI_RING2");
-    P.epi.ring2 = ((e ? atoi(e) != 0 : false) && !P.pair && !epi_narrow(P.block_n) && !d->has_residual) ? 1 : 0;
-  }
   {
     P.acc_stride = (P.block_n + 31) / 32 * 32;
     P.nacc = 512 / P.acc_stride;
@@ -603,8 +592,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
     if (G > 4) G = 4;
     if (G > num_kb) G = num_kb;
     { const char* e = getenv("PVB200_G"); if (e && atoi(e) >= 1 && atoi(e) <= 8) G = atoi(e) < num_kb ? atoi(e) : num_kb; }
-    P.epi_bytes = EPI_SMEM_BYTES + (epi_wide_prefetch(P.epi) ? (EPI_RING - 1) * EPI_STAGING_BYTES : 0) +
-                  (epi_wide_ring2(P.epi) ? (EPI_RING_NORES - 1) * EPI_STAGING_BYTES : 0);
+    P.epi_bytes = EPI_SMEM_BYTES + (epi_wide_prefetch(P.epi) ? (EPI_RING - 1) * EPI_STAGING_BYTES : 0);
     {
       static const bool no_alias = getenv("PVB200_NO_ALIAS") != nullptr;
       const long long units = P.pair ? 2ll * P.pair_tiles : (long long)P.m_tiles * P.n_tiles;

@@ -2,8 +2,7 @@
 REP identical launches (no host launch latency in the number).  One process: PVB200_DEBUG / PVB200_BN are read per launch.
    python tools/epi_sweep.py [layer-substring ...]
 PVB200_DEBUG bits: 1 skip stores, 2 skip epilogue math, 4 producers skip loads, 32 MMA warp skips the MMAs,
-512 single-buffer residual epilogue.  PVB200_BN = tile width override, PVB200_EPI_RING2 = double-buffered staging for wide
-tiles without a residual."""
+512 single-buffer residual epilogue.  PVB200_BN = tile width override."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -37,10 +36,7 @@ LAYERS += [
 VARIANTS = [("base", {}), ("bn128", {"PVB200_BN": "128"}), ("bn64", {"PVB200_BN": "64"}),
             ("no_store", {"PVB200_DEBUG": "1"}), ("no_math", {"PVB200_DEBUG": "2"}),
             ("epi_only", {"PVB200_DEBUG": "36"}), ("epi_only_no_store", {"PVB200_DEBUG": "37"}),
-            ("no_mma", {"PVB200_DEBUG": "32"}), ("single_buf", {"PVB200_DEBUG": "512"}),
-            ("ring2", {"PVB200_EPI_RING2": "1"}), ("ring2_no_store", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "1"}),
-            ("ring2_no_math", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "2"}),
-            ("ring2_ld64", {"PVB200_EPI_RING2": "1", "PVB200_DEBUG": "4096"})]
+            ("no_mma", {"PVB200_DEBUG": "32"}), ("single_buf", {"PVB200_DEBUG": "512"})]
 if os.environ.get("SWEEP_VARIANTS"):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ["SWEEP_VARIANTS"].split(",")]
 REP = 10
@@ -78,7 +74,7 @@ def main():
                 continue
             if vname == "single_buf" and not use_res:
                 continue
-            for kk in ("PVB200_DEBUG", "PVB200_BN", "PVB200_EPI_RING2"):
+            for kk in ("PVB200_DEBUG", "PVB200_BN"):
                 os.environ.pop(kk, None)
             os.environ.update(env)
             side = torch.cuda.Stream()
@@ -100,7 +96,7 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / REP)
             out[vname] = round(best * 1e3, 2)
-        for kk in ("PVB200_DEBUG", "PVB200_BN", "PVB200_EPI_RING2"):
+        for kk in ("PVB200_DEBUG", "PVB200_BN"):
             os.environ.pop(kk, None)
         print(json.dumps(out), flush=True)
         rows.append(out)
