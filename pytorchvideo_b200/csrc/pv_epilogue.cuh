@@ -28,6 +28,7 @@ struct EpiParams {
   CUtensorMap y_map;    // output  [Co, d1, d2, d3, d4], box [64, b1, b2, b3, b4], SWIZZLE_128B
   CUtensorMap r_map;    // residual, same geometry
   int block_n, Co, rows, act, has_residual;
+  int teams;   // wide residual tiles: 1 = eight warps on one tile, 2 = two teams of four warps on alternate tiles (epilogue_tile_ring_teams)
   int dbg;   // debug bit mask (PVB200_DEBUG env): 1 = skip stores, 2 = skip epilogue math, 4 = producers skip loads,
              // 32 = MMA warp skips the MMAs, 64 = flip the direct / TMA-staged epilogue choice (see epi_direct)
   // direct (register -> global) epilogue for BLOCK_N <= 64: row r of a tile decodes into box coordinates
@@ -435,6 +436,91 @@ __device__ __forceinline__ void epilogue_tile_ring(const EpiParams& E, const flo
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two epilogue teams for wide residual tiles.  tools/epi_sweep.py (profiles/r02_epilogue_sweep.md): a conv_c + residual layer is a
+// latency chain per staging group - residual landed -> TMEM -> registers -> staging -> proxy fence -> barrier -> bulk store -> wait
+// for the previous store's read -> next residual request - and with eight warps on ONE tile only one such chain is in flight per SM.
+// TMEM holds two accumulators (BLOCK_N <= 256), so here the eight warps split into two teams of four (each team owns all four TMEM
+// lane quarters) that drain ALTERNATE tiles concurrently: a group is one 64-column sub-tile (16 KiB), each team has its own ring of
+// EPI_RING 16-KiB buffers (together the same 96 KiB as the single ring), its own scale / bias copy, residual barriers, named barrier
+// and issuing thread (bulk-group queues are per thread).  Same shape as the narrow-tile path of epilogue_tile, plus the residual ring.
+//   team_q      : running group counter of this TEAM (buffer = team_q % EPI_RING)
+//   group_at(q) : the team's q-th group -> (tile coordinates, first column, columns); groups per tile = ceil(BLOCK_N / 64)
+// ---------------------------------------------------------------------------------------------
+constexpr int EPI_TEAM_BUF_BYTES = 16384;                          // one [128 rows x 64 ch] swizzled sub-tile
+constexpr int EPI_TEAM_RING_BYTES = EPI_RING * EPI_TEAM_BUF_BYTES;
+
+__device__ __forceinline__ void epi_team_prefetch_residual(const EpiParams& E, uint32_t team_smem, uint32_t team_res_bar, int buf,
+                                                           const EpiGroup& G) {
+  const uint32_t bar = team_res_bar + 8u * (uint32_t)buf;
+  mbar_arrive_expect_tx(bar, (uint32_t)(E.rows * 128));
+  tma_load_5d(team_smem + (uint32_t)buf * EPI_TEAM_BUF_BYTES, &E.r_map, bar, G.n0, G.c1, G.c2, G.c3, G.c4);
+}
+
+template <typename GroupAt>
+__device__ __forceinline__ void epilogue_tile_ring_teams(const EpiParams& E, const float* __restrict__ scale,
+                                                         const float* __restrict__ bias, uint32_t t_acc, uint32_t epi_smem,
+                                                         uint8_t* epi_gen, uint32_t res_bar, uint32_t (&res_phase)[EPI_RING],
+                                                         int& team_q, int ewarp, int quarter, int lane, int n_tile0,
+                                                         uint32_t tempty_bar, GroupAt group_at) {
+  const int team = ewarp >> 2;
+  const int row = quarter * 32 + lane;
+  const int etid = (ewarp & 3) * 32 + lane;             // 0..127 inside the team
+  const bool leader = (etid == 0);
+  const int bar_id = 1 + team;
+  const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t rsw = (uint32_t)(row & 7);
+  const uint32_t team_smem = epi_smem + (uint32_t)team * EPI_TEAM_RING_BYTES;
+  uint8_t* team_gen = epi_gen + team * EPI_TEAM_RING_BYTES;
+  const uint32_t team_res_bar = res_bar + 8u * (uint32_t)(team * EPI_RING);
+  float* sb = reinterpret_cast<float*>(epi_gen + 2 * EPI_TEAM_RING_BYTES) + team * 512;   // scale / bias live after both rings
+  for (int i = etid; i < E.block_n; i += 128) {
+    const int c = n_tile0 + i;
+    const bool ok = c < E.Co;
+    sb[i] = ok ? __ldg(scale + c) : 0.f;
+    sb[256 + i] = ok ? __ldg(bias + c) : 0.f;
+  }
+  for (int g0 = 0; g0 < E.block_n; g0 += 64, ++team_q) {
+    const int buf = team_q % EPI_RING;
+    const EpiGroup G = group_at(team_q);
+    epi_bar_sync(bar_id, 128);                          // scale/bias visible; previous group of this team fully staged
+    mbar_wait(team_res_bar + 8u * (uint32_t)buf, res_phase[buf]);      // residual of THIS group (requested two groups ago)
+    res_phase[buf] ^= 1u;
+    if (!(E.dbg & 2)) {
+      uint8_t* srow = team_gen + buf * EPI_TEAM_BUF_BYTES + row * 128;
+      const float* sc = sb + g0;
+      const float* bi = sb + 256 + g0;
+      switch (E.act) {
+        case PV_ACT_RELU: epi_subtile<PV_ACT_RELU, true>(t_row + (uint32_t)g0, srow, rsw, sc, bi, G.ncols); break;
+        case PV_ACT_NONE: epi_subtile<PV_ACT_NONE, true>(t_row + (uint32_t)g0, srow, rsw, sc, bi, G.ncols); break;
+        case PV_ACT_SWISH: epi_subtile<PV_ACT_SWISH, true>(t_row + (uint32_t)g0, srow, rsw, sc, bi, G.ncols); break;
+        case PV_ACT_GELU: epi_subtile<PV_ACT_GELU, true>(t_row + (uint32_t)g0, srow, rsw, sc, bi, G.ncols); break;
+        default: epi_subtile<PV_ACT_SIGMOID, true>(t_row + (uint32_t)g0, srow, rsw, sc, bi, G.ncols); break;
+      }
+    }
+    if (g0 + 64 >= E.block_n) {                         // accumulator fully read: hand TMEM back to the MMA warp (4 arrivals)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar);
+    }
+    fence_proxy_async_smem();
+    epi_bar_sync(bar_id, 128);
+    if (leader) {
+      if (!(E.dbg & 1)) tma_store_5d(&E.y_map, team_smem + (uint32_t)buf * EPI_TEAM_BUF_BYTES, G.n0, G.c1, G.c2, G.c3, G.c4);
+      tma_store_commit();
+      const EpiGroup N2 = group_at(team_q + 2);         // its buffer was last used by group team_q - 1
+      if (N2.valid) {
+        tma_store_wait_read1();                         // every store of this thread but the newest has read its buffer
+        epi_team_prefetch_residual(E, team_smem, team_res_bar, (team_q + 2) % EPI_RING, N2);
+      }
+    }
+  }
+}
+
+__host__ __device__ inline bool epi_wide_teams(const EpiParams& E) {
+  return !epi_narrow(E.block_n) && E.has_residual && E.teams == 2 && !(E.dbg & 512);
 }
 
 __host__ __device__ inline bool epi_wide_prefetch(const EpiParams& E) {

@@ -95,7 +95,7 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
   const int nacc = P.nacc;                   // accumulator stages in TMEM (2..8)
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + nacc + s); };
   const uint32_t res_bar = bar_base + 8u * (2 * stages + 2 * nacc);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 2 * nacc + EPI_RING);     // res_bar: one barrier per ring buffer
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 2 * nacc + 2 * EPI_RING);     // res_bar: one barrier per ring buffer (and team)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,9 +112,9 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     for (int s = 0; s < nacc; ++s) {
       mbar_init(tfull_bar(s), 1);
       // one arrive per epilogue warp of the tile's group (pair mode: from both CTAs, on the leader's barrier)
-      mbar_init(tempty_bar(s), (epi_narrow(P.block_n) ? 4 : EPI_WARPS) * (pair ? 2 : 1));
+      mbar_init(tempty_bar(s), ((epi_narrow(P.block_n) || epi_wide_teams(P.epi)) ? 4 : EPI_WARPS) * (pair ? 2 : 1));
     }
-    for (int s = 0; s < EPI_RING; ++s) mbar_init(res_bar + 8u * s, 1);
+    for (int s = 0; s < 2 * EPI_RING; ++s) mbar_init(res_bar + 8u * s, 1);
     prefetch_tmap(&P.epi.y_map);
     fence_mbar_init();
   }
@@ -164,7 +164,9 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
     // thread sustains only ~one bulk-tensor load per 330-520 clk (tools/probe/tma_rate.cu), four warps one per ~130.
     // Warp 0 alone arrives on the full barrier with the expected bytes of the WHOLE chunk; the other warps' loads may
     // complete before that arrive (the transaction count goes negative, the phase cannot complete without the arrive).
-    const int nsplit = pair ? 1 : P.split_ab;
+    // (the load-skipping probe completes the full barrier from warp 0 alone: the other producer warps must not run, or they can fall
+    //  whole laps behind and wait for a phase that never comes once the tiles are exhausted)
+    const int nsplit = (pair || (P.epi.dbg & 4)) ? 1 : P.split_ab;
     if (warp < nsplit) {
       int stage = 0;
       uint32_t phase = 0;
@@ -300,14 +302,37 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       G.c1 = oc[0]; G.c2 = oc[1]; G.c3 = oc[2]; G.c4 = oc[3];
       return G;
     };
-    if (wide_prefetch && ewarp == 0 && lane == 0) {
+    const bool wide_teams = epi_wide_teams(P.epi);
+    const int team = ewarp >> 2;
+    const int gpt_team = (P.block_n + 63) >> 6;                             // 64-column groups per tile (team mode)
+    auto team_group_at = [&](int qq) {                                      // the team's qq-th group: tile 2 * (qq / gpt) + team of this CTA
+      EpiGroup G;
+      const int ts = qq / gpt_team, gi = qq - ts * gpt_team;
+      const int unit = unit0 + (2 * ts + team) * unit_step;
+      G.valid = unit < total_tiles ? 1 : 0;
+      int nt = 0, oc[4] = {0, 0, 0, 0};
+      if (G.valid) tile_coords(unit, nt, oc);
+      G.n0 = nt * P.block_n + gi * 64;
+      G.ncols = min(64, P.block_n - gi * 64);
+      G.c1 = oc[0]; G.c2 = oc[1]; G.c3 = oc[2]; G.c4 = oc[3];
+      return G;
+    };
+    if (wide_teams && (ewarp & 3) == 0 && lane == 0) {                     // each team leader: residuals of its first two groups
+      for (int qq = 0; qq < 2; ++qq) {
+        const EpiGroup G0 = team_group_at(qq);
+        if (G0.valid)
+          epi_team_prefetch_residual(P.epi, staging + (uint32_t)team * EPI_TEAM_RING_BYTES, res_bar + 8u * (uint32_t)(team * EPI_RING),
+                                     qq % EPI_RING, G0);
+      }
+    }
+    if (!wide_teams && wide_prefetch && ewarp == 0 && lane == 0) {
       for (int qq = 0; qq < 2; ++qq) {
         const EpiGroup G0 = group_at(qq);
         if (G0.valid) epi_prefetch_residual(P.epi, staging, res_bar, qq % EPI_RING, G0);
       }
     }
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tile_seq) {
-      if (narrow && (tile_seq & 1) != (ewarp >> 2)) continue;     // the other group's tile
+      if ((narrow || wide_teams) && (tile_seq & 1) != (ewarp >> 2)) continue;     // the other group's / team's tile
       const int acc = tile_seq % nacc;
       const uint32_t acc_phase = (uint32_t)((tile_seq / nacc) & 1);
       int n_tile, o[4];
@@ -319,6 +344,11 @@ conv3d_igemm_kernel(const __grid_constant__ IgemmParams P, const float* __restri
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (wide_teams) {
+        epilogue_tile_ring_teams(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
+                                 res_bar, res_phase3, q, ewarp, quarter, lane, n_tile * P.block_n, tempty_addr(acc), team_group_at);
+        continue;
+      }
       if (wide_prefetch) {
         epilogue_tile_ring(P.epi, scale, bias, tmem_base + (uint32_t)(acc * P.acc_stride), staging, smem_gen + staging_off,
                            res_bar, res_phase3, q, ewarp, quarter, lane, n_tile * P.block_n, tempty_addr(acc), group_at);
@@ -573,6 +603,16 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   P.epi.act = d->act;
   P.epi.has_residual = d->has_residual;
   { const char* e = getenv("PVB200_DEBUG"); P.epi.dbg = e ? atoi(e) : 0; }
+  // wide residual tiles: two epilogue teams on alternate tiles (needs two accumulators in TMEM); PVB200_EPI_TEAMS=1|2, read per launch
+  {
+    // Measured (profiles/r02_epilogue_sweep.md, one box): res2 conv_c 69.8 -> 62.1 us; SlowFast 3.070 -> 3.014 ms, CSN-R101 5.37 -> 5.19 ms,
+    // R(2+1)D 3.166 -> 3.070 ms, Slow-R50 1.913 -> 1.866 ms; X3D-M (96 / 192-wide tiles) 7.03 -> 7.14 ms - hence full-width tiles only,
+    // and only when some CTA runs at least two tiles (a single tile has nothing to overlap with and would be drained by four warps).
+    const char* e = getenv("PVB200_EPI_TEAMS");
+    const int want = e ? atoi(e) : 2;
+    P.epi.teams = (want == 2 && !P.pair && d->has_residual && P.block_n == 256 &&
+                   (long long)P.m_tiles * P.n_tiles > sm_count) ? 2 : 1;
+  }
   {
     P.acc_stride = (P.block_n + 31) / 32 * 32;
     P.nacc = 512 / P.acc_stride;
@@ -618,7 +658,7 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   const int stage_bytes = P.G * kb_bytes;
   if (P.alias_epi && (long long)P.stages * stage_bytes < P.epi_bytes) P.alias_epi = 0;     // ring smaller than the staging area
   const size_t smem_bytes = (size_t)P.stages * stage_bytes + 2048 /*align*/ + (P.alias_epi ? 0 : P.epi_bytes) +
-                            8 * (2 * P.stages + 2 * 8 + 4) + 16;
+                            8 * (2 * P.stages + 2 * 8 + 2 * EPI_RING + 1) + 16;
 
   // ---- taps -> (parity map, coordinate shift); original dims order: tap index = (kt, kh, kw)
   // merged dims never merge a dim that has taps, so each non-trivial original dim maps to one

@@ -2,7 +2,8 @@
 REP identical launches (no host launch latency in the number).  One process: PVB200_DEBUG / PVB200_BN are read per launch.
    python tools/epi_sweep.py [layer-substring ...]
 PVB200_DEBUG bits: 1 skip stores, 2 skip epilogue math, 4 producers skip loads, 32 MMA warp skips the MMAs,
-512 single-buffer residual epilogue.  PVB200_BN = tile width override."""
+512 single-buffer residual epilogue.  PVB200_BN = tile width override, PVB200_EPI_TEAMS = 1: one epilogue team (eight warps on one
+tile) instead of two teams on alternate tiles for full-width residual tiles."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -36,7 +37,9 @@ LAYERS += [
 VARIANTS = [("base", {}), ("bn128", {"PVB200_BN": "128"}), ("bn64", {"PVB200_BN": "64"}),
             ("no_store", {"PVB200_DEBUG": "1"}), ("no_math", {"PVB200_DEBUG": "2"}),
             ("epi_only", {"PVB200_DEBUG": "36"}), ("epi_only_no_store", {"PVB200_DEBUG": "37"}),
-            ("no_mma", {"PVB200_DEBUG": "32"}), ("single_buf", {"PVB200_DEBUG": "512"})]
+            ("no_mma", {"PVB200_DEBUG": "32"}), ("single_buf", {"PVB200_DEBUG": "512"}),
+            ("one_team", {"PVB200_EPI_TEAMS": "1"}), ("one_team_no_store", {"PVB200_EPI_TEAMS": "1", "PVB200_DEBUG": "1"}),
+            ("one_team_no_math", {"PVB200_EPI_TEAMS": "1", "PVB200_DEBUG": "2"})]
 if os.environ.get("SWEEP_VARIANTS"):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ["SWEEP_VARIANTS"].split(",")]
 REP = 10
@@ -72,9 +75,9 @@ def main():
         for vname, env in VARIANTS:
             if "PVB200_BN" in env and int(env["PVB200_BN"]) >= co:
                 continue
-            if vname == "single_buf" and not use_res:
+            if (vname == "single_buf" or vname.startswith("one_team")) and not use_res:
                 continue
-            for kk in ("PVB200_DEBUG", "PVB200_BN"):
+            for kk in ("PVB200_DEBUG", "PVB200_BN", "PVB200_EPI_TEAMS"):
                 os.environ.pop(kk, None)
             os.environ.update(env)
             side = torch.cuda.Stream()
@@ -96,7 +99,7 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / REP)
             out[vname] = round(best * 1e3, 2)
-        for kk in ("PVB200_DEBUG", "PVB200_BN"):
+        for kk in ("PVB200_DEBUG", "PVB200_BN", "PVB200_EPI_TEAMS"):
             os.environ.pop(kk, None)
         print(json.dumps(out), flush=True)
         rows.append(out)

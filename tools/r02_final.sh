@@ -12,8 +12,10 @@ for w in slowfast_r50 mvit_base_16x4 x3d_m; do
 done
 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 300 -c 260 --csv \
     --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_launches.log 2>&1
-timeout 300 ncu --set full --clock-control none -k regex:"add_layernorm|layernorm_reg" -s 6 -c 4 -o gpurun_out/r02_prof_ln \
+timeout 300 ncu --set full --clock-control none -k regex:"add_layernorm|layernorm_reg" -s 6 -c 2 -o gpurun_out/r02_prof_ln \
     python bench.py --workload mvit_base_16x4 --steps 1 --warmup 3 --resident-only > gpurun_out/r02_prof_ln.log 2>&1
 ncu -i gpurun_out/r02_prof_ln.ncu-rep --page raw --csv > gpurun_out/r02_prof_ln.raw.csv 2>/dev/null
 [ -f gpurun_out/r02_prof_ln.ncu-rep ] && [ $(stat -c %s gpurun_out/r02_prof_ln.ncu-rep) -gt 8000000 ] && rm -f gpurun_out/r02_prof_ln.ncu-rep
+SWEEP_VARIANTS=base,one_team,one_team_no_store,one_team_no_math,epi_only timeout 200 python tools/epi_sweep.py _res > gpurun_out/r02_epi_sweep_teams.jsonl 2> gpurun_out/r02_epi_sweep_teams.err
+cat gpurun_out/r02_epi_sweep_teams.jsonl; tail -n 2 gpurun_out/r02_epi_sweep_teams.err
 ls -la gpurun_out | head -30
