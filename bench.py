@@ -473,6 +473,17 @@ def main():
                 "algorithmic_mb_per_launch": kd["bytes"] / kd["n"] / 1e6,
                 "peak_source": peaks["source"],
                 "timing": "share of per-launch CUDA-event time (eager replay) x measured graph step time"}
+    # Two more views of the same kernel, beside the primary one: (1) its launches judged as an HBM stream (many of them are:
+    # conv_c + residual moves 231 MB for 6.6 GFLOP); (2) every launch against ITS OWN binding roofline,
+    # sum_i max(flops_i / tensor peak, bytes_i / HBM peak) / time in the step - the fraction of the per-launch speed of light.
+    dom_ops = [(m, t) for m, t in zip(cm.plan.meta, per_op) if m["kind"] == dom]
+    ideal_ms = sum(max(m["flops"] / (peaks["tflops_sustained"] * 1e12), m["bytes"] / (peaks["hbm_gbs"] * 1e9)) for m, _ in dom_ops) * 1e3
+    roof["hbm_view"] = {"achieved": kd["bytes"] / (in_step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": kd["bytes"] / (in_step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "algorithmic_mb_per_launch": kd["bytes"] / kd["n"] / 1e6}
+    roof["per_launch_roofline_frac"] = ideal_ms / in_step_ms
+    roof["launches_hbm_bound"] = sum(1 for m, _ in dom_ops
+                                     if m["bytes"] / (peaks["hbm_gbs"] * 1e9) > m["flops"] / (peaks["tflops_sustained"] * 1e12))
     model_flops = sum(m["flops"] for m in cm.plan.meta)
     whole = {"model_gflop_per_clip": model_flops / B / 1e9,
              "model_tflops_achieved": model_flops / (ms_per_step * 1e-3) / 1e12,
