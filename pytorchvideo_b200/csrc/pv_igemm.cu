@@ -606,12 +606,14 @@ int conv3d_tcgen05_launch(const pv_conv3d_desc* d, const void* x, const void* w,
   // wide residual tiles: two epilogue teams on alternate tiles (needs two accumulators in TMEM); PVB200_EPI_TEAMS=1|2, read per launch
   {
     // Measured (profiles/r02_epilogue_sweep.md, one box): res2 conv_c 69.8 -> 62.1 us; SlowFast 3.070 -> 3.014 ms, CSN-R101 5.37 -> 5.19 ms,
-    // R(2+1)D 3.166 -> 3.070 ms, Slow-R50 1.913 -> 1.866 ms; X3D-M (96 / 192-wide tiles) 7.03 -> 7.14 ms - hence full-width tiles only,
-    // and only when some CTA runs at least two tiles (a single tile has nothing to overlap with and would be drained by four warps).
+    // R(2+1)D 3.166 -> 3.070 ms, Slow-R50 1.913 -> 1.866 ms; X3D-M (96 / 192-wide tiles) 7.03 -> 7.14 ms - hence full-width tiles only.
+    // Per layer (same file, run 4): 10.6 tiles per CTA (res2 conv_c) 69.5 -> 61.6 us, 5.3 tiles (res3) 45.2 -> 45.3 us, 2.6 tiles (res4)
+    // 23.4 -> 25.4 us, 1.4 tiles (res5) 19.0 -> 19.5 us: a tile drained by four warps instead of eight only pays when each team has several
+    // tiles to pipeline - hence at least four tiles per CTA.
     const char* e = getenv("PVB200_EPI_TEAMS");
     const int want = e ? atoi(e) : 2;
     P.epi.teams = (want == 2 && !P.pair && d->has_residual && P.block_n == 256 &&
-                   (long long)P.m_tiles * P.n_tiles > sm_count) ? 2 : 1;
+                   (long long)P.m_tiles * P.n_tiles >= 4ll * sm_count) ? 2 : 1;
   }
   {
     P.acc_stride = (P.block_n + 31) / 32 * 32;
