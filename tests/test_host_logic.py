@@ -311,3 +311,31 @@ def test_numa_helpers_are_safe_without_sysfs(tmp_path):
     # no GPU / no sysfs entry: a silent no-op, never an exception (bench.py calls it on every multi-rank run)
     assert PAR.gpu_numa_cpus(0, sysfs=str(tmp_path)) == (None, None)
     assert PAR.bind_to_gpu_numa(0) is None
+
+
+@pytest.mark.parametrize("variant", ["default", "no_cls", "no_sep_pos", "pool_max", "separate_qkv", "dim_mul_in_att",
+                                     "residual_pool_off", "no_kv_pool"])
+def test_mvit_variants_lower_on_the_host(variant):
+    """create_multiscale_vision_transformers options (models/vision_transformers.py:185-437) all reach a plan in both
+    precision modes: fused K|V pooling where the two branches are depthwise convs with LayerNorms, separate launches
+    otherwise; the fp32 trunk only in the f16 engine."""
+    from pytorchvideo_b200.models.vision_transformers import create_multiscale_vision_transformers as mk
+    base = dict(spatial_size=64, temporal_size=4, depth=4, embed_dim_mul=[[1, 2.0], [3, 2.0]], atten_head_mul=[[1, 2.0], [3, 2.0]],
+                pool_q_stride_size=[[1, 1, 2, 2], [3, 1, 2, 2]], pool_kv_stride_adaptive=[1, 4, 4], pool_kvq_kernel=[3, 3, 3])
+    kw = {"default": {}, "no_cls": {"cls_embed_on": False}, "no_sep_pos": {"sep_pos_embed": False},
+          "pool_max": {"pool_kv_stride_adaptive": None, "pool_kv_stride_size": [[0, 1, 2, 2]], "pooling_mode": "max"},
+          "separate_qkv": {"separate_qkv": True}, "dim_mul_in_att": {"dim_mul_in_att": True},
+          "residual_pool_off": {"residual_pool": False},
+          "no_kv_pool": {"pool_kv_stride_adaptive": None, "pool_q_stride_size": None}}[variant]
+    m = mk(**{**base, **kw}).eval()
+    x = torch.zeros(1, 3, 4, 64, 64)
+    for dt in ("f16", "f32"):
+        plan, shp = lower_only(m, x, dtype=dt)
+        assert shp == (1, 400)
+        names = [mm["name"] for mm in plan.meta]
+        assert plan.trunk32 == (dt == "f16")
+        assert sum(n.endswith(".attn.core") for n in names) == 4
+        if variant in ("default", "separate_qkv"):
+            assert sum(n.endswith(".pool_kv.dwconv") for n in names) == 4 and not any(".pool_k." in n for n in names)
+        if variant == "no_kv_pool":
+            assert not any(".pool_" in n and ".attn." in n for n in names)
