@@ -222,8 +222,11 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "clip": [3, T, H, W], "batch_per_step": b,
-                       "note": "reference CPU forward restated in oracle/interp.py (bit-exact vs the reference in the authoring container)"},
+            # the b200 arm's workload; each reference step is a bounded SAMPLE of it (batch_per_step clips of the batch)
+            "config": {"workload": args.workload, "clip": [3, T, H, W], "batch_per_gpu": B, "global_batch": B * max(1, args.gpus),
+                       "parallelism": "dp%d" % max(1, args.gpus), "batch_per_step": b,
+                       "note": "reference CPU forward restated in oracle/interp.py (bit-exact vs the reference in the authoring container); "
+                               "each step = %d clip of the %d-clip batch on the host cores" % (b, B)},
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
                              "sample": "%d clip per step x %d steps" % (b, args.steps)},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
